@@ -1,0 +1,201 @@
+/*
+ * ttv_b200.h -- C-ABI of the B200-native mode-q tensor-times-vector product  C = A x_q b.
+ *
+ * This is the drop-in boundary.  The reference (bassoy/ttv) has no FFI layer; its operator API is the
+ * C-like template function
+ *
+ *     tlib::ttv::ttv(ep, sp, fp, q, p, a, na, wa, pia, b, nb, c, nc, wc, pic)      reference include/tlib/ttv.h:54-92
+ *
+ * and everything else (tensor-level ttv ttv.h:99-114, operator* ttv.h:122-127, ttvpy.ttv wrapped_ttv.cpp:18-78)
+ * forwards to it.  Each ttv_b200_<type>() below replaces one instantiation of that template: same thirteen
+ * arguments in the same order and with the same meaning (1-based modes, element strides, layout tuples),
+ * plain pointers and sizes only.  `include/tlib/ttv.h` in this repo is the header-style C++17 host API on top
+ * of these symbols; `ttv_b200/ttvpy.py` is the Python binding on top of the same symbols.
+ *
+ * Semantics
+ *   - a, b, c may be HOST or DEVICE pointers (classified with cudaPointerGetAttributes).  Device pointers are
+ *     used in place.  Host pointers are staged: H2D of A and b, kernel, D2H of C, all inside the call.
+ *   - C is OVERWRITTEN (C = A x_q b), which is what every caller of the reference observes because all of them
+ *     zero C first (tensor.h:70, wrapped_ttv.cpp:67, gtest_tlib_ttv.cpp:125) and what the BLAS build always does
+ *     (beta = 0, matrix_times_vector.h:213-215).  TTV_B200_FLAG_ACCUMULATE selects C += A x_q b, the behaviour of
+ *     the reference's non-BLAS column kernel (matrix_times_vector.h:124).
+ *   - Argument checks, their order and their messages follow ttv.h:64-89 and tensor_times_vector.h:147-168.
+ *   - The call is synchronous unless TTV_B200_FLAG_ASYNC is set together with device pointers.
+ *   - There is no CPU fallback: without a usable CUDA device every compute entry returns TTV_B200_ERR_CUDA.
+ *     ttv_b200_plan() is pure host code and needs no device.
+ */
+#ifndef TTV_B200_H
+#define TTV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TTV_B200_VERSION 100
+
+/* element types ----------------------------------------------------------------------------------------- */
+enum ttv_b200_dtype {
+  TTV_B200_F32  = 0,  /* float                                     */
+  TTV_B200_F64  = 1,  /* double                                    */
+  TTV_B200_C64  = 2,  /* std::complex<float>   (re, im) pairs      */
+  TTV_B200_C128 = 3,  /* std::complex<double>  (re, im) pairs      */
+  TTV_B200_I32  = 4,  /* int32_t, wrap-around arithmetic           */
+  TTV_B200_I64  = 5,  /* int64_t, wrap-around arithmetic           */
+  TTV_B200_DTYPE_COUNT = 6
+};
+
+/* status codes; 1..20 are the reference's throw sites in the order they are evaluated --------------------- */
+enum ttv_b200_status {
+  TTV_B200_OK = 0,
+  TTV_B200_ERR_ORDER_ZERO      = 1,   /* ttv.h:64  */
+  TTV_B200_ERR_MODE            = 2,   /* ttv.h:65  */
+  TTV_B200_ERR_A_NULL          = 3,   /* ttv.h:66  */
+  TTV_B200_ERR_B_NULL          = 4,   /* ttv.h:67  */
+  TTV_B200_ERR_C_NULL          = 5,   /* ttv.h:68  */
+  TTV_B200_ERR_NA_NULL         = 6,   /* ttv.h:70  */
+  TTV_B200_ERR_NB_NULL         = 7,   /* ttv.h:71  */
+  TTV_B200_ERR_NC_NULL         = 8,   /* ttv.h:72  */
+  TTV_B200_ERR_WA_NULL         = 9,   /* ttv.h:74  */
+  TTV_B200_ERR_WC_NULL         = 10,  /* ttv.h:75  */
+  TTV_B200_ERR_PIA_NULL        = 11,  /* ttv.h:77  */
+  TTV_B200_ERR_PIC_NULL        = 12,  /* ttv.h:78  */
+  TTV_B200_ERR_EXTENT_MISMATCH = 13,  /* ttv.h:80  */
+  TTV_B200_ERR_SHAPE_A         = 14,  /* ttv.h:82  */
+  TTV_B200_ERR_SHAPE_C         = 15,  /* ttv.h:83  */
+  TTV_B200_ERR_LAYOUT_A        = 16,  /* ttv.h:85  */
+  TTV_B200_ERR_LAYOUT_C        = 17,  /* ttv.h:86  */
+  TTV_B200_ERR_STRIDES_A       = 18,  /* ttv.h:88  */
+  TTV_B200_ERR_STRIDES_C       = 19,  /* ttv.h:89  */
+  TTV_B200_ERR_LAYOUT_BEGIN    = 20,  /* tensor_times_vector.h:160 */
+  TTV_B200_ERR_LAYOUT_END      = 21,  /* tensor_times_vector.h:164 */
+  /* not in the reference: conditions it leaves undefined or cannot meet */
+  TTV_B200_ERR_NOT_PACKED      = 30,  /* wa/wc/nc are not the packed strides/shape of (na, pia, q); the reference
+                                         asserts or silently assumes this (tensor_times_vector.h:956, mtv ignores wa) */
+  TTV_B200_ERR_DTYPE           = 31,
+  TTV_B200_ERR_OPTS            = 32,
+  TTV_B200_ERR_CUDA            = 40,  /* no device, launch or runtime failure; text in ttv_b200_last_error() */
+  TTV_B200_ERR_MIXED_POINTERS  = 41   /* a, b, c must be all host or all device */
+};
+
+/* policy hints: mirror the reference's tag types (include/tlib/detail/tags.h:21-63).  All of them select the
+ * same GPU path; they are accepted so that call sites keep compiling and recorded in the plan. */
+enum ttv_b200_execution { TTV_B200_EXEC_SEQ = 0, TTV_B200_EXEC_SEQ_BLAS, TTV_B200_EXEC_PAR, TTV_B200_EXEC_PAR_LOOP,
+                          TTV_B200_EXEC_PAR_TASKLOOP, TTV_B200_EXEC_PAR_TASK, TTV_B200_EXEC_PAR_BLAS,
+                          TTV_B200_EXEC_PAR_BLAS_LOOP };
+enum ttv_b200_slicing   { TTV_B200_SLICE = 0, TTV_B200_SUBTENSOR = 1 };
+enum ttv_b200_fusion    { TTV_B200_FUSE_NONE = 0, TTV_B200_FUSE_OUTER = 1, TTV_B200_FUSE_ALL = 2 };
+
+/* kernel families.  0 lets the chooser decide; the others force a family (used by the tests to
+ * run every kernel on every shape it supports). */
+enum ttv_b200_kernel {
+  TTV_B200_KERNEL_AUTO   = 0,
+  TTV_B200_KERNEL_DOT    = 1,  /* mode q contiguous (inner == 1): cooperating lanes per fiber, shuffle reduction   */
+  TTV_B200_KERNEL_COL    = 2,  /* column GEMV: thread owns contiguous outputs, streams A along inner                */
+  TTV_B200_KERNEL_STREAM = 3,  /* small inner / small n_q: slab staged through shared memory with bulk copies       */
+  TTV_B200_KERNEL_COUNT  = 4
+};
+
+enum ttv_b200_flags {
+  TTV_B200_FLAG_ACCUMULATE = 1,   /* C += A x_q b                                                        */
+  TTV_B200_FLAG_ASYNC      = 2,   /* device pointers only: return after enqueueing on opts->stream       */
+  TTV_B200_FLAG_NO_VEC     = 4    /* testing: force scalar loads                                          */
+};
+
+typedef struct ttv_b200_opts {
+  int32_t  device;      /* CUDA device ordinal, -1 = current device                                          */
+  int32_t  execution;   /* enum ttv_b200_execution (hint)                                                    */
+  int32_t  slicing;     /* enum ttv_b200_slicing   (hint)                                                    */
+  int32_t  fusion;      /* enum ttv_b200_fusion    (hint)                                                    */
+  int32_t  kernel;      /* enum ttv_b200_kernel, 0 = auto                                                    */
+  int32_t  ksplit;      /* number of n_q partitions, 0 = auto, 1 = never split                               */
+  uint32_t flags;       /* enum ttv_b200_flags                                                               */
+  int32_t  reserved;
+  void*    stream;      /* cudaStream_t; NULL = the legacy default stream                                    */
+} ttv_b200_opts;
+
+/* what the layout folder and the kernel chooser decided for one call -------------------------------------- */
+typedef struct ttv_b200_plan_t {
+  uint64_t outer;       /* product of the extents after  q in layout order                                   */
+  uint64_t nq;          /* contraction extent na[q-1]                                                        */
+  uint64_t inner;       /* product of the extents before q in layout order ( == wa[q-1] )                    */
+  uint32_t k;           /* 1-based position of q in pia  ( pia^-1(q) )                                       */
+  uint32_t ref_case;    /* the reference's case 1..8 (include/tlib/detail/cases.h:24-36)                     */
+  int32_t  kernel;      /* enum ttv_b200_kernel chosen                                                       */
+  int32_t  vec;         /* elements per vector load                                                          */
+  int32_t  tx, ty;      /* thread tile: tx threads along inner, ty along n_q                                  */
+  int32_t  ksplit;      /* n_q partitions (second pass reduces them when > 1)                                */
+  int32_t  threads;     /* threads per CTA                                                                   */
+  uint64_t ctas;        /* grid size                                                                         */
+  uint64_t smem_bytes;  /* dynamic shared memory per CTA                                                     */
+  uint64_t algo_bytes;  /* sizeof(T) * (N + n_q + N/n_q): read A once, read b once, write C once             */
+  uint64_t algo_flops;  /* 2*N (real) or 8*N (complex)                                                       */
+  uint64_t workspace_bytes;
+} ttv_b200_plan_t;
+
+/* generic entry; the typed entries below forward to it */
+int ttv_b200_run(int dtype, uint64_t q, uint64_t p,
+                 const void* a, const uint64_t* na, const uint64_t* wa, const uint64_t* pia,
+                 const void* b, const uint64_t* nb,
+                 void* c, const uint64_t* nc, const uint64_t* wc, const uint64_t* pic,
+                 const ttv_b200_opts* opts);
+
+/* one entry per element type: replaces tlib::ttv::ttv<value_t,size_t,...>  (ttv.h:54-92) */
+int ttv_b200_f32 (uint64_t q, uint64_t p, const float*   a, const uint64_t* na, const uint64_t* wa, const uint64_t* pia,
+                  const float*   b, const uint64_t* nb, float*   c, const uint64_t* nc, const uint64_t* wc,
+                  const uint64_t* pic, const ttv_b200_opts* opts);
+int ttv_b200_f64 (uint64_t q, uint64_t p, const double*  a, const uint64_t* na, const uint64_t* wa, const uint64_t* pia,
+                  const double*  b, const uint64_t* nb, double*  c, const uint64_t* nc, const uint64_t* wc,
+                  const uint64_t* pic, const ttv_b200_opts* opts);
+int ttv_b200_c64 (uint64_t q, uint64_t p, const void*    a, const uint64_t* na, const uint64_t* wa, const uint64_t* pia,
+                  const void*    b, const uint64_t* nb, void*    c, const uint64_t* nc, const uint64_t* wc,
+                  const uint64_t* pic, const ttv_b200_opts* opts);
+int ttv_b200_c128(uint64_t q, uint64_t p, const void*    a, const uint64_t* na, const uint64_t* wa, const uint64_t* pia,
+                  const void*    b, const uint64_t* nb, void*    c, const uint64_t* nc, const uint64_t* wc,
+                  const uint64_t* pic, const ttv_b200_opts* opts);
+int ttv_b200_i32 (uint64_t q, uint64_t p, const int32_t* a, const uint64_t* na, const uint64_t* wa, const uint64_t* pia,
+                  const int32_t* b, const uint64_t* nb, int32_t* c, const uint64_t* nc, const uint64_t* wc,
+                  const uint64_t* pic, const ttv_b200_opts* opts);
+int ttv_b200_i64 (uint64_t q, uint64_t p, const int64_t* a, const uint64_t* na, const uint64_t* wa, const uint64_t* pia,
+                  const int64_t* b, const uint64_t* nb, int64_t* c, const uint64_t* nc, const uint64_t* wc,
+                  const uint64_t* pic, const ttv_b200_opts* opts);
+
+/* Validation + layout folding + kernel choice without touching a device (pure host code).  Pointers a, b, c are
+ * only checked for null-ness; pass any non-null value.  Returns the same status codes as ttv_b200_run. */
+int ttv_b200_plan(int dtype, uint64_t q, uint64_t p,
+                  const void* a, const uint64_t* na, const uint64_t* wa, const uint64_t* pia,
+                  const void* b, const uint64_t* nb,
+                  const void* c, const uint64_t* nc, const uint64_t* wc, const uint64_t* pic,
+                  const ttv_b200_opts* opts, ttv_b200_plan_t* plan);
+
+/* The canonical view directly: C[outer][inner] (=|+=) sum_k A[outer][k][inner] * b[k], everything packed, DEVICE
+ * pointers only.  This is the shape every legal (na, pia, q) folds to; the sharded multi-GPU driver and the
+ * detail::gemv_* shims (reference matrix_times_vector.h:51-127) call it. */
+int ttv_b200_view(int dtype, uint64_t outer, uint64_t nq, uint64_t inner,
+                  const void* a, const void* b, void* c, const ttv_b200_opts* opts);
+int ttv_b200_plan_view(int dtype, uint64_t outer, uint64_t nq, uint64_t inner,
+                       const ttv_b200_opts* opts, ttv_b200_plan_t* plan);
+
+/* L0 helpers of the reference, restated (shape.h, layout.h, strides.h); pure host code ------------------- */
+int ttv_b200_is_valid_shape  (const uint64_t* n,  uint64_t p);                       /* shape.h:30-34    */
+int ttv_b200_is_valid_layout (const uint64_t* pi, uint64_t p);                       /* layout.h:29-55   */
+int ttv_b200_is_valid_strides(const uint64_t* pi, uint64_t p, const uint64_t* w);    /* strides.h:76-101 */
+int ttv_b200_compute_strides (const uint64_t* n,  const uint64_t* pi, uint64_t p, uint64_t* w);    /* strides.h:31-57  */
+int ttv_b200_output_shape    (const uint64_t* na, uint64_t p, uint64_t q, uint64_t* nc);           /* shape.h:103-123  */
+int ttv_b200_output_layout   (const uint64_t* pia, uint64_t p, uint64_t q, uint64_t* pic);         /* layout.h:143-172 */
+int ttv_b200_k_order_layout  (uint64_t p, uint64_t k, uint64_t* pi);                               /* layout.h:57-76   */
+
+/* diagnostics */
+const char* ttv_b200_strerror(int status);     /* the reference's message text for codes 1..21 */
+const char* ttv_b200_last_error(void);         /* thread-local; message of the last failing call on this thread */
+int         ttv_b200_version(void);
+int         ttv_b200_device_count(void);       /* 0 when no usable CUDA device */
+uint64_t    ttv_b200_launch_count(void);       /* kernels launched by this library in this process */
+int         ttv_b200_dtype_size(int dtype);
+void        ttv_b200_release(void);            /* frees cached workspaces / staging buffers */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTV_B200_H */
