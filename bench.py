@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""bench.py -- the TTV hot path on B200, measured against the HBM roofline, with the reference's CPU path beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          own arm (CUDA kernels through the C-ABI)
+    python bench.py --impl reference ...                         the reference's own CPU implementation (oracle/_ref)
+    torchrun --nproc-per-node N bench.py --gpus N ...            one rank per GPU (NCCL)
+
+Workload (BASELINE.json configs[1], symmetric sweep): an order-4 fp32 tensor with a 256^4 slab (16 GiB) PER GPU,
+first-order layout, and one STEP = the four products q = 1, 2, 3, 4 on it.  With N ranks the global tensor is
+(256, 256, 256, 256*N) sharded along its slowest mode (weak scaling): q = 1..3 are free-mode splits without
+communication, q = 4 contracts the split mode, so every rank reduces over its 256 rows and the partial C (64 MiB) is
+summed with one NCCL reduce.  N = 1 is exactly the named 256^4 case.
+
+metric = effective HBM GB/s = algorithmic bytes / time, algorithmic bytes per product = 4 * (N_el + n_q + N_el/n_q)
+(read A once, read b once, write C once).  Inputs (16 GiB) are far larger than L2 (126 MB), so no flush is
+needed between iterations.  `value` has the inputs resident in HBM; `e2e` is the same step through the public API
+with HOST (pinned) buffers, host<->device copies inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+EXT = 256                       # extent of every mode of the per-GPU slab
+ORDER = 4
+DTYPE = "f32"
+ELEM = 4
+SEED_A, SEED_B = 0x77170001, 0x77170002
+METRIC = "TTV effective HBM GB/s"
+
+
+def algo_bytes(na, q, elem=ELEM):
+    n = int(np.prod(na, dtype=object))
+    return elem * (n + na[q - 1] + n // na[q - 1])
+
+
+def workload_name(n):
+    return (f"cfg2 symmetric sweep: order-4 fp32 n=(256,256,256,{EXT * n}) first-order, one step = q=1..4; "
+            f"{'single GPU' if n == 1 else f'sharded along mode 4 over {n} GPUs (q=1..3 free split, q=4 n_q split + NCCL reduce)'}")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks during the timed region (NVML)
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int, period: float = 0.02):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self.index, self.period = index, period
+
+    def __enter__(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        except Exception:
+            self.nv = None
+        return self
+
+    def _run(self):
+        nv = self.nv
+        names = {getattr(nv, k): k for k in dir(nv) if k.startswith("nvmlClocksEventReason") or k.startswith("nvmlClocksThrottleReason")}
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((mhz, util))
+                for bit, name in names.items():
+                    if isinstance(bit, int) and bit and (mask & bit) == bit and bit & (bit - 1) == 0:
+                        self.reasons.add(name.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", ""))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=1)
+
+    def summary(self):
+        busy = [m for m, u in self.samples if u > 0] or [m for m, _ in self.samples]
+        reasons = sorted(r for r in self.reasons if r not in ("None", "GpuIdle", "ApplicationsClocksSetting"))
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's CPU implementation (oracle/_ref): cpu_baseline leg and --impl reference
+# ---------------------------------------------------------------------------------------------------------------------
+def load_reference():
+    from oracle.oracle import Oracle, Reference
+    helpers = Oracle()
+    for blas in (True, False):
+        try:
+            if Reference.available(blas=blas):
+                return Reference(blas=blas), helpers, "reference"
+        except OSError:
+            continue
+    return None, helpers, "port"
+
+
+def cpu_step(ref, helpers, kind, a, na, pia, bs, cs):
+    """one step (q = 1..4) on the host; returns seconds"""
+    t0 = time.perf_counter()
+    for q in range(1, ORDER + 1):
+        if kind == "reference":
+            ref.ttv(q, a, na, pia, bs[q - 1], combo=("par_loop", "subtensor", "all"), helpers=helpers, c0=cs[q - 1])
+        else:
+            cs[q - 1][:] = helpers.ttv(q, a, na, pia, bs[q - 1])
+    return time.perf_counter() - t0
+
+
+def cpu_measure(last_extent, steps, warmup, budget_s=None):
+    ref, helpers, kind = load_reference()
+    na = [EXT, EXT, EXT, last_extent]
+    pia = [1, 2, 3, 4]
+    n = int(np.prod(na))
+    a = np.empty(n, np.float32)
+    chunk = 1 << 24
+    pattern = helpers.fill(DTYPE, chunk, SEED_A)
+    for s in range(0, n, chunk):
+        a[s:s + chunk] = pattern[: min(chunk, n - s)]
+    bs = [helpers.fill(DTYPE, na[q - 1], SEED_B + q) for q in range(1, ORDER + 1)]
+    cs = [np.zeros(n // na[q - 1], np.float32) for q in range(1, ORDER + 1)]
+    for _ in range(warmup):
+        cpu_step(ref, helpers, kind, a, na, pia, bs, cs)
+    times = []
+    t_start = time.perf_counter()
+    for _ in range(steps):
+        for c in cs:
+            c.fill(0)                       # the non-BLAS column kernel accumulates (matrix_times_vector.h:124)
+        times.append(cpu_step(ref, helpers, kind, a, na, pia, bs, cs))
+        if budget_s is not None and time.perf_counter() - t_start > budget_s:
+            break
+    total_bytes = sum(algo_bytes(na, q) for q in range(1, ORDER + 1))
+    cores = ref.cores() if ref is not None else 1
+    blas = bool(ref is not None and ref.blas)
+    return {"seconds_per_step": statistics.mean(times), "steps_done": len(times), "bytes_per_step": total_bytes,
+            "gbs": total_bytes / statistics.mean(times) / 1e9, "kind": kind, "cores": cores, "blas": blas, "na": na}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # size the sample so that (steps + warmup) steps end within ~150 s: probe on a small slab first
+    probe = cpu_measure(8, 1, 1)
+    rate = probe["gbs"] * 1e9
+    want_s = 150.0 / max(1, args.steps + args.warmup)
+    last = EXT
+    try:
+        avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
+    except Exception:
+        avail = 32 << 30
+    while last > 8 and (4 * algo_bytes([EXT, EXT, EXT, last], 1) / rate > want_s or 4 * EXT ** 3 * last * 2.5 > avail):
+        last //= 2
+    m = cpu_measure(last, args.steps, args.warmup)
+    sample = (f"unmodified reference headers ({'OpenBLAS ' if m['blas'] else 'non-BLAS '}par_loop/subtensor/all, OpenMP), "
+              f"n=({EXT},{EXT},{EXT},{last}) fp32 {'= the full per-GPU tensor' if last == EXT else 'slab of the 256^4 tensor'}, q=1..4 per step")
+    line = {"impl": "reference", "metric": METRIC, "value": round(m["gbs"], 2), "unit": "GB/s", "n_gpus": args.gpus,
+            "steps": m["steps_done"], "warmup": args.warmup, "ms_per_step": round(m["seconds_per_step"] * 1e3, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+            "config": {"workload": workload_name(args.gpus), "timed_on": "host CPU cores"},
+            "cpu_baseline": {"value": round(m["gbs"], 2), "unit": "GB/s", "cores": m["cores"], "kind": m["kind"], "sample": sample},
+            "e2e": {"value": round(m["gbs"], 2), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gflops": round(2 * EXT ** 3 * last * 4 / m["seconds_per_step"] / 1e9, 2)}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# own arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_own_arm(args):
+    import torch
+    import torch.distributed as dist
+    import ttv_b200
+    from ttv_b200.sharded import make_shard, ttv_sharded
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N with N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this framework has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    na_global = [EXT, EXT, EXT, EXT * world]
+    pia = [1, 2, 3, 4]
+    shards = {q: make_shard(q, na_global, pia, rank, world) for q in range(1, ORDER + 1)}
+    sh = shards[1]
+    a = torch.empty(sh.a_count, dtype=torch.float32, device=dev)
+    ttv_b200.fill(a, SEED_A, first=sh.a_offset)
+    bs = {}
+    for q in range(1, ORDER + 1):
+        bs[q] = torch.empty(na_global[q - 1], dtype=torch.float32, device=dev)
+        ttv_b200.fill(bs[q], SEED_B + q)
+    cs = {q: torch.full((shards[q].c_count,), float("nan"), dtype=torch.float32, device=dev) for q in range(1, ORDER + 1)}
+
+    def step():
+        for q in range(1, ORDER + 1):
+            ttv_sharded(q, a, na_global, pia, bs[q], rank=rank, world=world, c_local=cs[q], reduce_to=0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- smoke check of one product against the oracle on sampled fibers (the checker, not the thing measured) ----
+    step()
+    torch.cuda.synchronize()
+    verify_sample(torch, cs, shards, na_global, bs, rank, world)
+
+    total_bytes = sum(algo_bytes(na_global, q) for q in range(1, ORDER + 1))
+    total_flops = 2 * int(np.prod(na_global, dtype=object)) * ORDER
+
+    with ClockSampler(local) as clocks:
+        for _ in range(max(args.warmup, 3)):
+            step()
+        barrier()
+        launches0 = ttv_b200.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+        launches = ttv_b200.launch_count() - launches0
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+            dist.all_reduce(lt)
+            launches = int(lt.item())
+
+        # ---- per-product timing of the dominant kernel (events around every launch on the launching stream) ----
+        per_q = {}
+        for q in range(1, ORDER + 1):
+            reps = max(5, min(args.steps, 20))
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+            barrier()
+            for s, e in evs:
+                s.record()
+                local_product(ttv_b200, q, a, shards[q], pia, bs[q], cs[q])
+                e.record()
+            torch.cuda.synchronize()
+            per_q[q] = statistics.mean(s.elapsed_time(e) for s, e in evs)
+    clk = clocks.summary()
+
+    ms_per_step = ms / args.steps
+    value = total_bytes / (ms_per_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel: the column-GEMV kernel (3 of the 4 launches of a step) -------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    col_q = [2, 3, 4]
+    col_bytes = [algo_bytes(list(shards[q].na_local), q) for q in col_q]
+    col_ms = [per_q[q] for q in col_q]
+    achieved = sum(col_bytes) / (sum(col_ms) * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("col_kernel_dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "ttv_col_kernel<float,4,8>", "achieved": round(achieved, 1), "peak": peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                "unit": "GB/s", "frac": round(achieved / peak, 4), "frac_of_nominal_8000": round(achieved / 8000.0, 4),
+                "traffic": traffic, "algorithmic_bytes_per_launch": int(statistics.mean(col_bytes)),
+                "per_product": {f"q{q}": {"ms": round(per_q[q], 4),
+                                          "gbs": round(algo_bytes(list(shards[q].na_local), q) / (per_q[q] * 1e-3) / 1e9, 1)}
+                                for q in range(1, ORDER + 1)}}
+
+    # ---- end to end through the public API with host buffers --------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = measure_e2e(torch, dist, ttv_b200, args, a, bs, cs, shards, na_global, pia, rank, world, dev, total_bytes)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            m = cpu_measure(32, 3, 1, budget_s=25.0)
+            cpu = {"value": round(m["gbs"], 2), "unit": "GB/s", "cores": m["cores"], "kind": m["kind"],
+                   "sample": (f"{'unmodified reference headers' if m['kind'] == 'reference' else 'oracle port'} "
+                              f"({'OpenBLAS ' if m['blas'] else 'non-BLAS '}par_loop/subtensor/all), slab n=(256,256,256,32) fp32 of the "
+                              f"256^4 tensor, q=1..4, {m['steps_done']} steps after 1 warm-up")}
+        except Exception as exc:  # the baseline is reported, never required for the GPU number
+            cpu = {"value": None, "unit": "GB/s", "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+                "config": {"workload": workload_name(world), "layout": "first-order", "per_gpu_tensor_bytes": sh.a_count * ELEM,
+                           "l2": "inputs (16 GiB per GPU) are larger than L2; no flush needed",
+                           "timing": "CUDA events on the launching stream, max over ranks"},
+                "gflops": round(total_flops / (ms_per_step * 1e-3) / 1e9, 1),
+                "frac_of_measured_peak": round(value / (peak * world), 4),
+                "frac_of_nominal_8000": round(value / (8000.0 * world), 4),
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def local_product(ttv_b200, q, a, shard, pia, b, c):
+    """this rank's kernel launch for product q (no collective): what the roofline of the kernel is measured on"""
+    na = list(shard.na_local)
+    bq = b[shard.begin: shard.begin + shard.count] if shard.kind == "nq" else b
+    nc = ttv_b200.generate_output_shape(na, q); pic = ttv_b200.generate_output_layout(pia, q)
+    ttv_b200.ttv_lowlevel(q, len(na), a, na, ttv_b200.generate_strides(na, pia), pia, bq, [int(bq.shape[0])], c, nc,
+                          ttv_b200.generate_strides(nc, pic), pic, flags=2)
+
+
+def verify_sample(torch, cs, shards, na_global, bs, rank, world):
+    """64 sampled outputs per product against a host long-double dot on regenerated data (oracle generator)"""
+    from oracle.oracle import Oracle
+    oracle = Oracle()
+    rng = np.random.default_rng(1234 + rank)
+    for q in range(1, ORDER + 1):
+        sh = shards[q]
+        if sh.kind == "nq" and (world > 1 and rank != 0):
+            continue
+        c = cs[q]
+        inner = int(np.prod(na_global[: q - 1], dtype=object)) if q > 1 else 1
+        nq = na_global[q - 1]
+        bh = bs[q].cpu().numpy().astype(np.longdouble)
+        for j in rng.integers(0, sh.c_count, 64):
+            jg = int(j) + sh.c_offset                       # index into the global C
+            o, i = divmod(jg, inner)
+            idx = (o * nq + np.arange(nq)) * inner + i      # global element indices of the fiber
+            fiber = np.array([oracle.fill(DTYPE, 1, SEED_A, first=int(e))[0] for e in idx], dtype=np.longdouble)
+            want = float(np.dot(fiber, bh))
+            tol = 2 * nq * (np.finfo(np.float32).eps / 2) * float(np.dot(np.abs(fiber), np.abs(bh))) + 1e-30
+            got = float(c[int(j)].item())
+            if not abs(got - want) <= tol:
+                raise SystemExit(f"bench.py: parity check failed for q={q}, output {jg}: got {got}, want {want}, tol {tol}")
+
+
+def measure_e2e(torch, dist, ttv_b200, args, a, bs, cs, shards, na_global, pia, rank, world, dev, total_bytes):
+    """Same step, inputs in pinned HOST memory: every product copies its slab of A and b to the device and reads C
+    back inside the timed region.  N = 1 goes through the C-ABI's host-pointer path (the call a user of the reference
+    makes); N > 1 stages explicitly because the n_q-split reduce runs on device buffers."""
+    sh = shards[1]
+    steps = max(1, args.e2e_steps)
+    a_host = torch.empty(sh.a_count, dtype=torch.float32, pin_memory=True)
+    a_host.copy_(a)                                      # same synthetic data as the device run
+    b_host = {q: bs[q].cpu().pin_memory() for q in bs}
+    c_host = {q: torch.empty(shards[q].c_count, dtype=torch.float32, pin_memory=True) for q in cs}
+    h2d = sum(sh.a_count * ELEM + (shards[q].count if shards[q].kind == "nq" else na_global[q - 1]) * ELEM for q in range(1, ORDER + 1))
+    d2h = sum(shards[q].c_count * ELEM for q in range(1, ORDER + 1) if not (shards[q].kind == "nq" and rank != 0))
+
+    def e2e_step():
+        for q in range(1, ORDER + 1):
+            s = shards[q]
+            if world == 1:
+                na = list(s.na_local)
+                nc = ttv_b200.generate_output_shape(na, q); pic = ttv_b200.generate_output_layout(pia, q)
+                ttv_b200.ttv_lowlevel(q, ORDER, a_host.numpy(), na, ttv_b200.generate_strides(na, pia), pia, b_host[q].numpy(),
+                                      [na[q - 1]], c_host[q].numpy(), nc, ttv_b200.generate_strides(nc, pic), pic)
+            else:
+                from ttv_b200.sharded import ttv_sharded
+                a.copy_(a_host, non_blocking=True)
+                bs[q].copy_(b_host[q], non_blocking=True)
+                ttv_sharded(q, a, na_global, pia, bs[q], rank=rank, world=world, c_local=cs[q], reduce_to=0)
+                if not (s.kind == "nq" and rank != 0):
+                    c_host[q].copy_(cs[q], non_blocking=True)
+                torch.cuda.synchronize()
+
+    e2e_step()                                            # warm-up (also sizes the staging buffers)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        hb = torch.tensor([h2d, d2h], device=dev, dtype=torch.int64)
+        dist.all_reduce(hb)
+        h2d, d2h = int(hb[0].item()), int(hb[1].item())
+    # the result of the last product must be the device-resident one
+    if world == 1 and not torch.equal(c_host[2], cs[2].cpu()):
+        raise SystemExit("bench.py: e2e result differs from the device-resident result")
+    return {"value": round(total_bytes / (dt / steps) / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "ms_per_step": round(dt / steps * 1e3, 2), "steps": steps,
+            "path": "C-ABI host-pointer path (pinned host buffers)" if world == 1 else "pinned host -> device copy, sharded TTV, device -> host"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_own_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -177,6 +177,11 @@ int ttv_b200_view(int dtype, uint64_t outer, uint64_t nq, uint64_t inner,
 int ttv_b200_plan_view(int dtype, uint64_t outer, uint64_t nq, uint64_t inner,
                        const ttv_b200_opts* opts, ttv_b200_plan_t* plan);
 
+/* x[i] = synth(seed, first + i), i < count, written on the device by a kernel (x is a DEVICE pointer).  The generator
+ * is the counter-based splitmix64 one of SURVEY 8(d); oracle/ttv_oracle.c carries the identical host version, so
+ * tensors too large for host memory can be checked by sampling. */
+int ttv_b200_fill(int dtype, void* x, uint64_t first, uint64_t count, uint64_t seed, const ttv_b200_opts* opts);
+
 /* L0 helpers of the reference, restated (shape.h, layout.h, strides.h); pure host code ------------------- */
 int ttv_b200_is_valid_shape  (const uint64_t* n,  uint64_t p);                       /* shape.h:30-34    */
 int ttv_b200_is_valid_layout (const uint64_t* pi, uint64_t p);                       /* layout.h:29-55   */

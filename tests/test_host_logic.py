@@ -1,0 +1,213 @@
+"""CPU-only tests of the boundary: the C-ABI library loads and exports every symbol include/ttv_b200.h declares, the
+restated L0 helpers agree with the oracle (and with the live reference when built), the argument checks fire in the
+reference's order with its messages, and the layout folder / kernel chooser behave.  No compute calls (no GPU here)."""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+import os
+import re
+
+import numpy as np
+import pytest
+
+import ttv_b200
+from ttv_b200 import _lib
+from conftest import all_layouts, fold
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "ttv_b200.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(ttv_b200_[a-z0-9_]+)\s*\(", body))
+    assert len(declared) >= 25
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} is declared in include/ttv_b200.h but not exported"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    assert lib.ttv_b200_version() == 100
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(_lib.Opts) == 40
+    assert C.sizeof(_lib.Plan) == 3 * 8 + 2 * 4 + 6 * 4 + 5 * 8
+
+
+# ---- L0 helpers ------------------------------------------------------------------------------------------------------
+def test_layout_helpers_match_reference_literals():
+    """literals of test/src/gtest_tlib_layout.cpp and gtest_tlib_strides.cpp / gtest_tlib_shape.cpp"""
+    g = ttv_b200.generate_k_order_layout
+    assert g(4, 1) == [1, 2, 3, 4] and g(4, 2) == [2, 1, 3, 4] and g(4, 3) == [3, 2, 1, 4]
+    assert g(4, 4) == [4, 3, 2, 1] and g(4, 0) == [4, 3, 2, 1] and g(4, 9) == [4, 3, 2, 1] and g(1, 1) == [1]
+    for bad in ([], [0], [0, 1], [1, 0], [2], [1, 1], [1, 3], [1, 3, 5], [2, 2, 1]):
+        assert not ttv_b200.is_valid_layout(bad), bad
+    for good in ([1], [1, 2], [2, 1], [3, 1, 2], [4, 3, 2, 1]):
+        assert ttv_b200.is_valid_layout(good), good
+    s = ttv_b200.generate_strides
+    assert s([4, 4, 2], [1, 2, 3]) == [1, 4, 16]
+    assert s([4, 2, 2], [2, 1, 3]) == [2, 1, 8]
+    assert s([4, 4, 2], [3, 2, 1]) == [8, 2, 1]
+    assert s([1, 1], [1, 2]) == [1, 1] and s([4, 1], [1, 2]) == [1, 1] and s([1, 4], [2, 1]) == [1, 1]
+    assert s([4], [1]) == [1] and s([1], [1]) == [1]
+    assert s([3, 4], [1, 2]) == [1, 3] and s([3, 4], [2, 1]) == [4, 1]
+    assert ttv_b200.generate_output_shape([4, 3, 2], 1) == [3, 2]
+    assert ttv_b200.generate_output_shape([4, 3, 2], 2) == [4, 2]
+    assert ttv_b200.generate_output_shape([4, 3, 2], 3) == [4, 3]
+    assert ttv_b200.generate_output_layout([3, 1, 2], 1) == [2, 1]
+    assert ttv_b200.generate_output_layout([3, 1, 2], 3) == [1, 2]
+    assert not ttv_b200.is_valid_shape([]) and not ttv_b200.is_valid_shape([3, 0]) and ttv_b200.is_valid_shape([1])
+
+
+def test_helpers_agree_with_oracle_and_reference(oracle, reference):
+    shapes = [s for p in (1, 2, 3, 4) for s in itertools.product([1, 2, 3], repeat=p)]
+    for n in shapes:
+        p = len(n)
+        for pi in all_layouts(p):
+            w = ttv_b200.generate_strides(n, pi)
+            assert w == oracle.strides(n, pi)
+            assert ttv_b200.is_valid_strides(pi, w) == oracle.is_valid_strides(pi, w)
+            if reference is not None:
+                rw = np.zeros(p, np.uint64)
+                nn, pp = np.asarray(n, np.uint64), np.asarray(pi, np.uint64)
+                reference.lib.ttv_ref_compute_strides(nn.ctypes.data_as(_lib.u64p), pp.ctypes.data_as(_lib.u64p), p,
+                                                      rw.ctypes.data_as(_lib.u64p))
+                assert w == [int(x) for x in rw], (n, pi)
+            for q in range(1, p + 1):
+                if p > 1:
+                    assert ttv_b200.generate_output_shape(n, q) == oracle.output_shape(n, q)
+                    assert ttv_b200.generate_output_layout(pi, q) == oracle.output_layout(pi, q)
+    for p in range(1, 8):
+        for k in range(0, p + 2):
+            assert ttv_b200.generate_k_order_layout(p, k) == oracle.k_order_layout(p, k)
+    # strides that decrease along the layout are invalid (strides.h:76-101)
+    assert not ttv_b200.is_valid_strides([1, 2, 3], [1, 8, 4])
+    assert ttv_b200.is_valid_strides([1, 2, 3], [1, 4, 4])
+
+
+# ---- argument checks ---------------------------------------------------------------------------------------------------
+def _plan_status(q, p, a, na, wa, pia, b, nb, c, nc, wc, pic):
+    lib = _lib.load()
+    keep = [ttv_b200.api._tuple(v) for v in (na, wa, pia, nb, nc, wc, pic)]
+    ptrs = [k[1] for k in keep]
+    st = lib.ttv_b200_plan(0, q, p, a, ptrs[0], ptrs[1], ptrs[2], b, ptrs[3], c, ptrs[4], ptrs[5], ptrs[6], None, None)
+    return st, lib.ttv_b200_last_error().decode() if st else ""
+
+
+def test_argument_checks_follow_the_reference(oracle, reference):
+    """ttv.h:64-89: sixteen checks, evaluated in order; same status and same text as the oracle (and as the what()
+    of the exception the live reference throws)."""
+    one = C.c_void_p(64)
+    ok = dict(q=2, p=3, a=one, na=[4, 3, 2], wa=[1, 4, 12], pia=[1, 2, 3], b=one, nb=[3], c=one, nc=[4, 2], wc=[1, 4], pic=[1, 2])
+    assert _plan_status(**ok)[0] == 0
+    cases = [
+        (1, dict(p=0)), (2, dict(q=0)), (2, dict(q=4)), (3, dict(a=None)), (4, dict(b=None)), (5, dict(c=None)),
+        (6, dict(na=None)), (7, dict(nb=None)), (8, dict(nc=None)), (9, dict(wa=None)), (10, dict(wc=None)),
+        (11, dict(pia=None)), (12, dict(pic=None)), (13, dict(nb=[4])), (14, dict(na=[4, 3, 0])), (15, dict(nc=[0, 2])),
+        (16, dict(pia=[1, 2, 2])), (16, dict(pia=[0, 1, 2])), (17, dict(pic=[1, 1])), (17, dict(pic=[3, 1])),
+        (18, dict(wa=[12, 4, 1])), (19, dict(wc=[4, 1])),
+        (20, dict(pic=[2, 1], wc=[2, 1])),                                 # beginning of the layout tuples differs (case 8 only)
+        (2, dict(p=0 + 1, q=2)),                                 # q > p
+        (15, dict(p=1, q=1, na=[3], wa=[1], pia=[1], nc=[1], wc=[1], pic=[1])),   # order 1 always throws here
+        # several things wrong at once: the earliest check wins
+        (3, dict(a=None, na=None, pia=[9, 9, 9])), (13, dict(nb=[9], na=[4, 3, 0])), (14, dict(na=[0, 3, 2], pia=[1, 1, 1])),
+    ]
+    dummy = np.zeros(64)
+    for want, change in cases:
+        args = dict(ok); args.update(change)
+        st, msg = _plan_status(**args)
+        assert st == want, (want, change, st, msg)
+        assert msg.startswith(oracle.strerror(want)), (msg, oracle.strerror(want))
+        # the oracle, given the same arguments, reports the same status
+        def arr(v):
+            return None if v is None else np.asarray(v, np.uint64)
+        def buf(v):
+            return None if v is None else dummy
+        ost = oracle.run_raw(1, 1, args["q"], args["p"], buf(args["a"]), arr(args["na"]), arr(args["wa"]), arr(args["pia"]),
+                             buf(args["b"]), arr(args["nb"]), buf(args["c"]), arr(args["nc"]), arr(args["wc"]), arr(args["pic"]))
+        assert ost == want, (want, change, ost)
+        if reference is not None:
+            rst = reference.run_raw(1, ("seq", "slice", "none"), args["q"], args["p"], buf(args["a"]), arr(args["na"]),
+                                    arr(args["wa"]), arr(args["pia"]), buf(args["b"]), arr(args["nb"]), buf(args["c"]),
+                                    arr(args["nc"]), arr(args["wc"]), arr(args["pic"]))
+            assert rst == -1 and reference.last_error() == oracle.strerror(want), (want, change, reference.last_error())
+
+
+def test_layout_end_mismatch():
+    one = C.c_void_p(64)
+    st, msg = _plan_status(2, 4, one, [2, 3, 4, 5], [1, 2, 6, 24], [1, 2, 3, 4], one, [3], one, [2, 4, 5], [1, 10, 2], [1, 3, 2])
+    assert st == 21 and "end of layout tuples" in msg
+
+
+def test_non_packed_strides_are_rejected_in_case_8_only():
+    one = C.c_void_p(64)
+    st, msg = _plan_status(2, 3, one, [4, 3, 2], [1, 8, 24], [1, 2, 3], one, [3], one, [4, 2], [1, 4], [1, 2])
+    assert st == 30, msg
+    # cases 1-7 ignore wa / wc exactly like the reference's mtv (matrix_times_vector.h:314-336)
+    st, _ = _plan_status(1, 3, one, [4, 3, 2], [1, 8, 24], [1, 2, 3], one, [4], one, [3, 2], [1, 3], [1, 2])
+    assert st == 0
+    # extent-1 modes may carry any stride
+    st, _ = _plan_status(2, 4, one, [3, 2, 1, 4], [1, 3, 4, 6], [1, 2, 3, 4], one, [2], one, [3, 1, 4], [1, 2, 3], [1, 2, 3])
+    assert st == 0
+
+
+# ---- folder + chooser ----------------------------------------------------------------------------------------------------
+def test_fold_and_case_classification(oracle):
+    for p in (2, 3, 4, 5):
+        for na in [(2, 3, 4, 5, 6)[:p], (5, 1, 3, 1, 2)[:p]]:
+            for pia in all_layouts(p):
+                for q in range(1, p + 1):
+                    pl = ttv_b200.plan(q, na, pia, dtype="f64")
+                    assert (pl["outer"], pl["nq"], pl["inner"]) == fold(na, pia, q)
+                    assert pl["ref_case"] == oracle.case(p, q, pia)
+                    assert pl["k"] == list(pia).index(q) + 1
+                    n = int(np.prod(na))
+                    assert pl["algo_bytes"] == 8 * (n + na[q - 1] + n // na[q - 1])
+                    assert pl["algo_flops"] == 2 * n
+                    assert pl["kernel"] == (1 if pl["inner"] == 1 else 2)
+
+
+def test_chooser_named_configs():
+    # cfg1: 512^3 fp32 q=2 -> column GEMV, 16-byte vectors, a full row per CTA
+    pl = ttv_b200.plan(2, [512, 512, 512], [1, 2, 3], dtype="f32")
+    assert pl["kernel"] == 2 and pl["vec"] == 4 and pl["tx"] == 128 and pl["algo_bytes"] == 537921536
+    # cfg5 q=1: DOT, one warp per 16 KiB fiber; q=3: column GEMV over 4 Mi outputs
+    pl = ttv_b200.plan(1, [2048] * 3, [1, 2, 3], dtype="f64")
+    assert pl["kernel"] == 1 and pl["vec"] == 2 and pl["ty"] == 32 and pl["ksplit"] == 1
+    pl = ttv_b200.plan(3, [2048] * 3, [1, 2, 3], dtype="f64")
+    assert pl["kernel"] == 2 and pl["vec"] == 2 and pl["tx"] == 256 and pl["ksplit"] == 1
+    # odd inner extent: scalar loads along inner; odd n_q: scalar loads along n_q
+    assert ttv_b200.plan(2, [23, 23, 23], [1, 2, 3], dtype="f32")["vec"] == 1
+    assert ttv_b200.plan(1, [23, 23, 23], [1, 2, 3], dtype="f32")["vec"] == 1
+    # a single huge fiber: split n_q across CTAs
+    pl = ttv_b200.plan(1, [1 << 26, 2], [1, 2], dtype="f32")
+    assert pl["kernel"] == 1 and pl["ksplit"] > 64 and pl["workspace_bytes"] == pl["ksplit"] * 2 * 4
+    # complex<double>: one element per 16-byte load
+    assert ttv_b200.plan(2, [64, 64, 64], [1, 2, 3], dtype="c128")["vec"] == 1
+    # forcing
+    assert ttv_b200.plan(1, [64, 64], [1, 2], dtype="f32", kernel="col")["kernel"] == 2
+    with pytest.raises(ttv_b200.TTVError):
+        ttv_b200.plan(2, [64, 64, 64], [1, 2, 3], dtype="f32", kernel="dot")
+    assert ttv_b200.plan(2, [512, 512, 512], [1, 2, 3], dtype="f32", ksplit=3)["ksplit"] == 3
+    assert ttv_b200.plan(2, [512, 512, 512], [1, 2, 3], dtype="f32", flags=4)["vec"] == 1
+
+
+def test_no_cpu_fallback_without_device():
+    if ttv_b200.device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    with pytest.raises(ttv_b200.TTVError) as e:
+        ttv_b200.ttv(2, np.ones((3, 4)), np.ones(4))
+    assert e.value.status == 40 and "no CPU fallback" in str(e.value)
+
+
+def test_chain_plan_orders():
+    from ttv_b200.ttvpy import chain_plan
+    # backward: highest mode first, numbering of the lower modes is unaffected
+    assert chain_plan(2, (3, 2, 4, 5), "backward") == [(4, 2), (3, 1), (1, 0)]
+    # forward: always mode 1 until q is reached, then always mode 2
+    assert chain_plan(2, (3, 2, 4, 5), "forward") == [(1, 0), (2, 1), (2, 2)]
+    assert chain_plan(1, (3, 2, 4, 5), "forward") == [(2, 0), (2, 1), (2, 2)]
+    # optimal: longest vector first
+    assert chain_plan(1, (3, 2, 4, 5), "optimal") == [(4, 2), (3, 1), (2, 0)]
+    assert chain_plan(4, (3, 9, 4, 5), "optimal") == [(2, 1), (2, 2), (1, 0)]

@@ -1,0 +1,271 @@
+"""Parity of the CUDA path with the oracle, through the C-ABI.  Needs a B200 (pytest -m gpu).
+
+Bit-exact for integer element types and for integer-valued float data; within 2*n_q*eps*sum|a||b| per element for
+float/double/complex data in [-1,1).  The test grid of the reference (gtest_tlib_ttv.cpp:192-425) is run
+in full for double like the reference does, plus every other element type on a thinned grid, plus what the reference
+never tests: non-power-of-two extents, extents of 1, order > 4, forced kernels / split n_q / scalar loads, device
+pointers, accumulate, large sizes through size-independent properties."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import pytest
+
+import ttv_b200
+from conftest import (all_layouts, assert_close, fold, random_case, real_case, reference_expected, reference_init,
+                      reference_shapes)
+
+pytestmark = pytest.mark.gpu
+
+ALL_DTYPES = [np.float32, np.float64, np.complex64, np.complex128, np.int32, np.int64]
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ttv_golden.npz")
+
+
+def run_lowlevel(q, a, na, pia, b, *, c0=None, **opts):
+    """call the C-like interface with host buffers the way gtest_tlib_ttv.cpp:96-135 does"""
+    p = len(na)
+    nc = ttv_b200.generate_output_shape(na, q)
+    pic = ttv_b200.generate_output_layout(pia, q)
+    wa = ttv_b200.generate_strides(na, pia)
+    wc = ttv_b200.generate_strides(nc, pic)
+    c = np.zeros(int(np.prod(nc, dtype=object)), a.dtype) if c0 is None else c0
+    ttv_b200.ttv_lowlevel(q, p, a, na, wa, pia, b, [len(b)], c, nc, wc, pic, **opts)
+    return c
+
+
+# ---- the reference's own grid -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("order", [2, 3, 4])
+def test_reference_grid_double(order):
+    """TEST(TensorTimesVector, *): double, {2,4,8}^p, all layouts, every q, b = 1, closed form :132"""
+    before = ttv_b200.launch_count()
+    n_calls = 0
+    for na in reference_shapes(order):
+        for pia in all_layouts(order):
+            for q in range(1, order + 1):
+                a = reference_init(na, pia, q, np.float64)
+                b = np.ones(na[q - 1], np.float64)
+                c = run_lowlevel(q, a, na, pia, b)
+                assert np.array_equal(c, reference_expected(na, q, c.size, np.float64)), (na, pia, q)
+                n_calls += 1
+    assert ttv_b200.launch_count() - before >= n_calls      # the CUDA kernels ran, nothing else could have
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.complex64, np.complex128, np.int32, np.int64])
+def test_reference_grid_other_types(dtype, oracle):
+    rng = np.random.default_rng(5)
+    for order in (2, 3, 4):
+        shapes = reference_shapes(order)
+        for na in shapes[:: max(1, len(shapes) // 9)]:
+            for pia in all_layouts(order):
+                for q in range(1, order + 1):
+                    a, b = random_case(rng, na, q, dtype)
+                    c = run_lowlevel(q, a, na, pia, b)
+                    assert np.array_equal(c, oracle.ttv(q, a, na, pia, b)), (na, pia, q, dtype)
+
+
+@pytest.mark.parametrize("policy", [("seq", "slice", "none"), ("par_loop", "slice", "all"), ("par_loop", "slice", "outer"),
+                                    ("par_blas", "subtensor", "all"), ("par_taskloop", "subtensor", "none")])
+def test_policy_hints_select_the_same_path(policy, oracle):
+    rng = np.random.default_rng(6)
+    na, pia = (4, 8, 2, 4), (3, 1, 4, 2)
+    for q in range(1, 5):
+        a, b = random_case(rng, na, q, np.float64)
+        c = run_lowlevel(q, a, na, pia, b, execution=policy[0], slicing=policy[1], fusion=policy[2])
+        assert np.array_equal(c, oracle.ttv(q, a, na, pia, b, "slice" if policy[1] == "slice" else "subtensor"))
+
+
+# ---- what the reference does not test ----------------------------------------------------------------------------------------
+ODD_SHAPES = [(3, 5), (1, 7), (7, 1), (257, 3), (3, 5, 7), (1, 4, 1), (5, 1, 3), (33, 2, 17), (2, 129, 3), (3, 4, 5, 2),
+              (1, 1, 6, 2), (2, 3, 1, 5, 2), (2, 2, 3, 2, 2, 3), (2, 2, 2, 2, 2, 2, 3), (2, 1, 2, 2, 1, 2, 2, 3)]
+
+
+@pytest.mark.parametrize("dtype", ALL_DTYPES)
+def test_non_power_of_two_and_unit_extents(dtype, oracle):
+    rng = np.random.default_rng(8)
+    for na in ODD_SHAPES:
+        p = len(na)
+        layouts = all_layouts(p) if p <= 3 else [tuple(ttv_b200.generate_k_order_layout(p, k)) for k in (1, 0, 2)] + \
+            [tuple(int(x) for x in rng.permutation(p) + 1) for _ in range(3)]
+        for pia in layouts:
+            for q in range(1, p + 1):
+                a, b = random_case(rng, na, q, dtype)
+                c = run_lowlevel(q, a, na, pia, b)
+                assert np.array_equal(c, oracle.naive(q, a, na, pia, b)), (na, pia, q, dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.complex128])
+def test_rounding_within_stated_tolerance(dtype, oracle):
+    rng = np.random.default_rng(9)
+    for na, pia in [((64, 300, 5), (1, 2, 3)), ((64, 300, 5), (3, 2, 1)), ((5, 7, 1000), (2, 3, 1)), ((1000, 37), (1, 2)),
+                    ((1000, 37), (2, 1)), ((12, 20, 6, 9), (4, 2, 1, 3))]:
+        for q in range(1, len(na) + 1):
+            a, b = real_case(rng, na, q, dtype)
+            wide, mag = oracle.naive(q, a, na, pia, b, want_abs=True)
+            ref = oracle.ttv(q, a, na, pia, b)
+            c = run_lowlevel(q, a, na, pia, b)
+            assert_close(c, wide, mag, na[q - 1], dtype, f"cuda vs wide {na} {pia} q={q}")
+            assert_close(c, ref, 2 * mag, na[q - 1], dtype, f"cuda vs oracle {na} {pia} q={q}")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.int32])
+@pytest.mark.parametrize("variant", [dict(ksplit=1), dict(ksplit=3), dict(ksplit=7), dict(flags=4), dict(flags=4, ksplit=2),
+                                     dict(kernel="col"), dict(kernel="col", ksplit=4)])
+def test_forced_variants(dtype, variant, oracle):
+    """every kernel family / split / vector width on shapes that reach each of their code paths"""
+    rng = np.random.default_rng(10)
+    shapes = [((8, 64, 6), (1, 2, 3)), ((300, 40), (1, 2)), ((300, 40), (2, 1)), ((2, 500, 3), (1, 2, 3)), ((16, 9, 33), (3, 1, 2)),
+              ((1024, 70), (1, 2)), ((4, 4100), (2, 1))]
+    for na, pia in shapes:
+        for q in range(1, len(na) + 1):
+            a, b = random_case(rng, na, q, dtype)
+            c = run_lowlevel(q, a, na, pia, b, **variant)
+            assert np.array_equal(c, oracle.ttv(q, a, na, pia, b)), (na, pia, q, variant)
+
+
+def test_golden_fixtures_of_the_reference(oracle):
+    g = np.load(GOLDEN, allow_pickle=False)
+    for i in range(int(g["count"])):
+        na = g[f"na_{i}"].tolist(); pia = g[f"pia_{i}"].tolist(); q = int(g[f"q_{i}"])
+        a, b, c_ref = g[f"a_{i}"], g[f"b_{i}"], g[f"c_{i}"]
+        c = run_lowlevel(q, a, na, pia, b)
+        if bool(g[f"exact_{i}"]):
+            assert np.array_equal(c, c_ref), (i, na, pia, q, a.dtype)
+        else:
+            _, mag = oracle.naive(q, a, na, pia, b, want_abs=True)
+            assert_close(c, c_ref, mag, na[q - 1], a.dtype, what=f"golden case {i}")
+
+
+def test_known_answers():
+    a = np.arange(1, 25, dtype=np.float32)        # example/interface3.cpp
+    assert run_lowlevel(2, a, (4, 3, 2), (1, 2, 3), np.ones(3, np.float32)).tolist() == [15, 18, 21, 24, 51, 54, 57, 60]
+    A = np.arange(24, dtype=np.float64).reshape(3, 2, 4)     # ttvpy/README.md:61-66
+    assert ttv_b200.ttvpy.ttv(1, A, np.arange(3, dtype=np.float64)).tolist() == [[40, 43, 46, 49], [52, 55, 58, 61]]
+
+
+def test_overwrite_and_accumulate(oracle):
+    """C is overwritten by default (what the BLAS build of the reference does, matrix_times_vector.h:213-215);
+    FLAG_ACCUMULATE gives the non-BLAS column kernel's C += (matrix_times_vector.h:124)."""
+    rng = np.random.default_rng(12)
+    for na, pia in [((4, 3, 2), (1, 2, 3)), ((40, 30), (1, 2)), ((6, 50, 7), (2, 3, 1))]:
+        for q in range(1, len(na) + 1):
+            a, b = random_case(rng, na, q, np.float64)
+            expect = oracle.ttv(q, a, na, pia, b)
+            c0 = np.full(expect.size, 100.0)
+            assert np.array_equal(run_lowlevel(q, a, na, pia, b, c0=c0.copy()), expect)
+            assert np.array_equal(run_lowlevel(q, a, na, pia, b, c0=c0.copy(), flags=1), expect + 100.0)
+            assert np.array_equal(run_lowlevel(q, a, na, pia, b, c0=c0.copy(), flags=1, ksplit=3), expect + 100.0)
+
+
+def test_errors_surface_with_reference_messages():
+    a = np.zeros(24); b = np.zeros(3); c = np.zeros(8)
+    with pytest.raises(ttv_b200.TTVError) as e:
+        ttv_b200.ttv_lowlevel(2, 3, a, [4, 3, 2], [1, 4, 12], [1, 2, 3], b, [4], c, [4, 2], [1, 4], [1, 2])
+    assert e.value.status == 13 and str(e.value).startswith("Error in tlib::tensor_times_vector: contraction dimension")
+    with pytest.raises(ttv_b200.TTVError) as e:
+        ttv_b200.ttv_lowlevel(2, 3, a, [4, 3, 2], [1, 4, 12], [1, 2, 3], b, [3], c, [4, 2], [2, 1], [2, 1])
+    assert e.value.status == 20
+
+
+# ---- device pointers ------------------------------------------------------------------------------------------------------
+def test_device_pointers_in_place(oracle):
+    import torch
+    rng = np.random.default_rng(13)
+    for dtype in ALL_DTYPES:
+        for na, pia in [((6, 50, 7), (2, 3, 1)), ((129, 65), (1, 2))]:
+            for q in range(1, len(na) + 1):
+                a, b = random_case(rng, na, q, dtype)
+                ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+                nc = ttv_b200.generate_output_shape(na, q); pic = ttv_b200.generate_output_layout(pia, q)
+                tc = torch.full((int(np.prod(nc)),), 7, dtype=ta.dtype, device="cuda")
+                ttv_b200.ttv_lowlevel(q, len(na), ta, na, ttv_b200.generate_strides(na, pia), pia, tb, [len(b)], tc, nc,
+                                      ttv_b200.generate_strides(nc, pic), pic)
+                assert np.array_equal(tc.cpu().numpy(), oracle.ttv(q, a, na, pia, b))
+    # mixing host and device buffers is an error, not a silent copy
+    with pytest.raises(ttv_b200.TTVError) as e:
+        ttv_b200.ttv_lowlevel(1, 2, ta, [129, 65], [1, 129], [1, 2], b if len(b) == 129 else np.zeros(129, a.dtype), [129],
+                              tc[:65], [65], [1], [1])
+    assert e.value.status == 41
+
+
+def test_tensor_level_interface_numpy_and_torch(oracle):
+    import torch
+    rng = np.random.default_rng(14)
+    A = rng.integers(-5, 6, (5, 4, 6, 3)).astype(np.float64)
+    subs = {1: "ijkl,i->jkl", 2: "ijkl,j->ikl", 3: "ijkl,k->ijl", 4: "ijkl,l->ijk"}
+    for q in range(1, 5):
+        b = rng.integers(-5, 6, A.shape[q - 1]).astype(np.float64)
+        want = np.einsum(subs[q], A, b)
+        assert np.array_equal(ttv_b200.ttv(q, A, b), want)                                   # C order  (last-order)
+        assert np.array_equal(ttv_b200.ttv(q, np.asfortranarray(A), b), want)                # F order  (first-order)
+        got = ttv_b200.ttv(q, torch.from_numpy(A).cuda(), torch.from_numpy(b).cuda())
+        assert np.array_equal(got.cpu().numpy(), want)
+
+
+# ---- sizes the oracle cannot hold: size-independent properties ------------------------------------------------------------------
+def test_large_shapes_by_properties(oracle):
+    """BASELINE config 1 at full size (512^3 fp32, q=2) and a 2^31+-element index range: linearity in b, agreement of
+    independent kernel variants, and sampled fibers against a host long-double dot on generator-defined data."""
+    import torch
+    n = 512
+    seed_a, seed_b = 0x77170001, 0x77170002
+    A = torch.empty(n * n * n, dtype=torch.float32, device="cuda")
+    ttv_b200.fill(A, seed_a)
+    b1 = torch.empty(n, dtype=torch.float32, device="cuda"); ttv_b200.fill(b1, seed_b)
+    b2 = torch.empty(n, dtype=torch.float32, device="cuda"); ttv_b200.fill(b2, seed_b + 5)
+    a_host_sample = oracle.fill("f32", 4096, seed_a)
+    assert np.array_equal(A[:4096].cpu().numpy(), a_host_sample)            # device generator == oracle generator
+    na, pia = [n, n, n], [1, 2, 3]
+    wa = ttv_b200.generate_strides(na, pia)
+    bh = b1.cpu().numpy().astype(np.longdouble)
+    rng = np.random.default_rng(15)
+    for q in (1, 2, 3):
+        nc = ttv_b200.generate_output_shape(na, q); pic = ttv_b200.generate_output_layout(pia, q)
+        wc = ttv_b200.generate_strides(nc, pic)
+        outs = []
+        for bb, kw in ((b1, {}), (b2, {}), (b1 + b2, {}), (b1, dict(ksplit=4)), (b1, dict(flags=4))):
+            c = torch.empty(n * n, dtype=torch.float32, device="cuda")
+            ttv_b200.ttv_lowlevel(q, 3, A, na, wa, pia, bb, [n], c, nc, wc, pic, **kw)
+            outs.append(c.cpu().numpy().astype(np.float64))
+        c1, c2, c12, c1_split, c1_scalar = outs
+        tol = 8 * n * np.finfo(np.float32).eps
+        assert np.abs(c12 - (c1 + c2)).max() <= tol * 4                     # linearity in b
+        assert np.abs(c1 - c1_split).max() <= tol and np.abs(c1 - c1_scalar).max() <= tol
+        # sampled fibers vs a host long-double dot on regenerated data (SURVEY 8c "too big for host")
+        outer, nq, inner = fold(na, pia, q)
+        for j in rng.integers(0, n * n, 64):
+            o, i = divmod(int(j), inner)
+            idx = (o * nq + np.arange(nq)) * inner + i
+            fiber = np.array([oracle.fill("f32", 1, seed_a, first=int(e))[0] for e in idx], dtype=np.longdouble)
+            want = float(np.dot(fiber, bh))
+            assert abs(c1[j] - want) <= 2 * nq * (np.finfo(np.float32).eps / 2) * float(np.dot(np.abs(fiber), np.abs(bh)))
+
+
+def test_more_than_2_to_32_elements():
+    """64-bit indexing: 2^32 + 2^20 int32 elements (16.4 GiB), q in every position; checksums in closed form."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 * 2 ** 30:
+        pytest.skip("needs 40 GiB of free HBM")
+    na = [1024, 4097, 1024]                 # 2^32 + 2^20 elements
+    total = na[0] * na[1] * na[2]
+    A = torch.ones(total, dtype=torch.int32, device="cuda")
+    # A = 1 everywhere except one marked element near the end of the index range
+    marked = total - 12345
+    A[marked] = 1000
+    pia = [1, 2, 3]
+    wa = ttv_b200.generate_strides(na, pia)
+    for q in (1, 2, 3):
+        nq = na[q - 1]
+        b = torch.arange(1, nq + 1, dtype=torch.int32, device="cuda")
+        nc = ttv_b200.generate_output_shape(na, q); pic = ttv_b200.generate_output_layout(pia, q)
+        c = torch.empty(total // nq, dtype=torch.int32, device="cuda")
+        ttv_b200.ttv_lowlevel(q, 3, A, na, wa, pia, b, [nq], c, nc, ttv_b200.generate_strides(nc, pic), pic)
+        base = nq * (nq + 1) // 2
+        outer, _, inner = fold(na, pia, q)
+        o, rem = divmod(marked, nq * inner)
+        k, i = divmod(rem, inner)
+        expect_marked = base + 999 * (k + 1)
+        j = o * inner + i
+        assert int(c[j]) == expect_marked
+        assert int((c != base).sum()) == 1

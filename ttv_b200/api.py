@@ -1,0 +1,297 @@
+"""Python host side of the TTV path on top of the C-ABI (include/ttv_b200.h).
+
+Mirrors the reference's interfaces for this path:
+
+  ttv_lowlevel(...)   the C-like interface   tlib::ttv::ttv(ep, sp, fp, q, p, a, na, wa, pia, b, nb, c, nc, wc, pic)
+                      (reference include/tlib/ttv.h:54-92): flat buffers + shape / stride / layout tuples, 1-based modes
+  ttv(q, A, b)        the tensor-level interface (ttv.h:99-114) on numpy arrays or torch CUDA tensors; the output
+                      shape / layout follow detail/shape.h:126-158 and detail/layout.h:175-207
+
+numpy arrays are HOST buffers (staged through the device inside the call); torch CUDA tensors are used in place.
+torch is only used for device memory and streams -- all arithmetic happens in libttv_b200.so.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import Opts, Plan
+
+DTYPE_CODES = {"f32": 0, "f64": 1, "c64": 2, "c128": 3, "i32": 4, "i64": 5}
+_NP_CODES = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.complex64): 2,
+             np.dtype(np.complex128): 3, np.dtype(np.int32): 4, np.dtype(np.int64): 5}
+
+EXECUTION = {"seq": 0, "seq_blas": 1, "par": 2, "par_loop": 3, "par_taskloop": 4, "par_task": 5, "par_blas": 6,
+             "par_blas_loop": 7}
+SLICING = {"slice": 0, "subtensor": 1}
+FUSION = {"none": 0, "outer": 1, "all": 2}
+KERNELS = {"auto": 0, "dot": 1, "col": 2, "stream": 3}
+
+FLAG_ACCUMULATE, FLAG_ASYNC, FLAG_NO_VEC = 1, 2, 4
+
+
+class TTVError(RuntimeError):
+    """Raised for every non-zero status of the C-ABI; str() is the reference's message text (ttv.h:64-89)."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(message)
+        self.status = status
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.split(".")[0] == "torch"
+
+
+def dtype_code(x) -> int:
+    if _is_torch(x):
+        import torch
+        table = {torch.float32: 0, torch.float64: 1, torch.complex64: 2, torch.complex128: 3, torch.int32: 4,
+                 torch.int64: 5}
+        if x.dtype not in table:
+            raise TTVError(31, f"Error in ttv_b200: unsupported element type {x.dtype}.")
+        return table[x.dtype]
+    dt = np.asarray(x).dtype
+    if dt not in _NP_CODES:
+        raise TTVError(31, f"Error in ttv_b200: unsupported element type {dt}.")
+    return _NP_CODES[dt]
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    if _is_torch(x):
+        return C.c_void_p(x.data_ptr())
+    return C.c_void_p(x.ctypes.data)
+
+
+def _tuple(v):
+    if v is None:
+        return None, None
+    arr = np.ascontiguousarray(np.asarray(list(v), dtype=np.uint64))
+    if arr.size == 0:
+        arr = np.zeros(1, np.uint64)        # keep the pointer non-null; the length travels separately (p)
+    return arr, arr.ctypes.data_as(_lib.u64p)
+
+
+def make_opts(*, execution="par_loop", slicing="subtensor", fusion="all", kernel="auto", ksplit=0, flags=0, device=-1,
+              stream=None) -> Opts:
+    if stream is not None and not isinstance(stream, int):
+        stream = stream.cuda_stream          # torch.cuda.Stream
+    return Opts(device=device, execution=EXECUTION[execution] if isinstance(execution, str) else int(execution),
+                slicing=SLICING[slicing] if isinstance(slicing, str) else int(slicing),
+                fusion=FUSION[fusion] if isinstance(fusion, str) else int(fusion),
+                kernel=KERNELS[kernel] if isinstance(kernel, str) else int(kernel),
+                ksplit=int(ksplit), flags=int(flags), reserved=0, stream=stream or None)
+
+
+def _current_torch_stream(x):
+    import torch
+    return torch.cuda.current_stream(x.device).cuda_stream
+
+
+def _check(status: int):
+    if status:
+        lib = _lib.load()
+        msg = lib.ttv_b200_last_error().decode() or lib.ttv_b200_strerror(status).decode()
+        raise TTVError(status, msg)
+
+
+# ---- L0 helpers (reference detail/shape.h, layout.h, strides.h) ----------------------------------------------------
+def is_valid_shape(n) -> bool:
+    arr, p = _tuple(n)
+    return bool(_lib.load().ttv_b200_is_valid_shape(p, len(n)))
+
+
+def is_valid_layout(pi) -> bool:
+    arr, p = _tuple(pi)
+    return bool(_lib.load().ttv_b200_is_valid_layout(p, len(pi)))
+
+
+def is_valid_strides(pi, w) -> bool:
+    a1, p1 = _tuple(pi); a2, p2 = _tuple(w)
+    r = _lib.load().ttv_b200_is_valid_strides(p1, len(pi), p2)
+    if r < 0:
+        raise TTVError(16, "Error in tlib::detail::is_valid_strides(): input layout is not valid.")
+    return bool(r)
+
+
+def generate_strides(n, pi) -> list[int]:
+    a1, p1 = _tuple(n); a2, p2 = _tuple(pi)
+    w = np.zeros(max(len(n), 1), np.uint64)
+    if len(n) != len(pi) or _lib.load().ttv_b200_compute_strides(p1, p2, len(n), w.ctypes.data_as(_lib.u64p)):
+        raise TTVError(14, "Error in tlib::detail::compute_strides(): input shape or layout is not valid.")
+    return [int(x) for x in w[: len(n)]]
+
+
+def generate_output_shape(na, q) -> list[int]:
+    a1, p1 = _tuple(na)
+    nc = np.zeros(max(len(na), 1), np.uint64)
+    if _lib.load().ttv_b200_output_shape(p1, len(na), q, nc.ctypes.data_as(_lib.u64p)):
+        raise TTVError(14, "Error in tlib::detail::generate_output_shape(): input shape or contraction mode is not valid.")
+    return [int(x) for x in nc[: len(na) - 1]]
+
+
+def generate_output_layout(pia, q) -> list[int]:
+    a1, p1 = _tuple(pia)
+    pic = np.zeros(max(len(pia), 1), np.uint64)
+    if _lib.load().ttv_b200_output_layout(p1, len(pia), q, pic.ctypes.data_as(_lib.u64p)):
+        raise TTVError(16, "Error in tlib::detail::generate_output_layout(): input layout or contraction mode is not valid.")
+    return [int(x) for x in pic[: len(pia) - 1]]
+
+
+def generate_k_order_layout(p, k) -> list[int]:
+    pi = np.zeros(max(p, 1), np.uint64)
+    if _lib.load().ttv_b200_k_order_layout(p, k, pi.ctypes.data_as(_lib.u64p)):
+        raise TTVError(16, "Error in tlib::detail::compute_k_order: range provided by begin and end not correct!")
+    return [int(x) for x in pi[:p]]
+
+
+# ---- the low-level interface -----------------------------------------------------------------------------------------
+def ttv_lowlevel(q: int, p: int, a, na, wa, pia, b, nb, c, nc, wc, pic, *, dtype: int | None = None,
+                 opts: Opts | None = None, **opt_kwargs) -> None:
+    """The reference's C-like interface (ttv.h:54-92).  a, b, c: numpy arrays (host), torch CUDA tensors (device),
+    raw integer addresses, or None; the tuples are sequences of ints or None.  Raises TTVError with the
+    reference's message on invalid arguments.  C is overwritten."""
+    lib = _lib.load()
+    if dtype is None:
+        probe = next((x for x in (a, b, c) if x is not None and not isinstance(x, int)), None)
+        if probe is None:
+            raise ValueError("dtype is required when a, b, c are raw addresses")
+        dtype = dtype_code(probe)
+    if opts is None:
+        if "stream" not in opt_kwargs:
+            dev = next((x for x in (a, b, c) if x is not None and _is_torch(x) and x.is_cuda), None)
+            if dev is not None:
+                opt_kwargs["stream"] = _current_torch_stream(dev)
+        opts = make_opts(**opt_kwargs)
+    keep = [_tuple(v) for v in (na, wa, pia, nb, nc, wc, pic)]
+    (na_, wa_, pia_, nb_, nc_, wc_, pic_) = [k[1] for k in keep]
+    st = lib.ttv_b200_run(dtype, q, p, _ptr(a), na_, wa_, pia_, _ptr(b), nb_, _ptr(c), nc_, wc_, pic_, C.byref(opts))
+    _check(st)
+
+
+def plan(q: int, na, pia, *, dtype="f32", wa=None, wc=None, pic=None, **opt_kwargs) -> dict:
+    """What the layout folder and the kernel chooser decide for (na, pia, q): pure host code, needs no GPU."""
+    lib = _lib.load()
+    p = len(na)
+    code = DTYPE_CODES[dtype] if isinstance(dtype, str) else int(dtype)
+    nc = generate_output_shape(na, q) if p > 1 else [1]
+    pic = list(pic) if pic is not None else (generate_output_layout(pia, q) if p > 1 else [1])
+    wa = list(wa) if wa is not None else generate_strides(na, pia)
+    wc = list(wc) if wc is not None else (generate_strides(nc, pic) if p > 1 else [1])
+    keep = [_tuple(v) for v in (na, wa, pia, [na[q - 1]], nc, wc, pic)]
+    (na_, wa_, pia_, nb_, nc_, wc_, pic_) = [k[1] for k in keep]
+    out = Plan()
+    opts = make_opts(**opt_kwargs)
+    one = C.c_void_p(16)   # any non-null value: plan never dereferences a, b, c
+    _check(lib.ttv_b200_plan(code, q, p, one, na_, wa_, pia_, one, nb_, one, nc_, wc_, pic_, C.byref(opts), C.byref(out)))
+    return out.as_dict()
+
+
+def plan_view(outer: int, nq: int, inner: int, *, dtype="f32", **opt_kwargs) -> dict:
+    lib = _lib.load()
+    code = DTYPE_CODES[dtype] if isinstance(dtype, str) else int(dtype)
+    out = Plan()
+    opts = make_opts(**opt_kwargs)
+    _check(lib.ttv_b200_plan_view(code, outer, nq, inner, C.byref(opts), C.byref(out)))
+    return out.as_dict()
+
+
+def ttv_view(outer: int, nq: int, inner: int, a, b, c, **opt_kwargs) -> None:
+    """C[outer][inner] = sum_k A[outer][k][inner] b[k] on DEVICE tensors (the canonical view every legal input folds to)."""
+    lib = _lib.load()
+    if "stream" not in opt_kwargs and _is_torch(a):
+        opt_kwargs["stream"] = _current_torch_stream(a)
+    opts = make_opts(**opt_kwargs)
+    _check(lib.ttv_b200_view(dtype_code(a), outer, nq, inner, _ptr(a), _ptr(b), _ptr(c), C.byref(opts)))
+
+
+def fill(x, seed: int, first: int = 0, count: int | None = None) -> None:
+    """x[i] = synth(seed, first + i) on the device (torch CUDA tensor, flat)."""
+    lib = _lib.load()
+    n = x.numel() if count is None else count
+    opts = make_opts(stream=_current_torch_stream(x))
+    _check(lib.ttv_b200_fill(dtype_code(x), _ptr(x), first, n, seed, C.byref(opts)))
+
+
+# ---- the tensor-level interface ----------------------------------------------------------------------------------------
+def _layout_of(x, layout) -> list[int]:
+    p = x.ndim
+    if layout is not None:
+        layout = [int(v) for v in layout]
+        if len(layout) != p:
+            raise TTVError(16, "Error in tlib::tensor: shape vector and layout vector must have the same length.")
+        return layout
+    # a C-contiguous array is a last-order tensor (what ttvpy assumes, wrapped_ttv.cpp:44-45); an F-contiguous one
+    # is a first-order tensor
+    if _is_torch(x):
+        if x.is_contiguous():
+            return generate_k_order_layout(p, 0)
+        if x.permute(*reversed(range(p))).is_contiguous():
+            return generate_k_order_layout(p, 1)
+    else:
+        if x.flags.c_contiguous:
+            return generate_k_order_layout(p, 0)
+        if x.flags.f_contiguous:
+            return generate_k_order_layout(p, 1)
+    raise TTVError(30, "Error in ttv_b200: the array is neither C- nor F-contiguous; pass a packed array.")
+
+
+def ttv(q: int, A, b, *, layout: Sequence[int] | None = None, out=None, **opt_kwargs):
+    """C = A x_q b (1-based q).  A: numpy array (host) or torch CUDA tensor of order p >= 2; b: vector of length
+    A.shape[q-1] of the same kind.  `layout` is the 1-based layout tuple of A's memory; by default it is derived from
+    the array's contiguity.  With an explicit `layout` A must be a FLAT buffer plus `shape=` in opt_kwargs.
+    Returns an array of the same kind with shape A.shape minus mode q, stored in the output layout."""
+    shape = opt_kwargs.pop("shape", None)
+    torch_in = _is_torch(A)
+    if shape is None:
+        shape = [int(s) for s in A.shape]
+        pia = _layout_of(A, layout)
+    else:
+        shape = [int(s) for s in shape]
+        pia = [int(v) for v in layout] if layout is not None else generate_k_order_layout(len(shape), 1)
+    p = len(shape)
+    if p == 0:
+        raise TTVError(1, _lib.load().ttv_b200_strerror(1).decode())
+    if q == 0 or q > p:
+        raise TTVError(2, _lib.load().ttv_b200_strerror(2).decode())
+    if p == 1:
+        raise TTVError(15, _lib.load().ttv_b200_strerror(15).decode())
+    nc = generate_output_shape(shape, q)
+    pic = generate_output_layout(pia, q)
+    wa = generate_strides(shape, pia)
+    wc = generate_strides(nc, pic)
+    n_out = int(np.prod(nc, dtype=object))
+    nb = [int(b.shape[0])] if b.ndim >= 1 else [1]
+
+    if torch_in:
+        import torch
+        if not A.is_cuda:
+            raise TTVError(40, "Error in ttv_b200: torch tensors must live on a CUDA device (there is no CPU fallback).")
+        flat_c = out if out is not None else torch.empty(n_out, dtype=A.dtype, device=A.device)
+    else:
+        A = np.asarray(A)
+        flat_c = out if out is not None else np.empty(n_out, dtype=A.dtype)
+    ttv_lowlevel(q, p, A, shape, wa, pia, b, nb, flat_c, nc, wc, pic, **opt_kwargs)
+    if out is not None:
+        return out
+    # hand the flat result back as an array of shape nc whose memory order is the output layout
+    order_slow_to_fast = [m - 1 for m in reversed(pic)]          # axes from slowest to fastest
+    packed_shape = [nc[ax] for ax in order_slow_to_fast]
+    inv = np.argsort(order_slow_to_fast)
+    if torch_in:
+        return flat_c.view(*packed_shape).permute(*[int(i) for i in inv])
+    return flat_c.reshape(packed_shape).transpose([int(i) for i in inv])
+
+
+def launch_count() -> int:
+    return int(_lib.load().ttv_b200_launch_count())
+
+
+def device_count() -> int:
+    return int(_lib.load().ttv_b200_device_count())

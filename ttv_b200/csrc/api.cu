@@ -1,0 +1,332 @@
+// api.cu -- the C-ABI of include/ttv_b200.h: validation, pointer classification, host staging, workspace, launch.
+//
+// This is the drop-in boundary for the reference's low-level interface tlib::ttv::ttv (include/tlib/ttv.h:54-92).
+// There is no CPU fallback: if no CUDA device can be used every compute entry returns TTV_B200_ERR_CUDA.
+#include "../../include/ttv_b200.h"
+#include "launch.h"
+#include "plan.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <utility>
+
+using namespace ttvb;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int status, const char* fmt = nullptr, ...)
+{
+  g_last_error = status_message(status);
+  if (fmt) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error += " [";
+    g_last_error += buf;
+    g_last_error += "]";
+  }
+  return status;
+}
+
+int fail_cuda(cudaError_t e, const char* what)
+{
+  cudaGetLastError();   // clear the sticky-less error state
+  return fail(TTV_B200_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define CUDA_TRY(expr, what) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return fail_cuda(e__, what); } while (0)
+
+// ---- per-device state ------------------------------------------------------------------------------------------
+struct Buffer {
+  void*  ptr = nullptr;
+  size_t bytes = 0;
+};
+
+struct DeviceState {
+  int sm_count = 0;
+  std::map<cudaStream_t, Buffer> workspace;   // split-n_q partials, one per stream so that streams do not share it
+  Buffer stage_a, stage_b, stage_c;           // staging for host-pointer calls
+};
+
+std::mutex g_mutex;
+std::map<int, DeviceState> g_devices;
+
+int device_state(int device, DeviceState** out)
+{
+  auto it = g_devices.find(device);
+  if (it == g_devices.end()) {
+    DeviceState st;
+    CUDA_TRY(cudaDeviceGetAttribute(&st.sm_count, cudaDevAttrMultiProcessorCount, device), "cudaDeviceGetAttribute");
+    it = g_devices.emplace(device, st).first;
+  }
+  *out = &it->second;
+  return TTV_B200_OK;
+}
+
+int ensure(Buffer& buf, size_t bytes)
+{
+  if (buf.bytes >= bytes && buf.ptr) return TTV_B200_OK;
+  if (buf.ptr) { cudaFree(buf.ptr); buf.ptr = nullptr; buf.bytes = 0; }
+  if (bytes == 0) bytes = 256;
+  CUDA_TRY(cudaMalloc(&buf.ptr, bytes), "cudaMalloc");
+  buf.bytes = bytes;
+  return TTV_B200_OK;
+}
+
+enum class Where { Host, Device };
+
+int classify(const void* p, Where* where, int* device)
+{
+  cudaPointerAttributes attr;
+  cudaError_t e = cudaPointerGetAttributes(&attr, p);
+  if (e != cudaSuccess) return fail_cuda(e, "cudaPointerGetAttributes (is a CUDA device visible?)");
+  if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) { *where = Where::Device; *device = attr.device; }
+  else { *where = Where::Host; *device = -1; }
+  return TTV_B200_OK;
+}
+
+uint64_t alignment_of(const void* p)
+{
+  const uintptr_t x = reinterpret_cast<uintptr_t>(p);
+  return x ? (uint64_t)(x & (~x + 1)) : 256;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool active = false;
+  cudaError_t set(int device) {
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess) return e;
+    if (prev != device) { e = cudaSetDevice(device); active = (e == cudaSuccess); }
+    return e;
+  }
+  ~DeviceGuard() { if (active) cudaSetDevice(prev); }
+};
+
+// runs the canonical view with device pointers on `device`
+int run_view_device(int dtype, const View& v, const void* a, const void* b, void* c, const ttv_b200_opts* opts,
+                    int device, bool sync)
+{
+  cudaStream_t stream = opts ? static_cast<cudaStream_t>(opts->stream) : nullptr;
+  const bool accumulate = opts && (opts->flags & TTV_B200_FLAG_ACCUMULATE);
+
+  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceState* st = nullptr;
+  if (int rc = device_state(device, &st)) return rc;
+
+  Launch l;
+  int rc = choose_launch(dtype, v, opts, alignment_of(a), alignment_of(b), alignment_of(c), st->sm_count, &l);
+  if (rc) return fail(rc);
+
+  void* ws = nullptr;
+  if (l.workspace_bytes) {
+    Buffer& buf = st->workspace[stream];
+    if (buf.bytes < l.workspace_bytes) {
+      // the old block may still be in use by work queued on this stream
+      if (buf.ptr) CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+      if (int r2 = ensure(buf, (size_t)l.workspace_bytes)) return r2;
+    }
+    ws = buf.ptr;
+  }
+  CUDA_TRY(launch_view(dtype, v, l, a, b, c, ws, accumulate, st->sm_count, stream), "kernel launch");
+  if (sync) CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+  return TTV_B200_OK;
+}
+
+// host pointers: H2D(A, b) -> kernel -> D2H(C), all on one stream, then wait
+int run_view_host(int dtype, const View& v, const void* a, const void* b, void* c, const ttv_b200_opts* opts)
+{
+  int device = opts ? opts->device : -1;
+  if (device < 0) CUDA_TRY(cudaGetDevice(&device), "cudaGetDevice (is a CUDA device visible?)");
+  DeviceGuard guard;
+  CUDA_TRY(guard.set(device), "cudaSetDevice");
+
+  const size_t s = (size_t)dtype_size(dtype);
+  const size_t bytes_a = (size_t)(v.outer * v.nq * v.inner) * s;
+  const size_t bytes_b = (size_t)v.nq * s;
+  const size_t bytes_c = (size_t)(v.outer * v.inner) * s;
+  cudaStream_t stream = opts ? static_cast<cudaStream_t>(opts->stream) : nullptr;
+  const bool accumulate = opts && (opts->flags & TTV_B200_FLAG_ACCUMULATE);
+
+  void *da = nullptr, *db = nullptr, *dc = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    DeviceState* st = nullptr;
+    if (int rc = device_state(device, &st)) return rc;
+    if (int rc = ensure(st->stage_a, bytes_a)) return rc;
+    if (int rc = ensure(st->stage_b, bytes_b)) return rc;
+    if (int rc = ensure(st->stage_c, bytes_c)) return rc;
+    da = st->stage_a.ptr; db = st->stage_b.ptr; dc = st->stage_c.ptr;
+  }
+  CUDA_TRY(cudaMemcpyAsync(da, a, bytes_a, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync H2D A");
+  CUDA_TRY(cudaMemcpyAsync(db, b, bytes_b, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync H2D b");
+  if (accumulate) CUDA_TRY(cudaMemcpyAsync(dc, c, bytes_c, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync H2D C");
+  if (int rc = run_view_device(dtype, v, da, db, dc, opts, device, false)) return rc;
+  CUDA_TRY(cudaMemcpyAsync(c, dc, bytes_c, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync D2H C");
+  CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+  return TTV_B200_OK;
+}
+
+int run_any(int dtype, const View& v, const void* a, const void* b, void* c, const ttv_b200_opts* opts)
+{
+  Where wa, wb, wc;
+  int da = -1, db = -1, dc = -1;
+  if (int rc = classify(a, &wa, &da)) return rc;
+  if (int rc = classify(b, &wb, &db)) return rc;
+  if (int rc = classify(c, &wc, &dc)) return rc;
+  if (wa != wb || wa != wc) return fail(TTV_B200_ERR_MIXED_POINTERS);
+  if (wa == Where::Host) return run_view_host(dtype, v, a, b, c, opts);
+  if (da != db || da != dc) return fail(TTV_B200_ERR_MIXED_POINTERS, "a, b, c live on devices %d, %d, %d", da, db, dc);
+  DeviceGuard guard;
+  CUDA_TRY(guard.set(da), "cudaSetDevice");
+  const bool async = opts && (opts->flags & TTV_B200_FLAG_ASYNC);
+  return run_view_device(dtype, v, a, b, c, opts, da, !async);
+}
+
+} // namespace
+
+// ================================================================================================================
+extern "C" {
+
+int ttv_b200_run(int dtype, uint64_t q, uint64_t p,
+                 const void* a, const uint64_t* na, const uint64_t* wa, const uint64_t* pia,
+                 const void* b, const uint64_t* nb,
+                 void* c, const uint64_t* nc, const uint64_t* wc, const uint64_t* pic,
+                 const ttv_b200_opts* opts)
+{
+  if (dtype_size(dtype) == 0) return fail(TTV_B200_ERR_DTYPE);
+  View v;
+  if (int rc = validate_and_fold(q, p, a, na, wa, pia, b, nb, c, nc, wc, pic, &v)) return fail(rc);
+  return run_any(dtype, v, a, b, c, opts);
+}
+
+#define TTV_B200_TYPED(NAME, CODE, CT)                                                                              \
+  int NAME(uint64_t q, uint64_t p, const CT* a, const uint64_t* na, const uint64_t* wa, const uint64_t* pia,        \
+           const CT* b, const uint64_t* nb, CT* c, const uint64_t* nc, const uint64_t* wc, const uint64_t* pic,     \
+           const ttv_b200_opts* opts)                                                                               \
+  { return ttv_b200_run(CODE, q, p, a, na, wa, pia, b, nb, c, nc, wc, pic, opts); }
+
+TTV_B200_TYPED(ttv_b200_f32,  TTV_B200_F32,  float)
+TTV_B200_TYPED(ttv_b200_f64,  TTV_B200_F64,  double)
+TTV_B200_TYPED(ttv_b200_c64,  TTV_B200_C64,  void)
+TTV_B200_TYPED(ttv_b200_c128, TTV_B200_C128, void)
+TTV_B200_TYPED(ttv_b200_i32,  TTV_B200_I32,  int32_t)
+TTV_B200_TYPED(ttv_b200_i64,  TTV_B200_I64,  int64_t)
+#undef TTV_B200_TYPED
+
+int ttv_b200_plan(int dtype, uint64_t q, uint64_t p,
+                  const void* a, const uint64_t* na, const uint64_t* wa, const uint64_t* pia,
+                  const void* b, const uint64_t* nb,
+                  const void* c, const uint64_t* nc, const uint64_t* wc, const uint64_t* pic,
+                  const ttv_b200_opts* opts, ttv_b200_plan_t* plan)
+{
+  if (dtype_size(dtype) == 0) return fail(TTV_B200_ERR_DTYPE);
+  View v;
+  if (int rc = validate_and_fold(q, p, a, na, wa, pia, b, nb, c, nc, wc, pic, &v)) return fail(rc);
+  Launch l;
+  if (int rc = choose_launch(dtype, v, opts, 256, 256, 256, 148, &l)) return fail(rc);
+  if (plan) fill_plan(dtype, v, l, plan);
+  return TTV_B200_OK;
+}
+
+int ttv_b200_plan_view(int dtype, uint64_t outer, uint64_t nq, uint64_t inner, const ttv_b200_opts* opts,
+                       ttv_b200_plan_t* plan)
+{
+  if (dtype_size(dtype) == 0) return fail(TTV_B200_ERR_DTYPE);
+  if (outer == 0 || nq == 0 || inner == 0) return fail(TTV_B200_ERR_SHAPE_A);
+  View v;
+  v.outer = outer; v.nq = nq; v.inner = inner;
+  v.k = 0; v.ref_case = inner == 1 ? 6 : (outer == 1 ? 7 : 8);
+  Launch l;
+  if (int rc = choose_launch(dtype, v, opts, 256, 256, 256, 148, &l)) return fail(rc);
+  if (plan) fill_plan(dtype, v, l, plan);
+  return TTV_B200_OK;
+}
+
+int ttv_b200_view(int dtype, uint64_t outer, uint64_t nq, uint64_t inner, const void* a, const void* b, void* c,
+                  const ttv_b200_opts* opts)
+{
+  if (dtype_size(dtype) == 0) return fail(TTV_B200_ERR_DTYPE);
+  if (outer == 0 || nq == 0 || inner == 0) return fail(TTV_B200_ERR_SHAPE_A);
+  if (!a) return fail(TTV_B200_ERR_A_NULL);
+  if (!b) return fail(TTV_B200_ERR_B_NULL);
+  if (!c) return fail(TTV_B200_ERR_C_NULL);
+  View v;
+  v.outer = outer; v.nq = nq; v.inner = inner;
+  v.k = 0; v.ref_case = inner == 1 ? 6 : (outer == 1 ? 7 : 8);
+  return run_any(dtype, v, a, b, c, opts);
+}
+
+int ttv_b200_fill(int dtype, void* x, uint64_t first, uint64_t count, uint64_t seed, const ttv_b200_opts* opts)
+{
+  if (dtype_size(dtype) == 0) return fail(TTV_B200_ERR_DTYPE);
+  if (!x) return fail(TTV_B200_ERR_A_NULL);
+  Where w; int dev = -1;
+  if (int rc = classify(x, &w, &dev)) return rc;
+  if (w != Where::Device) return fail(TTV_B200_ERR_MIXED_POINTERS, "ttv_b200_fill needs a device pointer");
+  DeviceGuard guard;
+  CUDA_TRY(guard.set(dev), "cudaSetDevice");
+  cudaStream_t stream = opts ? static_cast<cudaStream_t>(opts->stream) : nullptr;
+  int sm = 148;
+  {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    DeviceState* st = nullptr;
+    if (int rc = device_state(dev, &st)) return rc;
+    sm = st->sm_count;
+  }
+  CUDA_TRY(launch_fill(dtype, x, first, count, seed, sm, stream), "fill launch");
+  if (!(opts && (opts->flags & TTV_B200_FLAG_ASYNC))) CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+  return TTV_B200_OK;
+}
+
+// ---- L0 helpers ------------------------------------------------------------------------------------------------
+int ttv_b200_is_valid_shape(const uint64_t* n, uint64_t p)   { return n && is_valid_shape(n, p) ? 1 : 0; }
+int ttv_b200_is_valid_layout(const uint64_t* pi, uint64_t p) { return pi && is_valid_layout(pi, p) ? 1 : 0; }
+int ttv_b200_is_valid_strides(const uint64_t* pi, uint64_t p, const uint64_t* w)
+{
+  if (!pi || !w || !is_valid_layout(pi, p)) return -1;   // the reference throws here (strides.h:79-80)
+  return is_valid_strides(pi, p, w) ? 1 : 0;
+}
+int ttv_b200_compute_strides(const uint64_t* n, const uint64_t* pi, uint64_t p, uint64_t* w) { return compute_strides(n, pi, p, w); }
+int ttv_b200_output_shape(const uint64_t* na, uint64_t p, uint64_t q, uint64_t* nc)          { return output_shape(na, p, q, nc); }
+int ttv_b200_output_layout(const uint64_t* pia, uint64_t p, uint64_t q, uint64_t* pic)       { return output_layout(pia, p, q, pic); }
+int ttv_b200_k_order_layout(uint64_t p, uint64_t k, uint64_t* pi)                            { return k_order_layout(p, k, pi); }
+
+// ---- diagnostics ---------------------------------------------------------------------------------------------
+const char* ttv_b200_strerror(int status) { return status_message(status); }
+const char* ttv_b200_last_error(void)     { return g_last_error.c_str(); }
+int         ttv_b200_version(void)        { return TTV_B200_VERSION; }
+int         ttv_b200_dtype_size(int dtype) { return dtype_size(dtype); }
+uint64_t    ttv_b200_launch_count(void)   { return launch_count(); }
+
+int ttv_b200_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+void ttv_b200_release(void)
+{
+  std::lock_guard<std::mutex> lock(g_mutex);
+  for (auto& kv : g_devices) {
+    int prev = -1;
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); continue; }
+    cudaSetDevice(kv.first);
+    for (auto& w : kv.second.workspace) if (w.second.ptr) cudaFree(w.second.ptr);
+    kv.second.workspace.clear();
+    for (Buffer* b : {&kv.second.stage_a, &kv.second.stage_b, &kv.second.stage_c})
+      if (b->ptr) { cudaFree(b->ptr); b->ptr = nullptr; b->bytes = 0; }
+    cudaSetDevice(prev);
+  }
+}
+
+} // extern "C"

@@ -1,0 +1,18 @@
+// launch.h -- kernel launch entry points (implemented in launch.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include "plan.h"
+
+namespace ttvb {
+
+// Runs one TTV on the canonical view with DEVICE pointers.  `workspace` must hold l.workspace_bytes when l.ksplit > 1.
+cudaError_t launch_view(int dtype, const View& v, const Launch& l, const void* a, const void* b, void* c,
+                        void* workspace, bool accumulate, int sm_count, cudaStream_t stream);
+
+// x[i] = synth(seed, first + i) for i < count, on the device (same generator as oracle/ttv_oracle.c).
+cudaError_t launch_fill(int dtype, void* x, uint64_t first, uint64_t count, uint64_t seed, int sm_count, cudaStream_t stream);
+
+uint64_t launch_count();
+
+} // namespace ttvb

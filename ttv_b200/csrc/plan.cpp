@@ -1,0 +1,329 @@
+// plan.cpp -- argument validation, stride/layout folder, kernel chooser (pure host code).  See plan.h.
+#include "plan.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+namespace ttvb {
+
+// ---- dtypes -------------------------------------------------------------------------------------------------
+int dtype_size(int dtype)
+{
+  switch (dtype) {
+    case TTV_B200_F32:  return 4;
+    case TTV_B200_F64:  return 8;
+    case TTV_B200_C64:  return 8;
+    case TTV_B200_C128: return 16;
+    case TTV_B200_I32:  return 4;
+    case TTV_B200_I64:  return 8;
+    default: return 0;
+  }
+}
+int dtype_is_complex(int dtype) { return dtype == TTV_B200_C64 || dtype == TTV_B200_C128; }
+
+// ---- L0 helpers ---------------------------------------------------------------------------------------------
+// valid shape: at least one mode, no zero extent                                   (reference detail/shape.h:30-34)
+bool is_valid_shape(const uint64_t* n, uint64_t p)
+{
+  if (p == 0) return false;
+  return std::none_of(n, n + p, [](uint64_t x) { return x == 0; });
+}
+
+// valid layout: a permutation of 1..p                                             (reference detail/layout.h:29-55)
+bool is_valid_layout(const uint64_t* pi, uint64_t p)
+{
+  if (p == 0) return false;
+  for (uint64_t r = 0; r < p; ++r) {
+    if (pi[r] < 1 || pi[r] > p) return false;
+    if (std::find(pi + r + 1, pi + p, pi[r]) != pi + p) return false;
+  }
+  return true;
+}
+
+// strides never decrease when walking the modes in layout order                  (reference detail/strides.h:76-101)
+bool is_valid_strides(const uint64_t* pi, uint64_t p, const uint64_t* w)
+{
+  for (uint64_t r = 1; r < p; ++r)
+    if (w[pi[r] - 1] < w[pi[r - 1] - 1]) return false;
+  return true;
+}
+
+static bool rest_is_one(const uint64_t* n, uint64_t from, uint64_t p)
+{
+  return std::all_of(n + std::min(from, p), n + p, [](uint64_t x) { return x == 1; });
+}
+
+// Packed strides of (n, pi) -- except that scalar- and vector-shaped tensors get all-one strides, which is what the
+// reference hands out (detail/strides.h:42-45 with the shape predicates of detail/shape.h:38-63).
+int compute_strides(const uint64_t* n, const uint64_t* pi, uint64_t p, uint64_t* w)
+{
+  if (!is_valid_shape(n, p) || !is_valid_layout(pi, p)) return -1;
+  std::fill(w, w + p, uint64_t{1});
+  const bool scalar = rest_is_one(n, 0, p);
+  const bool vector = (p == 1 && n[0] > 1) ||
+                      (p >= 2 && (n[0] > 1 || n[1] > 1) && (n[0] == 1 || n[1] == 1) && rest_is_one(n, 2, p));
+  if (scalar || vector) return 0;
+  for (uint64_t r = 1; r < p; ++r) {
+    const uint64_t prev = pi[r - 1] - 1;
+    w[pi[r] - 1] = w[prev] * n[prev];
+  }
+  return 0;
+}
+
+// output shape = input shape without entry q                                     (reference detail/shape.h:103-123)
+int output_shape(const uint64_t* na, uint64_t p, uint64_t q, uint64_t* nc)
+{
+  if (!is_valid_shape(na, p) || q < 1 || q > p) return -1;
+  std::copy(na, na + (q - 1), nc);
+  std::copy(na + q, na + p, nc + (q - 1));
+  return 0;
+}
+
+// output layout = input layout without q, modes above q renumbered             (reference detail/layout.h:143-172)
+int output_layout(const uint64_t* pia, uint64_t p, uint64_t q, uint64_t* pic)
+{
+  if (!is_valid_layout(pia, p) || q < 1 || q > p) return -1;
+  uint64_t* out = pic;
+  for (uint64_t r = 0; r < p; ++r)
+    if (pia[r] != q) *out++ = pia[r] - (pia[r] > q ? 1 : 0);
+  return 0;
+}
+
+// k-order layout (k, k-1, .., 1, k+1, .., p); k = 0 or k > p => last-order        (reference detail/layout.h:57-76)
+int k_order_layout(uint64_t p, uint64_t k, uint64_t* pi)
+{
+  if (p == 0) return -1;
+  const uint64_t m = (k == 0 || k > p) ? p : k;
+  for (uint64_t r = 0; r < p; ++r) pi[r] = r < m ? m - r : r + 1;
+  return 0;
+}
+
+// the reference's 8 cases                                                         (reference detail/cases.h:24-36)
+int classify_case(uint64_t p, uint64_t q, const uint64_t* pia)
+{
+  if (p == 1) return 1;
+  if (p == 2) return pia[0] == 1 ? (q == 1 ? 2 : 3) : (q == 1 ? 4 : 5);
+  if (pia[0] == q) return 6;
+  if (pia[p - 1] == q) return 7;
+  return 8;
+}
+
+// ---- messages -----------------------------------------------------------------------------------------------
+const char* status_message(int status)
+{
+  switch (status) {
+    case TTV_B200_OK: return "ok";
+    case TTV_B200_ERR_ORDER_ZERO:      return "Error in tlib::tensor_times_vector: input tensor order should be greater zero.";
+    case TTV_B200_ERR_MODE:            return "Error in tlib::tensor_times_vector: contraction mode should be greater zero or less than or equal to p.";
+    case TTV_B200_ERR_A_NULL:          return "Error in tlib::tensor_times_vector: pointer to input tensor A should not be zero.";
+    case TTV_B200_ERR_B_NULL:          return "Error in tlib::tensor_times_vector: pointer to input vector B should not be zero.";
+    case TTV_B200_ERR_C_NULL:          return "Error in tlib::tensor_times_vector: pointer to output tensor C should not be zero.";
+    case TTV_B200_ERR_NA_NULL:         return "Error in tlib::tensor_times_vector: pointer to input tensor shape vector na should not be zero.";
+    case TTV_B200_ERR_NB_NULL:         return "Error in tlib::tensor_times_vector: pointer to input vector shape vector nb should not be zero.";
+    case TTV_B200_ERR_NC_NULL:         return "Error in tlib::tensor_times_vector: pointer to output tensor shape vector nc should not be zero.";
+    case TTV_B200_ERR_WA_NULL:         return "Error in tlib::tensor_times_vector: pointer to input tensor stride vector wa should not be zero.";
+    case TTV_B200_ERR_WC_NULL:         return "Error in tlib::tensor_times_vector: pointer to output tensor stride vector wc should not be zero.";
+    case TTV_B200_ERR_PIA_NULL:        return "Error in tlib::tensor_times_vector: pointer to input tensor permutation vector pia should not be zero.";
+    case TTV_B200_ERR_PIC_NULL:        return "Error in tlib::tensor_times_vector: pointer to output tensor permutation vector pic should not be zero.";
+    case TTV_B200_ERR_EXTENT_MISMATCH: return "Error in tlib::tensor_times_vector: contraction dimension of A and B are not equal.";
+    case TTV_B200_ERR_SHAPE_A:         return "Error in tlib::tensor_times_vector: shape vector of A is not valid.";
+    case TTV_B200_ERR_SHAPE_C:         return "Error in tlib::tensor_times_vector: shape vector of C is not valid.";
+    case TTV_B200_ERR_LAYOUT_A:        return "Error in tlib::tensor_times_vector: layout vector of A is not valid.";
+    case TTV_B200_ERR_LAYOUT_C:        return "Error in tlib::tensor_times_vector: layout vector of C is not valid.";
+    case TTV_B200_ERR_STRIDES_A:       return "Error in tlib::tensor_times_vector: stride vector of A is not valid.";
+    case TTV_B200_ERR_STRIDES_C:       return "Error in tlib::tensor_times_vector: stride vector of C is not valid.";
+    case TTV_B200_ERR_LAYOUT_BEGIN:    return "Error in tlib::detail::compute_inverse_pia_m: beginning of layout tuples of both tensors are not correct.";
+    case TTV_B200_ERR_LAYOUT_END:      return "Error in tlib::detail::compute_inverse_pia_m: end of layout tuples of both tensors are not correct.";
+    case TTV_B200_ERR_NOT_PACKED:      return "Error in ttv_b200: strides of A or C are not the packed strides of their shape and layout.";
+    case TTV_B200_ERR_DTYPE:           return "Error in ttv_b200: unknown element type.";
+    case TTV_B200_ERR_OPTS:            return "Error in ttv_b200: invalid options.";
+    case TTV_B200_ERR_CUDA:            return "Error in ttv_b200: CUDA failure (no CPU fallback exists).";
+    case TTV_B200_ERR_MIXED_POINTERS:  return "Error in ttv_b200: a, b and c must be all host or all device pointers.";
+    default: return "Error in ttv_b200: unknown status.";
+  }
+}
+
+// ---- validation + folding -----------------------------------------------------------------------------------
+int validate_and_fold(uint64_t q, uint64_t p,
+                      const void* a, const uint64_t* na, const uint64_t* wa, const uint64_t* pia,
+                      const void* b, const uint64_t* nb,
+                      const void* c, const uint64_t* nc, const uint64_t* wc, const uint64_t* pic,
+                      View* view)
+{
+  // the checks of the low-level interface in its order (reference ttv.h:64-89)
+  if (p == 0)                                 return TTV_B200_ERR_ORDER_ZERO;
+  if (q == 0 || q > p)                        return TTV_B200_ERR_MODE;
+  if (a == nullptr)                           return TTV_B200_ERR_A_NULL;
+  if (b == nullptr)                           return TTV_B200_ERR_B_NULL;
+  if (c == nullptr)                           return TTV_B200_ERR_C_NULL;
+  if (na == nullptr)                          return TTV_B200_ERR_NA_NULL;
+  if (nb == nullptr)                          return TTV_B200_ERR_NB_NULL;
+  if (nc == nullptr)                          return TTV_B200_ERR_NC_NULL;
+  if (wa == nullptr)                          return TTV_B200_ERR_WA_NULL;
+  if (wc == nullptr)                          return TTV_B200_ERR_WC_NULL;
+  if (pia == nullptr)                         return TTV_B200_ERR_PIA_NULL;
+  if (pic == nullptr)                         return TTV_B200_ERR_PIC_NULL;
+  if (na[q - 1] != nb[0])                     return TTV_B200_ERR_EXTENT_MISMATCH;
+  if (!is_valid_shape(na, p))                 return TTV_B200_ERR_SHAPE_A;
+  if (!is_valid_shape(nc, p - 1))             return TTV_B200_ERR_SHAPE_C;     // p == 1 always ends here
+  if (!is_valid_layout(pia, p))               return TTV_B200_ERR_LAYOUT_A;
+  if (!is_valid_layout(pic, p - 1))           return TTV_B200_ERR_LAYOUT_C;
+  if (!is_valid_strides(pia, p, wa))          return TTV_B200_ERR_STRIDES_A;
+  if (!is_valid_strides(pic, p - 1, wc))      return TTV_B200_ERR_STRIDES_C;
+  if (p > (uint64_t)kMaxOrder)                return TTV_B200_ERR_OPTS;
+
+  View v;
+  v.ref_case = (uint32_t)classify_case(p, q, pia);
+  uint64_t k = 0;
+  while (pia[k] != q) ++k;                    // 0-based position of q in the layout
+  v.k  = (uint32_t)(k + 1);
+  v.nq = na[q - 1];
+  for (uint64_t r = 0; r < k; ++r)     v.inner *= na[pia[r] - 1];
+  for (uint64_t r = k + 1; r < p; ++r) v.outer *= na[pia[r] - 1];
+
+  if (v.ref_case == 8) {
+    // C's layout must be A's layout without q (reference detail/tensor_times_vector.h:147-168).  In cases 1-7 the
+    // reference never looks at pic, wa, wc: it runs one GEMV on the packed tensor and writes C packed in the derived
+    // layout (detail/matrix_times_vector.h:314-336) -- and so does this library.
+    for (uint64_t i = 0; i < k; ++i)
+      if (pic[i] != pia[i] - (pia[i] > q ? 1 : 0)) return TTV_B200_ERR_LAYOUT_BEGIN;
+    for (uint64_t i = k; i + 1 < p; ++i)
+      if (pic[i] != pia[i + 1] - (pia[i + 1] > q ? 1 : 0)) return TTV_B200_ERR_LAYOUT_END;
+
+    // The loop nest of the reference walks A and C with wa / wc (tensor_times_vector.h:189-216) and asserts
+    // wa[q-1] == inner in the subtensor variants (:956).  Packed strides are the documented input (README.md:41);
+    // anything else is rejected instead of being silently mis-read.  Extent-1 modes may carry any stride.
+    uint64_t expect = 1;
+    for (uint64_t r = 0; r < p; ++r) {
+      const uint64_t m = pia[r] - 1;
+      if (na[m] > 1 && wa[m] != expect) return TTV_B200_ERR_NOT_PACKED;
+      expect *= na[m];
+    }
+    expect = 1;
+    for (uint64_t r = 0; r + 1 < p; ++r) {
+      const uint64_t mc = pic[r] - 1;                 // mode of C
+      const uint64_t ma = mc + (mc + 1 >= q ? 1 : 0); // the same mode in A
+      if (na[ma] > 1 && wc[mc] != expect) return TTV_B200_ERR_NOT_PACKED;
+      expect *= na[ma];
+    }
+  }
+  *view = v;
+  return TTV_B200_OK;
+}
+
+// ---- kernel chooser -----------------------------------------------------------------------------------------
+static uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+static uint64_t pow2_floor(uint64_t x) { uint64_t r = 1; while (r * 2 <= x) r *= 2; return r; }
+
+static int env_int(const char* name, int fallback)
+{
+  const char* s = std::getenv(name);
+  return (s && *s) ? std::atoi(s) : fallback;
+}
+
+int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t align_a, uint64_t align_b,
+                  uint64_t align_c, int sm_count, Launch* out)
+{
+  const uint64_t s = (uint64_t)dtype_size(dtype);
+  if (s == 0) return TTV_B200_ERR_DTYPE;
+  if (sm_count <= 0) sm_count = 148;
+  const uint32_t flags = opts ? opts->flags : 0u;
+  int forced = opts ? opts->kernel : 0;
+  if (forced < 0 || forced >= TTV_B200_KERNEL_COUNT) return TTV_B200_ERR_OPTS;
+  if (forced == TTV_B200_KERNEL_STREAM) forced = 0;   // not a separate kernel yet: falls back to the chooser
+
+  Launch l;
+  l.threads = (uint32_t)env_int("TTV_B200_THREADS", 256);
+  if (l.threads < 32 || l.threads > 256 || (l.threads % 32)) return TTV_B200_ERR_OPTS;
+  l.ku = env_int("TTV_B200_KU", 8);
+  if (l.ku != 1 && l.ku != 2 && l.ku != 4 && l.ku != 8 && l.ku != 16) return TTV_B200_ERR_OPTS;
+  const uint64_t NT = l.threads;
+  const uint64_t vmax = (flags & TTV_B200_FLAG_NO_VEC) ? 1 : std::max<uint64_t>(1, 16 / s);
+
+  const bool dot = (v.inner == 1) && forced != TTV_B200_KERNEL_COL;
+  if (forced == TTV_B200_KERNEL_DOT && v.inner != 1) return TTV_B200_ERR_OPTS;
+  l.kernel = dot ? TTV_B200_KERNEL_DOT : TTV_B200_KERNEL_COL;
+
+  uint64_t V = vmax;
+  if (dot) {
+    // vector along n_q: every fiber must start on a vector boundary and hold whole vectors
+    while (V > 1 && !((v.nq % V) == 0 && (align_a % (V * s)) == 0 && (align_b % (V * s)) == 0)) V /= 2;
+    const uint64_t kv = v.nq / V;                          // vector steps per fiber
+    l.tx = 1;
+    // one warp per fiber is the default; fewer lanes when the fiber is short
+    uint64_t ty = std::min<uint64_t>(32, pow2_floor(std::max<uint64_t>(1, kv / 2)));
+    // few fibers: put more lanes on each one, as long as every lane keeps at least four vectors
+    while (ty < NT && kv / (ty * 2) >= 4 && ceil_div(v.outer, std::max<uint64_t>(1, NT / ty)) < (uint64_t)sm_count * 4) ty *= 2;
+    const uint64_t to = std::max<uint64_t>(1, std::min<uint64_t>(NT / ty, v.outer));
+    l.ty = (uint32_t)ty; l.to = (uint32_t)to;
+    l.itiles = 1;
+  } else {
+    // vector along inner: rows must hold whole vectors and start on vector boundaries
+    while (V > 1 && !((v.inner % V) == 0 && (align_a % (V * s)) == 0 && (align_c % (V * s)) == 0)) V /= 2;
+    const uint64_t cv = v.inner / V;                       // vector columns
+    if (cv >= NT) { l.tx = (uint32_t)NT; l.ty = 1; l.to = 1; }
+    else {
+      l.tx = (uint32_t)cv;
+      const uint64_t rem = NT / cv;
+      uint64_t ty = 1;
+      if (v.inner * s < 128 && v.nq >= 8) ty = std::min<uint64_t>(rem, pow2_floor(v.nq / 4));   // short rows: lanes run along n_q too
+      uint64_t to = std::max<uint64_t>(1, std::min<uint64_t>(rem / ty, v.outer));
+      // few tiles: use the idle threads of the CTA along n_q
+      while (ty * 2 <= rem / to && v.nq / (ty * 2) >= 8 && ceil_div(v.outer, to) < (uint64_t)sm_count * 4) ty *= 2;
+      l.ty = (uint32_t)ty; l.to = (uint32_t)to;
+    }
+    l.itiles = ceil_div(cv, l.tx);
+  }
+  l.vec = (int)V;
+  l.otiles = ceil_div(v.outer, l.to);
+
+  // split n_q across CTAs when there are too few tiles to fill the machine
+  const uint64_t tiles0 = l.itiles * l.otiles;
+  const uint64_t target = (uint64_t)sm_count * 8;
+  const uint64_t kstep  = (uint64_t)l.ty * (dot ? V : 1);             // n_q elements one pass of the CTA covers
+  uint64_t ksplit = 1;
+  int want = opts ? opts->ksplit : 0;
+  if (want < 0) return TTV_B200_ERR_OPTS;
+  if (want == 0) want = env_int("TTV_B200_KSPLIT", 0);
+  if (want > 0) ksplit = (uint64_t)want;
+  else if (tiles0 * 2 <= target) {
+    const uint64_t max_split = std::max<uint64_t>(1, v.nq / (kstep * (uint64_t)l.ku * 2));
+    ksplit = std::min(ceil_div(target, tiles0), max_split);
+  }
+  ksplit = std::max<uint64_t>(1, std::min(ksplit, ceil_div(v.nq, kstep)));
+  uint64_t kchunk = ceil_div(ceil_div(v.nq, ksplit), kstep) * kstep;  // multiple of kstep keeps vectors aligned
+  ksplit = ceil_div(v.nq, kchunk);
+  l.ksplit = (uint32_t)ksplit;
+  l.kchunk = kchunk;
+  l.tiles  = tiles0 * ksplit;
+  l.ctas   = std::min<uint64_t>(l.tiles, (uint64_t)sm_count * 64);
+
+  // shared memory: a chunk of b (16 KB at most) + the cross-lane reduction scratch
+  uint64_t kb = std::min<uint64_t>(kchunk, 16384 / s);
+  kb = std::max<uint64_t>(kstep, kb / kstep * kstep);
+  if (kb * s > 96 * 1024) return TTV_B200_ERR_OPTS;
+  l.kb = (uint32_t)kb;
+  const uint64_t red_elems = NT * (dot ? 1 : V);
+  l.smem_bytes = kb * s + red_elems * s;
+  l.workspace_bytes = ksplit > 1 ? ksplit * v.outer * v.inner * s : 0;
+  *out = l;
+  return TTV_B200_OK;
+}
+
+void fill_plan(int dtype, const View& v, const Launch& l, ttv_b200_plan_t* plan)
+{
+  std::memset(plan, 0, sizeof *plan);
+  const uint64_t s = (uint64_t)dtype_size(dtype);
+  plan->outer = v.outer; plan->nq = v.nq; plan->inner = v.inner;
+  plan->k = v.k; plan->ref_case = v.ref_case;
+  plan->kernel = l.kernel; plan->vec = l.vec; plan->tx = (int32_t)l.tx; plan->ty = (int32_t)l.ty;
+  plan->ksplit = (int32_t)l.ksplit; plan->threads = (int32_t)l.threads; plan->ctas = l.ctas;
+  plan->smem_bytes = l.smem_bytes;
+  const uint64_t rest = v.outer * v.inner, total = rest * v.nq;
+  plan->algo_bytes = s * (total + v.nq + rest);
+  plan->algo_flops = (dtype_is_complex(dtype) ? 8 : 2) * total;
+  plan->workspace_bytes = l.workspace_bytes;
+}
+
+} // namespace ttvb

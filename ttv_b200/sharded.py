@@ -1,0 +1,108 @@
+"""Multi-GPU TTV on one node: one process per GPU, torch.distributed (NCCL over NVLink 5 / NVSwitch) for the plumbing.
+
+The reference is a single-process shared-memory library (OpenMP); it has no distributed path.  This module is the
+B200-native counterpart of its outer-loop parallelism (reference detail/tensor_times_vector.h:583-1351): instead of
+OpenMP threads over the free modes, GPUs over the slowest mode of the layout.
+
+Partitioning of a global tensor (na, pia) over G ranks, always along the SLOWEST mode pi_p of the layout,
+so that every rank owns one contiguous slab of A:
+
+  q != pi_p   free-mode split: the slab is itself a packed tensor with extent na[pi_p]/G in mode pi_p; every rank
+              computes its slab of C with the full b.  NO communication.
+  q == pi_p   n_q split: rank r holds rows [r*nq/G, (r+1)*nq/G) of the contraction mode and the matching slice of b,
+              computes a full-size partial C, and the partials are summed with ONE reduce / all-reduce (NCCL).
+              Integer sums are exact; float sums change order, which the n_q*eps tolerance covers.
+
+The arithmetic is always the C-ABI kernel on the local slab; nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Sequence
+
+
+@dataclass(frozen=True)
+class Shard:
+    """what one rank owns of the global problem"""
+    rank: int
+    world: int
+    mode: int                 # the split mode pi_p (1-based)
+    kind: str                 # "free" (no communication) or "nq" (partial C + reduce)
+    begin: int                # first index of the split mode on this rank
+    count: int                # number of indices of the split mode on this rank (may be 0 when world > extent)
+    na_local: tuple           # shape of the local slab
+    a_offset: int             # element offset of the slab inside the global A (packed strides)
+    a_count: int              # elements of the slab
+    c_offset: int             # element offset of the local C inside the global C (free split); 0 for the n_q split
+    c_count: int              # elements of the local C
+
+
+def split_range(extent: int, world: int, rank: int) -> tuple[int, int]:
+    """contiguous balanced ranges: the first extent % world ranks get one more"""
+    base, extra = divmod(extent, world)
+    begin = rank * base + min(rank, extra)
+    return begin, base + (1 if rank < extra else 0)
+
+
+def make_shard(q: int, na: Sequence[int], pia: Sequence[int], rank: int, world: int) -> Shard:
+    p = len(na)
+    if p < 2 or len(pia) != p or not (1 <= q <= p):
+        raise ValueError("make_shard: need order >= 2, a layout of the same length and 1 <= q <= p")
+    mode = int(pia[-1])
+    extent = int(na[mode - 1])
+    begin, count = split_range(extent, world, rank)
+    slab = 1
+    for m in pia[:-1]:
+        slab *= int(na[m - 1])          # elements per index of the slowest mode
+    na_local = list(int(x) for x in na)
+    na_local[mode - 1] = count
+    kind = "nq" if mode == q else "free"
+    if kind == "free":
+        c_per_index = slab // int(na[q - 1])
+        c_offset, c_count = begin * c_per_index, count * c_per_index
+    else:
+        c_offset, c_count = 0, slab
+    return Shard(rank, world, mode, kind, begin, count, tuple(na_local), begin * slab, count * slab, c_offset, c_count)
+
+
+def ttv_sharded(q: int, a_local, na: Sequence[int], pia: Sequence[int], b, *, rank: int, world: int, c_local=None,
+                group=None, reduce_to: int | None = 0, compute: Callable | None = None):
+    """One sharded TTV.  a_local: this rank's slab (flat, packed, see make_shard); b: the FULL vector (every rank
+    holds it; it is tiny).  Returns (c_local, shard):
+      free split  -> this rank's slab of C
+      n_q split   -> the reduced C on rank `reduce_to` (or on every rank when reduce_to is None); other ranks get
+                     their partial back
+    `compute(q, a, na_local, pia, b, c)` defaults to the C-ABI kernel; the gloo CPU tests inject a checker here to
+    exercise the partition arithmetic and the collective without a GPU."""
+    import torch
+    import torch.distributed as dist
+
+    sh = make_shard(q, na, pia, rank, world)
+    if compute is None:
+        from . import api
+
+        def compute(q_, a_, na_, pia_, b_, c_):
+            nc = api.generate_output_shape(na_, q_); pic = api.generate_output_layout(pia_, q_)
+            api.ttv_lowlevel(q_, len(na_), a_, na_, api.generate_strides(na_, pia_), pia_, b_, [int(b_.shape[0])], c_, nc,
+                             api.generate_strides(nc, pic), pic)
+
+    if c_local is None:
+        c_local = torch.empty(sh.c_count, dtype=a_local.dtype, device=a_local.device)
+    if sh.kind == "free":
+        if sh.count:
+            compute(q, a_local, list(sh.na_local), list(pia), b, c_local)
+        return c_local, sh
+
+    # n_q split
+    b_part = b[sh.begin: sh.begin + sh.count]
+    if sh.count:
+        compute(q, a_local, list(sh.na_local), list(pia), b_part, c_local)
+    else:
+        c_local.zero_()
+    if world > 1:
+        view = torch.view_as_real(c_local) if c_local.is_complex() else c_local     # complex reduces as 2x real
+        if reduce_to is None:
+            dist.all_reduce(view, op=dist.ReduceOp.SUM, group=group)
+        else:
+            dist.reduce(view, dst=reduce_to, op=dist.ReduceOp.SUM, group=group)
+    return c_local, sh

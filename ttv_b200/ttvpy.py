@@ -1,0 +1,103 @@
+"""Drop-in for the reference's Python binding `ttvpy` (reference ttvpy/src/wrapped_ttv.cpp), on the C-ABI.
+
+    ttv(q, A, b)                      one mode-q product                    wrapped_ttv.cpp:18-78
+    ttvs(q, A, bs, order="optimal")   the chain of p-1 products that leaves mode q; order in
+                                      {"optimal", "backward", "forward"}      wrapped_ttv.cpp:83-198
+
+Like the reference, A is read as a C-contiguous (last-order) array; unlike the reference (float64 only,
+wrapped_ttv.cpp:205-206) every element type of the C-ABI is accepted.  Errors the reference raises as
+std::invalid_argument surface as ValueError with the same text.
+
+ttvs keeps the intermediates in HBM: A and the vectors are uploaded once, the p-1 kernels run back to back on the
+device, and only the final vector is copied back.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import api
+
+__all__ = ["ttv", "ttvs", "chain_plan"]
+
+
+def _as_c_array(x):
+    a = np.asarray(x)
+    if a.dtype not in api._NP_CODES:
+        a = a.astype(np.float64)            # the reference binds double only and lets pybind11 convert
+    return np.ascontiguousarray(a)
+
+
+def ttv(q: int, A, b):
+    """Tensor-times-vector for the q-th mode (1-based) of a numpy array (host) or a torch CUDA tensor (device)."""
+    if api._is_torch(A):
+        p = A.dim()
+        if p == 0:
+            raise ValueError("Error calling ttvpy::ttv: input tensor order should be greater than zero.")
+        if q == 0 or q > p:
+            raise ValueError("Error calling ttvpy::ttv: contraction mode should be greater than zero or less than or equal to p.")
+        return api.ttv(q, A.contiguous(), b.contiguous())
+    A = _as_c_array(A)
+    b = np.ascontiguousarray(np.asarray(b), dtype=A.dtype)
+    p = A.ndim
+    if p == 0:
+        raise ValueError("Error calling ttvpy::ttv: input tensor order should be greater than zero.")
+    if q == 0 or q > p:
+        raise ValueError("Error calling ttvpy::ttv: contraction mode should be greater than zero or less than or equal to p.")
+    return np.ascontiguousarray(api.ttv(q, A, b))
+
+
+def chain_plan(q: int, shape, order: str = "optimal"):
+    """The sequence [(mode_to_contract, index_into_bs), ...] of the p-1 products, with modes renumbered after each
+    contraction (wrapped_ttv.cpp:144-192).  Pure host logic."""
+    p = len(shape)
+    # vector j (0-based) belongs to original mode r: r = j+1 if j+1 < q else j+2
+    modes = [(r, r - 1 if r < q else r - 2) for r in range(1, p + 1) if r != q]
+    if order == "backward":
+        seq = sorted(modes, key=lambda t: -t[0])
+    elif order == "forward":
+        seq = sorted(modes, key=lambda t: t[0])
+    else:  # "optimal": the longest vector first, so that the tensor shrinks as fast as possible
+        seq = sorted(modes, key=lambda t: (-int(shape[t[0] - 1]), t[0]))
+    out = []
+    alive = list(range(1, p + 1))           # original mode numbers still present, in order
+    for r, j in seq:
+        out.append((alive.index(r) + 1, j))
+        alive.remove(r)
+    return out
+
+
+def ttvs(q: int, A, bs, order: str = "optimal"):
+    """Multiplies A with p-1 vectors along every mode except q; returns the vector of length A.shape[q-1]."""
+    if order not in ("optimal", "backward", "forward"):
+        raise ValueError("Error calling ttvpy::ttvs: multiplication order should be either 'optimal', 'backward' or 'forward'.")
+    on_device = api._is_torch(A)
+    if not on_device:
+        A = _as_c_array(A)
+    p = A.ndim
+    if p == 0:
+        raise ValueError("Error calling ttvpy::ttvs: input tensor order should be greater than zero.")
+    if len(bs) != p - 1:
+        raise ValueError("Error calling ttvpy::ttvs: number of input vectors is not equal to the tensor order - 1.")
+    if q == 0 or q > p:
+        raise ValueError("Error calling ttvpy::ttvs: contraction mode should be greater than zero or less than or equal to p.")
+    if any(getattr(bj, "ndim", np.ndim(bj)) != 1 for bj in bs):
+        raise ValueError("Error calling ttvpy::ttvs: some of the input vectors is not a vector.")
+    shape = [int(s) for s in A.shape]
+    want = [shape[r - 1] for r in range(1, p + 1) if r != q]
+    if [int(bj.shape[0]) for bj in bs] != want:
+        raise ValueError("Error calling ttvpy::ttvs: vector dimension is not compatible with the dimension of a tensor mode.")
+    if p == 1:
+        return A
+
+    import torch
+    if on_device:
+        cur = A.contiguous()
+        vecs = [bj.contiguous() for bj in bs]
+    else:
+        if not torch.cuda.is_available():
+            raise api.TTVError(40, "Error in ttv_b200: CUDA failure (no CPU fallback exists). [no CUDA device]")
+        cur = torch.from_numpy(A).cuda()
+        vecs = [torch.from_numpy(np.ascontiguousarray(np.asarray(bj), dtype=A.dtype)).cuda() for bj in bs]
+    for mode, j in chain_plan(q, shape, order):
+        cur = api.ttv(mode, cur, vecs[j]).contiguous()      # output of a last-order tensor is last-order: no copy
+    return cur if on_device else cur.cpu().numpy()
