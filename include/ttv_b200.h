@@ -124,9 +124,11 @@ typedef struct ttv_b200_plan_t {
   uint32_t ref_case;    /* the reference's case 1..8 (include/tlib/detail/cases.h:24-36)                     */
   int32_t  kernel;      /* enum ttv_b200_kernel chosen                                                       */
   int32_t  vec;         /* elements per vector load                                                          */
-  int32_t  tx, ty;      /* thread tile: tx threads along inner, ty along n_q                                  */
+  int32_t  tx, ty, to;  /* thread tile: threads along inner / along n_q / along outer inside one CTA         */
+  int32_t  nu, ku;      /* loads in flight per thread: ku k-steps for each of nu independent outputs          */
   int32_t  ksplit;      /* n_q partitions (second pass reduces them when > 1)                                */
   int32_t  threads;     /* threads per CTA                                                                   */
+  int32_t  stream;      /* 1: A is loaded with L1::no_allocate                                               */
   uint64_t ctas;        /* grid size                                                                         */
   uint64_t smem_bytes;  /* dynamic shared memory per CTA                                                     */
   uint64_t algo_bytes;  /* sizeof(T) * (N + n_q + N/n_q): read A once, read b once, write C once             */

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Opts) == 40
-    assert C.sizeof(_lib.Plan) == 3 * 8 + 2 * 4 + 6 * 4 + 5 * 8
+    assert C.sizeof(_lib.Plan) == 3 * 8 + 2 * 4 + 10 * 4 + 5 * 8
 
 
 # ---- L0 helpers ------------------------------------------------------------------------------------------------------

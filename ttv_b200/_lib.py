@@ -25,7 +25,8 @@ class Plan(C.Structure):
     """struct ttv_b200_plan_t"""
     _fields_ = [("outer", C.c_uint64), ("nq", C.c_uint64), ("inner", C.c_uint64), ("k", C.c_uint32),
                 ("ref_case", C.c_uint32), ("kernel", C.c_int32), ("vec", C.c_int32), ("tx", C.c_int32),
-                ("ty", C.c_int32), ("ksplit", C.c_int32), ("threads", C.c_int32), ("ctas", C.c_uint64),
+                ("ty", C.c_int32), ("to", C.c_int32), ("nu", C.c_int32), ("ku", C.c_int32), ("ksplit", C.c_int32),
+                ("threads", C.c_int32), ("stream", C.c_int32), ("ctas", C.c_uint64),
                 ("smem_bytes", C.c_uint64), ("algo_bytes", C.c_uint64), ("algo_flops", C.c_uint64),
                 ("workspace_bytes", C.c_uint64)]
 
@@ -73,6 +74,15 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    override = os.environ.get("TTV_B200_LIB")       # experiments: an alternative build of the same library
+    if override:
+        lib = C.CDLL(override)
+        for name, (restype, argtypes) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+        return lib
     from . import build as _build
     try:
         if _build.stale():

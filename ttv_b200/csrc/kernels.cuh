@@ -7,17 +7,30 @@
 // Thread tile.  A CTA of `threads` threads is arranged as (to, ty, tx), tx fastest:
 //     tx  threads along inner (COL) -- each owns V contiguous outputs, so a warp reads a contiguous run of a row of A
 //     ty  threads along n_q         -- thread ty visits k = ty, ty+TY, ...   (DOT: vectors of V consecutive k)
-//     to  threads along outer       -- several slabs per CTA when one slab is smaller than the CTA
+//     to  threads along outer       -- several slabs / fibers per CTA when one of them is smaller than the CTA
 // When tx*V == inner the lanes (ty, tx) of a warp cover consecutive rows, i.e. one contiguous run of memory, which is
-// how small inner extents stay coalesced.  The ty partial sums are combined by warp shuffles (DOT, ty <= 32) or a
-// shared-memory tree; n_q partitions across CTAs (ksplit > 1) go to a workspace and are summed by ttv_reduce_kernel
-// in fixed order, so results are deterministic.
+// how small inner extents stay coalesced.
 //
-// Traffic: every element of A is loaded exactly once with ld.global.nc.L1::no_allocate (16 bytes when alignment
-// allows), b is staged in shared memory once per CTA (hoisted out of the tile loop when it fits), C is written once.
+// Loads in flight.  The path is HBM-bound, so what matters is bytes in flight per SM (Little's law: ~45 KB per SM at
+// 7+ TB/s).  Every thread issues one BATCH of NU x KU independent 16-byte loads before it consumes any of them:
+// KU steps along n_q for each of NU independent outputs ("units": further tiles along inner, or further slabs along
+// outer).  Short contractions (n_q = 2, 4, ...) therefore run with NU = 4 or 2 units instead of starving, and there is
+// no scalar remainder loop: the last batch is predicated.
+//
+// Reductions.  The ty partial sums of an output are combined by warp shuffles (DOT, ty <= 32) or a shared-memory
+// tree; n_q partitions across CTAs (ksplit > 1) go to a workspace and are summed by ttv_reduce_kernel in fixed order,
+// so results are deterministic.
+//
+// Traffic: every element of A is loaded exactly once (ld.global.nc, L1::no_allocate when a warp consumes whole
+// 128-byte lines by itself), b is staged in shared memory once per CTA (hoisted out of the tile loop when it fits),
+// C is written once.
 #pragma once
 
 #include "numeric.cuh"
+
+#ifndef TTVB_MIN_CTAS
+#define TTVB_MIN_CTAS 3      // CTAs of 256 threads per SM the register budget is planned for (3 -> 85 registers)
+#endif
 
 namespace ttvb {
 
@@ -28,22 +41,44 @@ struct TileParams {
   uint64_t outer, nq, inner;
   uint64_t kchunk;        // n_q elements per partition
   uint64_t itiles, otiles, tiles;
+  uint64_t a_ustride;     // elements between two units of one thread in A
+  uint64_t c_ustride;     // ... and in C
   uint32_t tx, ty, to;
   uint32_t ksplit;
   uint32_t kb;            // elements of b per shared-memory chunk
   uint32_t accumulate;    // C += (only honoured when ksplit == 1; otherwise the reduce pass does it)
+  uint32_t udir;          // units run along inner (0) or along outer (1)
+  uint32_t stream;        // 1: L1::no_allocate loads
 };
 
+template<class T, int V>
+__device__ __forceinline__ Vec<T, V> load_a(const T* p, bool stream)
+{
+  Vec<T, V> v;
+  if (stream) Ld<sizeof(T) * V>::nc(&v, p);
+  else        v = *reinterpret_cast<const Vec<T, V>*>(p);      // ld.global.nc through L1 (A is const __restrict__)
+  return v;
+}
+
+template<class T, int V>
+__device__ __forceinline__ Vec<T, V> zero_vec()
+{
+  Vec<T, V> v;
+#pragma unroll
+  for (int j = 0; j < V; ++j) v.e[j] = Num<T>::zero();
+  return v;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
-// COL: column GEMV, vector of V outputs along inner per thread.
+// COL: column GEMV, vector of V outputs along inner per thread and unit; NU units x KU k-steps in flight.
 // ------------------------------------------------------------------------------------------------------------------
-template<class T, int V, int KU>
-__global__ void __launch_bounds__(256, 4)
+template<class T, int V, int NU, int KU>
+__global__ void __launch_bounds__(256, TTVB_MIN_CTAS)
 ttv_col_kernel(const TileParams P)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sb  = reinterpret_cast<T*>(smem_raw);          // [kb]
-  T* red = sb + P.kb;                               // [threads][V]
+  T* red = sb + P.kb;                               // [threads][NU*V]
 
   const T* __restrict__ A = static_cast<const T*>(P.a);
   const T* __restrict__ B = static_cast<const T*>(P.b);
@@ -54,6 +89,7 @@ ttv_col_kernel(const TileParams P)
   const uint32_t ty  = (tid / P.tx) % P.ty;
   const uint32_t to  = tid / (P.tx * P.ty);
   const bool     live = to < P.to;
+  const bool     stream = P.stream != 0;
   const uint64_t kstride = (uint64_t)P.ty * P.inner;      // elements between two k visited by one thread
   const bool     b_resident = (P.ksplit == 1) && (P.nq <= P.kb);   // b fits: stage it once per CTA
 
@@ -67,15 +103,23 @@ ttv_col_kernel(const TileParams P)
     const uint64_t r  = tile / P.itiles;
     const uint32_t ks = (uint32_t)(r % P.ksplit);
     const uint64_t ot = r / P.ksplit;
-    const uint64_t o  = ot * P.to + to;
-    const uint64_t i0 = (it * P.tx + tx) * V;
-    const bool act = live && o < P.outer && i0 < P.inner;
+    // first unit of this thread; unit u adds u*tx*V along inner (udir 0) or u*to along outer (udir 1)
+    const uint64_t o  = (P.udir ? ot * NU : ot) * P.to + to;
+    const uint64_t i0 = ((P.udir ? it : it * NU) * P.tx + tx) * V;
+    int nvalid = 0;                                   // units [0, nvalid) of this thread exist
+    if (live && o < P.outer && i0 < P.inner) {
+      const uint64_t room = P.udir ? (P.outer - o + P.to - 1) / P.to
+                                   : (P.inner - i0 + (uint64_t)P.tx * V - 1) / ((uint64_t)P.tx * V);
+      nvalid = room < (uint64_t)NU ? (int)room : NU;
+    }
     const uint64_t kbeg = (uint64_t)ks * P.kchunk;
     const uint64_t kend = min(kbeg + P.kchunk, P.nq);
 
-    T acc[V];
+    T acc[NU][V];
 #pragma unroll
-    for (int j = 0; j < V; ++j) acc[j] = Num<T>::zero();
+    for (int u = 0; u < NU; ++u)
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[u][j] = Num<T>::zero();
 
     for (uint64_t k0 = kbeg; k0 < kend; k0 += P.kb) {
       const uint32_t kn = (uint32_t)min((uint64_t)P.kb, kend - k0);
@@ -84,70 +128,81 @@ ttv_col_kernel(const TileParams P)
         for (uint32_t j = tid; j < kn; j += blockDim.x) sb[j] = B[k0 + j];
         __syncthreads();
       }
-      if (act) {
+      if (nvalid > 0) {
         const T* ap = A + (o * P.nq + k0 + ty) * P.inner + i0;
-        uint32_t k = ty;
-        // main loop: KU independent vector loads in flight, then KU*V multiply-adds
-        for (; k + (KU - 1) * P.ty < kn; k += KU * P.ty, ap += KU * kstride) {
-          Vec<T, V> v[KU];
+        for (uint32_t k = ty; k < kn; k += KU * P.ty, ap += KU * kstride) {
+          Vec<T, V> v[NU][KU];
+          // one batch: NU*KU independent loads, predicated at the edges
 #pragma unroll
-          for (int u = 0; u < KU; ++u) v[u] = load_stream<T, V>(ap + u * kstride);
+          for (int u = 0; u < NU; ++u)
 #pragma unroll
-          for (int u = 0; u < KU; ++u) {
-            const T bb = sb[k + u * P.ty];
+            for (int s = 0; s < KU; ++s)
+              v[u][s] = (u < nvalid && k + s * P.ty < kn) ? load_a<T, V>(ap + u * P.a_ustride + s * kstride, stream)
+                                                          : zero_vec<T, V>();
 #pragma unroll
-            for (int j = 0; j < V; ++j) acc[j] = Num<T>::madd(v[u].e[j], bb, acc[j]);
+          for (int s = 0; s < KU; ++s) {
+            const T bb = (k + s * P.ty < kn) ? sb[k + s * P.ty] : Num<T>::zero();
+#pragma unroll
+            for (int u = 0; u < NU; ++u)
+#pragma unroll
+              for (int j = 0; j < V; ++j) acc[u][j] = Num<T>::madd(v[u][s].e[j], bb, acc[u][j]);
           }
-        }
-        for (; k < kn; k += P.ty, ap += kstride) {
-          const Vec<T, V> v = load_stream<T, V>(ap);
-          const T bb = sb[k];
-#pragma unroll
-          for (int j = 0; j < V; ++j) acc[j] = Num<T>::madd(v.e[j], bb, acc[j]);
         }
       }
     }
 
     // combine the ty partial sums of each output: shared-memory tree over ty
     if (P.ty > 1) {
+      T* mine = red + (size_t)tid * (NU * V);
       __syncthreads();
 #pragma unroll
-      for (int j = 0; j < V; ++j) red[tid * V + j] = acc[j];
+      for (int u = 0; u < NU; ++u)
+#pragma unroll
+        for (int j = 0; j < V; ++j) mine[u * V + j] = acc[u][j];
       __syncthreads();
       uint32_t span = 1;
       while (span < P.ty) span <<= 1;
       for (uint32_t h = span >> 1; h > 0; h >>= 1) {
         if (live && ty < h && ty + h < P.ty) {
+          const T* other = mine + (size_t)h * P.tx * (NU * V);
 #pragma unroll
-          for (int j = 0; j < V; ++j)
-            red[tid * V + j] = Num<T>::add(red[tid * V + j], red[(tid + h * P.tx) * V + j]);
+          for (int e = 0; e < NU * V; ++e) mine[e] = Num<T>::add(mine[e], other[e]);
         }
         __syncthreads();
       }
 #pragma unroll
-      for (int j = 0; j < V; ++j) acc[j] = red[tid * V + j];
+      for (int u = 0; u < NU; ++u)
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[u][j] = mine[u * V + j];
     }
 
-    if (act && ty == 0) {
+    if (ty == 0) {
       T* dst = C + (P.ksplit > 1 ? (uint64_t)ks * P.outer * P.inner : 0) + o * P.inner + i0;
-      Vec<T, V> outv;
-      if (P.accumulate && P.ksplit == 1) {
-        const Vec<T, V> old = *reinterpret_cast<const Vec<T, V>*>(dst);
 #pragma unroll
-        for (int j = 0; j < V; ++j) outv.e[j] = Num<T>::add(old.e[j], acc[j]);
-      } else {
+      for (int u = 0; u < NU; ++u) {
+        if (u < nvalid) {
+          Vec<T, V>* out = reinterpret_cast<Vec<T, V>*>(dst + u * P.c_ustride);
+          Vec<T, V> val;
+          if (P.accumulate && P.ksplit == 1) {
+            const Vec<T, V> old = *out;
 #pragma unroll
-        for (int j = 0; j < V; ++j) outv.e[j] = acc[j];
+            for (int j = 0; j < V; ++j) val.e[j] = Num<T>::add(old.e[j], acc[u][j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j) val.e[j] = acc[u][j];
+          }
+          *out = val;
+        }
       }
-      *reinterpret_cast<Vec<T, V>*>(dst) = outv;
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // DOT: mode q is the contiguous one (inner == 1).  ty lanes cooperate on one fiber with vectors of V consecutive k;
-// `to` fibers per CTA.  With ty <= 32 a fiber lives inside one warp and the partial sums are combined with
-// __shfl_xor_sync; larger ty uses the shared-memory tree.
+// a CTA holds `to` lane groups and every group works on NU fibers at once (NU*KU loads in flight per lane).  With
+// ty <= 32 a fiber lives inside one warp and the partial sums are combined with __shfl_xor_sync; larger ty (few, very
+// long fibers) uses the shared-memory tree.
 // ------------------------------------------------------------------------------------------------------------------
 template<class T>
 __device__ __forceinline__ T shfl_xor_elem(T v, int mask)
@@ -162,13 +217,13 @@ __device__ __forceinline__ T shfl_xor_elem(T v, int mask)
   return r;
 }
 
-template<class T, int V, int KU>
-__global__ void __launch_bounds__(256, 4)
+template<class T, int V, int NU, int KU>
+__global__ void __launch_bounds__(256, TTVB_MIN_CTAS)
 ttv_dot_kernel(const TileParams P)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sb  = reinterpret_cast<T*>(smem_raw);          // [kb]
-  T* red = sb + P.kb;                               // [threads]
+  T* red = sb + P.kb;                               // [threads][NU]
 
   const T* __restrict__ A = static_cast<const T*>(P.a);
   const T* __restrict__ B = static_cast<const T*>(P.b);
@@ -178,6 +233,7 @@ ttv_dot_kernel(const TileParams P)
   const uint32_t ty  = tid % P.ty;
   const uint32_t to  = tid / P.ty;
   const bool     live = to < P.to;
+  const bool     stream = P.stream != 0;
   const uint32_t kstep = P.ty * V;                   // n_q elements one pass of the fiber's lanes covers
   const bool     b_resident = (P.ksplit == 1) && (P.nq <= P.kb);
 
@@ -189,12 +245,18 @@ ttv_dot_kernel(const TileParams P)
   for (uint64_t tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
     const uint32_t ks = (uint32_t)(tile % P.ksplit);
     const uint64_t ot = tile / P.ksplit;
-    const uint64_t o  = ot * P.to + to;
-    const bool act = live && o < P.outer;
+    const uint64_t o  = ot * NU * P.to + to;         // fiber of unit 0; unit u is fiber o + u*to
+    int nvalid = 0;
+    if (live && o < P.outer) {
+      const uint64_t room = (P.outer - o + P.to - 1) / P.to;
+      nvalid = room < (uint64_t)NU ? (int)room : NU;
+    }
     const uint64_t kbeg = (uint64_t)ks * P.kchunk;
     const uint64_t kend = min(kbeg + P.kchunk, P.nq);
 
-    T acc = Num<T>::zero();
+    T acc[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) acc[u] = Num<T>::zero();
 
     for (uint64_t k0 = kbeg; k0 < kend; k0 += P.kb) {
       const uint32_t kn = (uint32_t)min((uint64_t)P.kb, kend - k0);   // multiple of V (nq % V == 0, kb % V == 0)
@@ -203,46 +265,60 @@ ttv_dot_kernel(const TileParams P)
         for (uint32_t j = tid; j < kn; j += blockDim.x) sb[j] = B[k0 + j];
         __syncthreads();
       }
-      if (act) {
+      if (nvalid > 0) {
         const T* ap = A + o * P.nq + k0 + (uint64_t)ty * V;
-        uint32_t k = ty * V;
-        for (; k + (KU - 1) * kstep < kn; k += KU * kstep, ap += KU * kstep) {
-          Vec<T, V> v[KU];
+        for (uint32_t k = ty * V; k < kn; k += KU * kstep, ap += KU * kstep) {
+          Vec<T, V> v[NU][KU];
 #pragma unroll
-          for (int u = 0; u < KU; ++u) v[u] = load_stream<T, V>(ap + u * kstep);
+          for (int u = 0; u < NU; ++u)
 #pragma unroll
-          for (int u = 0; u < KU; ++u) {
-            const Vec<T, V> bv = *reinterpret_cast<const Vec<T, V>*>(sb + k + u * kstep);
+            for (int s = 0; s < KU; ++s)
+              v[u][s] = (u < nvalid && k + s * kstep < kn) ? load_a<T, V>(ap + u * P.a_ustride + s * kstep, stream)
+                                                           : zero_vec<T, V>();
 #pragma unroll
-            for (int j = 0; j < V; ++j) acc = Num<T>::madd(v[u].e[j], bv.e[j], acc);
+          for (int s = 0; s < KU; ++s) {
+            const Vec<T, V> bv = (k + s * kstep < kn) ? *reinterpret_cast<const Vec<T, V>*>(sb + k + s * kstep)
+                                                      : zero_vec<T, V>();
+#pragma unroll
+            for (int u = 0; u < NU; ++u)
+#pragma unroll
+              for (int j = 0; j < V; ++j) acc[u] = Num<T>::madd(v[u][s].e[j], bv.e[j], acc[u]);
           }
-        }
-        for (; k < kn; k += kstep, ap += kstep) {
-          const Vec<T, V> v  = load_stream<T, V>(ap);
-          const Vec<T, V> bv = *reinterpret_cast<const Vec<T, V>*>(sb + k);
-#pragma unroll
-          for (int j = 0; j < V; ++j) acc = Num<T>::madd(v.e[j], bv.e[j], acc);
         }
       }
     }
 
     if (P.ty > 1 && P.ty <= 32) {
       // ty is a power of two <= 32 and divides the warp: butterfly inside the fiber's lane group
-      for (uint32_t h = P.ty >> 1; h > 0; h >>= 1) acc = Num<T>::add(acc, shfl_xor_elem(acc, (int)h));
+      for (uint32_t h = P.ty >> 1; h > 0; h >>= 1) {
+#pragma unroll
+        for (int u = 0; u < NU; ++u) acc[u] = Num<T>::add(acc[u], shfl_xor_elem(acc[u], (int)h));
+      }
     } else if (P.ty > 32) {
+      T* mine = red + (size_t)tid * NU;
       __syncthreads();
-      red[tid] = acc;
+#pragma unroll
+      for (int u = 0; u < NU; ++u) mine[u] = acc[u];
       __syncthreads();
       for (uint32_t h = P.ty >> 1; h > 0; h >>= 1) {     // ty is a power of two
-        if (live && ty < h) red[tid] = Num<T>::add(red[tid], red[tid + h]);
+        if (live && ty < h) {
+#pragma unroll
+          for (int u = 0; u < NU; ++u) mine[u] = Num<T>::add(mine[u], mine[(size_t)h * NU + u]);
+        }
         __syncthreads();
       }
-      acc = red[tid];
+#pragma unroll
+      for (int u = 0; u < NU; ++u) acc[u] = mine[u];
     }
 
-    if (act && ty == 0) {
+    if (ty == 0) {
       T* dst = C + (P.ksplit > 1 ? (uint64_t)ks * P.outer : 0) + o;
-      *dst = (P.accumulate && P.ksplit == 1) ? Num<T>::add(*dst, acc) : acc;
+#pragma unroll
+      for (int u = 0; u < NU; ++u)
+        if (u < nvalid) {
+          T* out = dst + (uint64_t)u * P.to;
+          *out = (P.accumulate && P.ksplit == 1) ? Num<T>::add(*out, acc[u]) : acc[u];
+        }
     }
   }
 }

@@ -1,13 +1,88 @@
-// launch.cu -- instantiates the kernels of kernels.cuh per (element type, vector width, unroll) and launches them.
+// launch.cu -- instantiates the kernels of kernels.cuh and launches them.
+//
+// Compiled several times by ttv_b200/build.py (in parallel):
+//   without TTVB_DTYPE   -> the dtype-independent part: launch_view / launch_fill / counters
+//   with -DTTVB_DTYPE=k  -> the kernels of element type k (enum ttv_b200_dtype) and their dispatcher
 #include "launch.h"
 #include "kernels.cuh"
 
+#include <algorithm>
 #include <atomic>
 
 namespace ttvb {
 
+// one dispatcher per element type, defined in the TTVB_DTYPE translation units
+using tile_fn_t   = cudaError_t (*)(const TileParams&, const Launch&, cudaStream_t);
+using reduce_fn_t = cudaError_t (*)(const void*, void*, uint64_t, uint32_t, bool, int, cudaStream_t);
+using fill_fn_t   = cudaError_t (*)(void*, uint64_t, uint64_t, uint64_t, int, cudaStream_t);
+
+#define TTVB_DECLARE(k)                                                                                          \
+  cudaError_t tile_dtype_##k(const TileParams&, const Launch&, cudaStream_t);                                    \
+  cudaError_t reduce_dtype_##k(const void*, void*, uint64_t, uint32_t, bool, int, cudaStream_t);                 \
+  cudaError_t fill_dtype_##k(void*, uint64_t, uint64_t, uint64_t, int, cudaStream_t);
+TTVB_DECLARE(0) TTVB_DECLARE(1) TTVB_DECLARE(2) TTVB_DECLARE(3) TTVB_DECLARE(4) TTVB_DECLARE(5)
+#undef TTVB_DECLARE
+
+void count_launch();
+
+#ifndef TTVB_DTYPE
+// ===================================================================================================================
 static std::atomic<uint64_t> g_launches{0};
 uint64_t launch_count() { return g_launches.load(); }
+void count_launch() { g_launches.fetch_add(1); }
+
+static const tile_fn_t   k_tile[]   = {tile_dtype_0, tile_dtype_1, tile_dtype_2, tile_dtype_3, tile_dtype_4, tile_dtype_5};
+static const reduce_fn_t k_reduce[] = {reduce_dtype_0, reduce_dtype_1, reduce_dtype_2, reduce_dtype_3, reduce_dtype_4, reduce_dtype_5};
+static const fill_fn_t   k_fill[]   = {fill_dtype_0, fill_dtype_1, fill_dtype_2, fill_dtype_3, fill_dtype_4, fill_dtype_5};
+
+cudaError_t launch_view(int dtype, const View& v, const Launch& l, const void* a, const void* b, void* c,
+                        void* workspace, bool accumulate, int sm_count, cudaStream_t stream)
+{
+  if (dtype < 0 || dtype >= TTV_B200_DTYPE_COUNT) return cudaErrorInvalidValue;
+  TileParams P;
+  P.a = a; P.b = b;
+  P.c = l.ksplit > 1 ? workspace : c;
+  P.outer = v.outer; P.nq = v.nq; P.inner = v.inner;
+  P.kchunk = l.kchunk;
+  P.itiles = l.itiles; P.otiles = l.otiles; P.tiles = l.tiles;
+  P.a_ustride = l.a_ustride; P.c_ustride = l.c_ustride;
+  P.tx = l.tx; P.ty = l.ty; P.to = l.to;
+  P.ksplit = l.ksplit; P.kb = l.kb;
+  P.accumulate = accumulate ? 1u : 0u;
+  P.udir = l.udir; P.stream = l.stream;
+
+  cudaError_t e = k_tile[dtype](P, l, stream);
+  if (e != cudaSuccess || l.ksplit <= 1) return e;
+  return k_reduce[dtype](workspace, c, v.outer * v.inner, l.ksplit, accumulate, sm_count, stream);
+}
+
+cudaError_t launch_fill(int dtype, void* x, uint64_t first, uint64_t count, uint64_t seed, int sm_count, cudaStream_t stream)
+{
+  if (dtype < 0 || dtype >= TTV_B200_DTYPE_COUNT) return cudaErrorInvalidValue;
+  if (count == 0) return cudaSuccess;
+  return k_fill[dtype](x, first, count, seed, sm_count, stream);
+}
+
+#else
+// ===================================================================================================================
+#if   TTVB_DTYPE == 0
+using elem_t = float;              constexpr int kVmax = 4;
+#elif TTVB_DTYPE == 1
+using elem_t = double;             constexpr int kVmax = 2;
+#elif TTVB_DTYPE == 2
+using elem_t = cf32;               constexpr int kVmax = 2;
+#elif TTVB_DTYPE == 3
+using elem_t = cf64;               constexpr int kVmax = 1;
+#elif TTVB_DTYPE == 4
+using elem_t = uint32_t;           constexpr int kVmax = 4;
+#elif TTVB_DTYPE == 5
+using elem_t = unsigned long long; constexpr int kVmax = 2;
+#else
+#error "unknown TTVB_DTYPE"
+#endif
+
+#define TTVB_CAT2(a, b) a##b
+#define TTVB_CAT(a, b)  TTVB_CAT2(a, b)
 
 template<class Kernel>
 static cudaError_t launch_tile(Kernel kern, const TileParams& P, const Launch& l, cudaStream_t stream)
@@ -17,92 +92,56 @@ static cudaError_t launch_tile(Kernel kern, const TileParams& P, const Launch& l
     if (e != cudaSuccess) return e;
   }
   kern<<<(unsigned)l.ctas, l.threads, l.smem_bytes, stream>>>(P);
-  g_launches.fetch_add(1);
+  count_launch();
   return cudaGetLastError();
 }
 
 template<class T, int V>
-static cudaError_t dispatch_ku(const TileParams& P, const Launch& l, cudaStream_t stream)
+static cudaError_t dispatch_batch(const TileParams& P, const Launch& l, cudaStream_t stream)
 {
-  const bool dot = l.kernel == TTV_B200_KERNEL_DOT;
+  if (l.kernel == TTV_B200_KERNEL_DOT) {
+    switch (l.ku) {
+      case 8:  return launch_tile(ttv_dot_kernel<T, V, 1, 8>, P, l, stream);
+      case 4:  return launch_tile(ttv_dot_kernel<T, V, 2, 4>, P, l, stream);
+      case 2:  return launch_tile(ttv_dot_kernel<T, V, 4, 2>, P, l, stream);
+      case 1:  return launch_tile(ttv_dot_kernel<T, V, 8, 1>, P, l, stream);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   switch (l.ku) {
-    case 1: case 2: case 4:
-      return dot ? launch_tile(ttv_dot_kernel<T, V, 4>, P, l, stream) : launch_tile(ttv_col_kernel<T, V, 4>, P, l, stream);
-    default:
-      return dot ? launch_tile(ttv_dot_kernel<T, V, 8>, P, l, stream) : launch_tile(ttv_col_kernel<T, V, 8>, P, l, stream);
+    case 8:  return launch_tile(ttv_col_kernel<T, V, 1, 8>, P, l, stream);
+    case 4:  return launch_tile(ttv_col_kernel<T, V, 2, 4>, P, l, stream);
+    case 2:  return launch_tile(ttv_col_kernel<T, V, 4, 2>, P, l, stream);
+    default: return cudaErrorInvalidValue;
   }
 }
 
-template<class T, int VMAX>
-static cudaError_t dispatch_vec(const TileParams& P, const Launch& l, cudaStream_t stream)
+cudaError_t TTVB_CAT(tile_dtype_, TTVB_DTYPE)(const TileParams& P, const Launch& l, cudaStream_t stream)
 {
-  if constexpr (VMAX >= 4) if (l.vec == 4) return dispatch_ku<T, 4>(P, l, stream);
-  if constexpr (VMAX >= 2) if (l.vec == 2) return dispatch_ku<T, 2>(P, l, stream);
-  if (l.vec == 1) return dispatch_ku<T, 1>(P, l, stream);
+  if (l.nu * l.ku != 8) return cudaErrorInvalidValue;
+  if constexpr (kVmax >= 4) if (l.vec == 4) return dispatch_batch<elem_t, 4>(P, l, stream);
+  if constexpr (kVmax >= 2) if (l.vec == 2) return dispatch_batch<elem_t, 2>(P, l, stream);
+  if (l.vec == 1) return dispatch_batch<elem_t, 1>(P, l, stream);
   return cudaErrorInvalidValue;
 }
 
-template<class T>
-static cudaError_t run_reduce(const void* ws, void* c, uint64_t n, uint32_t ksplit, bool accumulate, int sm_count, cudaStream_t stream)
+cudaError_t TTVB_CAT(reduce_dtype_, TTVB_DTYPE)(const void* ws, void* c, uint64_t n, uint32_t ksplit, bool accumulate,
+                                                 int sm_count, cudaStream_t stream)
 {
   const uint64_t blocks = std::min<uint64_t>((n + 255) / 256, (uint64_t)sm_count * 32);
-  ttv_reduce_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const T*>(ws), static_cast<T*>(c), n, ksplit, accumulate ? 1u : 0u);
-  g_launches.fetch_add(1);
+  ttv_reduce_kernel<elem_t><<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const elem_t*>(ws), static_cast<elem_t*>(c), n,
+                                                                  ksplit, accumulate ? 1u : 0u);
+  count_launch();
   return cudaGetLastError();
 }
 
-cudaError_t launch_view(int dtype, const View& v, const Launch& l, const void* a, const void* b, void* c,
-                        void* workspace, bool accumulate, int sm_count, cudaStream_t stream)
+cudaError_t TTVB_CAT(fill_dtype_, TTVB_DTYPE)(void* x, uint64_t first, uint64_t count, uint64_t seed, int sm_count, cudaStream_t stream)
 {
-  TileParams P;
-  P.a = a; P.b = b;
-  P.c = l.ksplit > 1 ? workspace : c;
-  P.outer = v.outer; P.nq = v.nq; P.inner = v.inner;
-  P.kchunk = l.kchunk;
-  P.itiles = l.itiles; P.otiles = l.otiles; P.tiles = l.tiles;
-  P.tx = l.tx; P.ty = l.ty; P.to = l.to;
-  P.ksplit = l.ksplit; P.kb = l.kb;
-  P.accumulate = accumulate ? 1u : 0u;
-
-  cudaError_t e;
-  switch (dtype) {
-    case TTV_B200_F32:  e = dispatch_vec<float, 4>(P, l, stream); break;
-    case TTV_B200_F64:  e = dispatch_vec<double, 2>(P, l, stream); break;
-    case TTV_B200_C64:  e = dispatch_vec<cf32, 2>(P, l, stream); break;
-    case TTV_B200_C128: e = dispatch_vec<cf64, 1>(P, l, stream); break;
-    case TTV_B200_I32:  e = dispatch_vec<uint32_t, 4>(P, l, stream); break;
-    case TTV_B200_I64:  e = dispatch_vec<unsigned long long, 2>(P, l, stream); break;
-    default: return cudaErrorInvalidValue;
-  }
-  if (e != cudaSuccess || l.ksplit <= 1) return e;
-
-  const uint64_t n = v.outer * v.inner;
-  switch (dtype) {
-    case TTV_B200_F32:  return run_reduce<float>(workspace, c, n, l.ksplit, accumulate, sm_count, stream);
-    case TTV_B200_F64:  return run_reduce<double>(workspace, c, n, l.ksplit, accumulate, sm_count, stream);
-    case TTV_B200_C64:  return run_reduce<cf32>(workspace, c, n, l.ksplit, accumulate, sm_count, stream);
-    case TTV_B200_C128: return run_reduce<cf64>(workspace, c, n, l.ksplit, accumulate, sm_count, stream);
-    case TTV_B200_I32:  return run_reduce<uint32_t>(workspace, c, n, l.ksplit, accumulate, sm_count, stream);
-    case TTV_B200_I64:  return run_reduce<unsigned long long>(workspace, c, n, l.ksplit, accumulate, sm_count, stream);
-    default: return cudaErrorInvalidValue;
-  }
-}
-
-cudaError_t launch_fill(int dtype, void* x, uint64_t first, uint64_t count, uint64_t seed, int sm_count, cudaStream_t stream)
-{
-  if (count == 0) return cudaSuccess;
   const unsigned blocks = (unsigned)std::min<uint64_t>((count + 255) / 256, (uint64_t)sm_count * 32);
-  switch (dtype) {
-    case TTV_B200_F32:  ttv_fill_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<float*>(x), first, count, seed); break;
-    case TTV_B200_F64:  ttv_fill_kernel<double><<<blocks, 256, 0, stream>>>(static_cast<double*>(x), first, count, seed); break;
-    case TTV_B200_C64:  ttv_fill_kernel<cf32><<<blocks, 256, 0, stream>>>(static_cast<cf32*>(x), first, count, seed); break;
-    case TTV_B200_C128: ttv_fill_kernel<cf64><<<blocks, 256, 0, stream>>>(static_cast<cf64*>(x), first, count, seed); break;
-    case TTV_B200_I32:  ttv_fill_kernel<uint32_t><<<blocks, 256, 0, stream>>>(static_cast<uint32_t*>(x), first, count, seed); break;
-    case TTV_B200_I64:  ttv_fill_kernel<unsigned long long><<<blocks, 256, 0, stream>>>(static_cast<unsigned long long*>(x), first, count, seed); break;
-    default: return cudaErrorInvalidValue;
-  }
-  g_launches.fetch_add(1);
+  ttv_fill_kernel<elem_t><<<blocks, 256, 0, stream>>>(static_cast<elem_t*>(x), first, count, seed);
+  count_launch();
   return cudaGetLastError();
 }
+#endif
 
 } // namespace ttvb

@@ -215,6 +215,7 @@ int validate_and_fold(uint64_t q, uint64_t p,
 // ---- kernel chooser -----------------------------------------------------------------------------------------
 static uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 static uint64_t pow2_floor(uint64_t x) { uint64_t r = 1; while (r * 2 <= x) r *= 2; return r; }
+static uint64_t pow2_ceil(uint64_t x) { uint64_t r = 1; while (r < x) r *= 2; return r; }
 
 static int env_int(const char* name, int fallback)
 {
@@ -228,6 +229,7 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
   const uint64_t s = (uint64_t)dtype_size(dtype);
   if (s == 0) return TTV_B200_ERR_DTYPE;
   if (sm_count <= 0) sm_count = 148;
+  const uint64_t sms = (uint64_t)sm_count;
   const uint32_t flags = opts ? opts->flags : 0u;
   int forced = opts ? opts->kernel : 0;
   if (forced < 0 || forced >= TTV_B200_KERNEL_COUNT) return TTV_B200_ERR_OPTS;
@@ -236,8 +238,6 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
   Launch l;
   l.threads = (uint32_t)env_int("TTV_B200_THREADS", 256);
   if (l.threads < 32 || l.threads > 256 || (l.threads % 32)) return TTV_B200_ERR_OPTS;
-  l.ku = env_int("TTV_B200_KU", 8);
-  if (l.ku != 1 && l.ku != 2 && l.ku != 4 && l.ku != 8 && l.ku != 16) return TTV_B200_ERR_OPTS;
   const uint64_t NT = l.threads;
   const uint64_t vmax = (flags & TTV_B200_FLAG_NO_VEC) ? 1 : std::max<uint64_t>(1, 16 / s);
 
@@ -246,65 +246,100 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
   l.kernel = dot ? TTV_B200_KERNEL_DOT : TTV_B200_KERNEL_COL;
 
   uint64_t V = vmax;
+  uint64_t units_avail = 1;           // how many units a thread could take (before n_q splitting)
   if (dot) {
     // vector along n_q: every fiber must start on a vector boundary and hold whole vectors
     while (V > 1 && !((v.nq % V) == 0 && (align_a % (V * s)) == 0 && (align_b % (V * s)) == 0)) V /= 2;
     const uint64_t kv = v.nq / V;                          // vector steps per fiber
     l.tx = 1;
-    // one warp per fiber is the default; fewer lanes when the fiber is short
-    uint64_t ty = std::min<uint64_t>(32, pow2_floor(std::max<uint64_t>(1, kv / 2)));
+    // lanes per fiber: about eight vectors per lane, at most one warp (a fiber then reduces with shuffles only)
+    uint64_t ty = std::min<uint64_t>(32, pow2_ceil(ceil_div(kv, 8)));
     // few fibers: put more lanes on each one, as long as every lane keeps at least four vectors
-    while (ty < NT && kv / (ty * 2) >= 4 && ceil_div(v.outer, std::max<uint64_t>(1, NT / ty)) < (uint64_t)sm_count * 4) ty *= 2;
+    while (ty < NT && kv / (ty * 2) >= 4 && ceil_div(v.outer, std::max<uint64_t>(1, NT / ty)) < sms * 2) ty *= 2;
     const uint64_t to = std::max<uint64_t>(1, std::min<uint64_t>(NT / ty, v.outer));
     l.ty = (uint32_t)ty; l.to = (uint32_t)to;
-    l.itiles = 1;
+    l.udir = 1;
+    units_avail = ceil_div(v.outer, to);
+    l.stream = ty >= 32 ? 1u : 0u;
   } else {
     // vector along inner: rows must hold whole vectors and start on vector boundaries
     while (V > 1 && !((v.inner % V) == 0 && (align_a % (V * s)) == 0 && (align_c % (V * s)) == 0)) V /= 2;
     const uint64_t cv = v.inner / V;                       // vector columns
-    if (cv >= NT) { l.tx = (uint32_t)NT; l.ty = 1; l.to = 1; }
-    else {
+    if (cv >= NT) {
+      l.tx = (uint32_t)NT; l.ty = 1; l.to = 1; l.udir = 0;
+      units_avail = ceil_div(cv, NT);
+      l.stream = 1;
+    } else {
       l.tx = (uint32_t)cv;
       const uint64_t rem = NT / cv;
       uint64_t ty = 1;
-      if (v.inner * s < 128 && v.nq >= 8) ty = std::min<uint64_t>(rem, pow2_floor(v.nq / 4));   // short rows: lanes run along n_q too
+      // short rows: lanes run along n_q too, so that a warp still reads one contiguous run of memory
+      if (v.inner * s < 128 && v.nq >= 16) ty = std::min<uint64_t>(rem, pow2_floor(v.nq / 8));
       uint64_t to = std::max<uint64_t>(1, std::min<uint64_t>(rem / ty, v.outer));
-      // few tiles: use the idle threads of the CTA along n_q
-      while (ty * 2 <= rem / to && v.nq / (ty * 2) >= 8 && ceil_div(v.outer, to) < (uint64_t)sm_count * 4) ty *= 2;
-      l.ty = (uint32_t)ty; l.to = (uint32_t)to;
+      // few slabs: use the idle threads of the CTA along n_q
+      while (ty * 2 <= rem / to && v.nq / (ty * 2) >= 8 && ceil_div(v.outer, to) < sms * 2) ty *= 2;
+      l.ty = (uint32_t)ty; l.to = (uint32_t)to; l.udir = 1;
+      units_avail = ceil_div(v.outer, to);
+      l.stream = (cv >= 32 || ty * cv >= 32) ? 1u : 0u;
     }
-    l.itiles = ceil_div(cv, l.tx);
   }
+  l.stream = (uint32_t)env_int("TTV_B200_STREAM", (int)l.stream);
   l.vec = (int)V;
-  l.otiles = ceil_div(v.outer, l.to);
 
-  // split n_q across CTAs when there are too few tiles to fill the machine
-  const uint64_t tiles0 = l.itiles * l.otiles;
-  const uint64_t target = (uint64_t)sm_count * 8;
-  const uint64_t kstep  = (uint64_t)l.ty * (dot ? V : 1);             // n_q elements one pass of the CTA covers
+  // split n_q across CTAs only when there are too few tiles to occupy the SMs at all
+  const uint64_t itiles1 = dot ? 1 : ceil_div(v.inner / V, l.tx);
+  const uint64_t otiles1 = ceil_div(v.outer, l.to);
+  const uint64_t tiles1  = itiles1 * otiles1;
+  const uint64_t kstep   = (uint64_t)l.ty * (dot ? V : 1);            // n_q elements one pass of the CTA covers
   uint64_t ksplit = 1;
   int want = opts ? opts->ksplit : 0;
   if (want < 0) return TTV_B200_ERR_OPTS;
   if (want == 0) want = env_int("TTV_B200_KSPLIT", 0);
   if (want > 0) ksplit = (uint64_t)want;
-  else if (tiles0 * 2 <= target) {
-    const uint64_t max_split = std::max<uint64_t>(1, v.nq / (kstep * (uint64_t)l.ku * 2));
-    ksplit = std::min(ceil_div(target, tiles0), max_split);
+  else if (tiles1 < sms) {
+    const uint64_t max_split = std::max<uint64_t>(1, v.nq / (kstep * 16));
+    ksplit = std::min(ceil_div(sms * 4, tiles1), max_split);
   }
   ksplit = std::max<uint64_t>(1, std::min(ksplit, ceil_div(v.nq, kstep)));
   uint64_t kchunk = ceil_div(ceil_div(v.nq, ksplit), kstep) * kstep;  // multiple of kstep keeps vectors aligned
   ksplit = ceil_div(v.nq, kchunk);
   l.ksplit = (uint32_t)ksplit;
   l.kchunk = kchunk;
-  l.tiles  = tiles0 * ksplit;
-  l.ctas   = std::min<uint64_t>(l.tiles, (uint64_t)sm_count * 64);
+
+  // batch shape: ku k-steps for each of nu units, nu*ku = 8 loads in flight per thread
+  const uint64_t per = ceil_div(std::min(kchunk, v.nq), kstep);       // k-steps one thread makes per unit
+  int ku = per >= 5 ? 8 : per >= 3 ? 4 : (per >= 2 || !dot) ? 2 : 1;
+  const int ku_env = env_int("TTV_B200_KU", 0);
+  if (ku_env == 8 || ku_env == 4 || ku_env == 2 || (ku_env == 1 && dot)) ku = ku_env;
+  l.ku = ku;
+  l.nu = 8 / ku;
+  (void)units_avail;   // units beyond the available ones are predicated off inside the kernel
+
+  if (dot) {
+    l.itiles = 1;
+    l.otiles = ceil_div(v.outer, (uint64_t)l.to * l.nu);
+    l.a_ustride = (uint64_t)l.to * v.nq;
+    l.c_ustride = l.to;
+  } else if (l.udir == 0) {
+    l.itiles = ceil_div(v.inner / V, (uint64_t)l.tx * l.nu);
+    l.otiles = v.outer;
+    l.a_ustride = (uint64_t)l.tx * V;
+    l.c_ustride = (uint64_t)l.tx * V;
+  } else {
+    l.itiles = 1;
+    l.otiles = ceil_div(v.outer, (uint64_t)l.to * l.nu);
+    l.a_ustride = (uint64_t)l.to * v.nq * v.inner;
+    l.c_ustride = (uint64_t)l.to * v.inner;
+  }
+  l.tiles = l.itiles * l.otiles * ksplit;
+  l.ctas  = std::min<uint64_t>(l.tiles, sms * 64);
 
   // shared memory: a chunk of b (16 KB at most) + the cross-lane reduction scratch
   uint64_t kb = std::min<uint64_t>(kchunk, 16384 / s);
   kb = std::max<uint64_t>(kstep, kb / kstep * kstep);
   if (kb * s > 96 * 1024) return TTV_B200_ERR_OPTS;
   l.kb = (uint32_t)kb;
-  const uint64_t red_elems = NT * (dot ? 1 : V);
+  const uint64_t red_elems = NT * (uint64_t)l.nu * (dot ? 1 : V);
   l.smem_bytes = kb * s + red_elems * s;
   l.workspace_bytes = ksplit > 1 ? ksplit * v.outer * v.inner * s : 0;
   *out = l;
@@ -317,7 +352,8 @@ void fill_plan(int dtype, const View& v, const Launch& l, ttv_b200_plan_t* plan)
   const uint64_t s = (uint64_t)dtype_size(dtype);
   plan->outer = v.outer; plan->nq = v.nq; plan->inner = v.inner;
   plan->k = v.k; plan->ref_case = v.ref_case;
-  plan->kernel = l.kernel; plan->vec = l.vec; plan->tx = (int32_t)l.tx; plan->ty = (int32_t)l.ty;
+  plan->kernel = l.kernel; plan->vec = l.vec; plan->tx = (int32_t)l.tx; plan->ty = (int32_t)l.ty; plan->to = (int32_t)l.to;
+  plan->nu = l.nu; plan->ku = l.ku; plan->stream = (int32_t)l.stream;
   plan->ksplit = (int32_t)l.ksplit; plan->threads = (int32_t)l.threads; plan->ctas = l.ctas;
   plan->smem_bytes = l.smem_bytes;
   const uint64_t rest = v.outer * v.inner, total = rest * v.nq;

@@ -28,7 +28,11 @@ struct View {
 struct Launch {
   int      kernel  = TTV_B200_KERNEL_COL;
   int      vec     = 1;     // elements per vector load (along inner for COL, along n_q for DOT)
-  int      ku      = 8;     // unroll = independent vector loads in flight per thread
+  int      ku      = 8;     // k-steps of one unit in flight per thread
+  int      nu      = 1;     // independent units (outputs) per thread; nu*ku vector loads are in flight per thread
+  uint32_t udir    = 0;     // units run along inner (0) or along outer (1)
+  uint32_t stream  = 1;     // L1::no_allocate loads (a warp consumes whole lines by itself)
+  uint64_t a_ustride = 0, c_ustride = 0;   // element distance between two units in A / C
   uint32_t tx = 1, ty = 1, to = 1;   // threads along inner / along n_q / along outer inside one CTA
   uint32_t threads = 256;
   uint32_t ksplit  = 1;     // n_q partitions across CTAs; > 1 => partials in the workspace + reduce pass
