@@ -3,6 +3,7 @@
 #pragma once
 
 #include <algorithm>
+#include <cassert>
 #include <array>
 #include <cstddef>
 #include <iterator>

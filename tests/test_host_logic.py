@@ -211,3 +211,28 @@ def test_chain_plan_orders():
     # optimal: longest vector first
     assert chain_plan(1, (3, 2, 4, 5), "optimal") == [(4, 2), (3, 1), (2, 0)]
     assert chain_plan(4, (3, 9, 4, 5), "optimal") == [(2, 1), (2, 2), (1, 0)]
+
+
+def test_chooser_only_picks_instantiated_kernels():
+    """fuzz of the canonical view: the (nu, ku) batch shape must be one the dispatcher instantiates (launch.cu), the
+    thread tile must fit the CTA, vectors must divide the extent they run along"""
+    import random
+    rng = random.Random(1)
+    size = {"f32": 4, "f64": 8, "c64": 8, "c128": 16, "i32": 4, "i64": 8}
+    for dt in size:
+        for _ in range(1500):
+            outer = rng.choice([1, 2, 3, 7, 100, 5000, 10 ** 6, 10 ** 8])
+            nq = rng.choice([1, 2, 3, 4, 5, 8, 16, 21, 23, 64, 215, 512, 1625, 4096, 65536, 10 ** 6])
+            inner = rng.choice([1, 1, 2, 3, 4, 6, 16, 21, 23, 64, 100, 512, 1625, 65536, 10 ** 6])
+            pl = ttv_b200.plan_view(outer, nq, inner, dtype=dt)
+            wide = pl["vec"] * size[dt] >= 16
+            key = (pl["nu"], pl["ku"])
+            if pl["kernel"] == 1:
+                allowed = {(1, 8), (2, 4), (4, 2), (8, 1)} if wide else {(1, 16), (2, 8), (4, 4), (8, 2), (8, 1)}
+            else:
+                allowed = {(1, 8), (2, 4), (4, 2)} if wide else {(1, 16), (2, 8), (4, 4), (8, 2)}
+            assert key in allowed, (dt, outer, nq, inner, pl)
+            assert pl["tx"] * pl["ty"] * pl["to"] <= pl["threads"] <= 256
+            assert pl["ksplit"] >= 1 and pl["ctas"] >= 1 and pl["smem_bytes"] <= 100 * 1024
+            if pl["kernel"] == 2:
+                assert inner % pl["vec"] == 0

@@ -90,6 +90,9 @@ def main():
     ap.add_argument("--set", default="quick")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.jsonl"))
     ap.add_argument("--variants", action="store_true", help="also sweep threads / unroll / ksplit on each config")
+    ap.add_argument("--only", default="", help="comma-separated config names to keep")
+    ap.add_argument("--envs", default="", help="semicolon-separated env variants, e.g. 'TTV_B200_STREAM=0;TTV_B200_KU=4,TTV_B200_THREADS=128'")
+    ap.add_argument("--reps", type=int, default=10)
     args = ap.parse_args()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     peak = 6553.9
@@ -99,7 +102,11 @@ def main():
         pass
     with open(args.out, "a") as f:
         for name, dt, na, pia, q in configs(args.set):
+            if args.only and name not in args.only.split(","):
+                continue
             variants = [dict()]
+            for spec in [e for e in args.envs.split(";") if e]:
+                variants.append(dict(env=dict(kv.split("=") for kv in spec.split(","))))
             if args.variants:
                 variants += [dict(env=dict(TTV_B200_THREADS=t, TTV_B200_KU=ku), ksplit=ks)
                              for t in ("128", "256") for ku in ("4", "8") for ks in (0, 1, 2, 4)]
@@ -110,7 +117,7 @@ def main():
                 opts = {k: v for k, v in var.items() if k != "env"}
                 try:
                     pl = ttv_b200.plan(q, na, pia, dtype=dt, **opts)
-                    r = bench_one(dt, na, pia, q, **opts)
+                    r = bench_one(dt, na, pia, q, reps=args.reps, **opts)
                 except Exception as exc:
                     r, pl = {"error": str(exc)}, {}
                 for k in env:

@@ -12,27 +12,30 @@
 // how small inner extents stay coalesced.
 //
 // Loads in flight.  The path is HBM-bound, so what matters is bytes in flight per SM (Little's law: ~45 KB per SM at
-// 7+ TB/s).  Every thread issues one BATCH of NU x KU independent 16-byte loads before it consumes any of them:
-// KU steps along n_q for each of NU independent outputs ("units": further tiles along inner, or further slabs along
-// outer).  Short contractions (n_q = 2, 4, ...) therefore run with NU = 4 or 2 units instead of starving, and there is
-// no scalar remainder loop: the last batch is predicated.
+// 7+ TB/s).  Every thread issues one BATCH of NU x KU independent loads (128 bytes with 16-byte vectors) before it
+// consumes any of them: KU steps along n_q for each of NU independent outputs ("units": further tiles along inner, or
+// further slabs / fibers along outer).  Short contractions (n_q = 2, 4, ...) therefore run with more units instead of
+// starving.  Full batches take an unpredicated fast path; the edges (last batch, last tile) are predicated -- there is
+// no scalar remainder loop.
 //
 // Reductions.  The ty partial sums of an output are combined by warp shuffles (DOT, ty <= 32) or a shared-memory
 // tree; n_q partitions across CTAs (ksplit > 1) go to a workspace and are summed by ttv_reduce_kernel in fixed order,
 // so results are deterministic.
 //
-// Traffic: every element of A is loaded exactly once (ld.global.nc, L1::no_allocate when a warp consumes whole
-// 128-byte lines by itself), b is staged in shared memory once per CTA (hoisted out of the tile loop when it fits),
-// C is written once.
+// Traffic: every element of A is loaded exactly once, b is staged in shared memory once per CTA (hoisted out of the
+// tile loop when it fits), C is written once.
 #pragma once
 
 #include "numeric.cuh"
 
-#ifndef TTVB_MIN_CTAS
-#define TTVB_MIN_CTAS 3      // CTAs of 256 threads per SM the register budget is planned for (3 -> 85 registers)
-#endif
-
 namespace ttvb {
+
+// CTAs of 256 threads per SM the register budget is planned for: 4 -> 64 registers, 3 -> 80, 2 -> 128.
+#ifdef TTVB_MIN_CTAS
+template<int NU, int KU> constexpr int min_ctas() { return TTVB_MIN_CTAS; }
+#else
+template<int NU, int KU> constexpr int min_ctas() { return 3; }
+#endif
 
 struct TileParams {
   const void* a;
@@ -56,7 +59,7 @@ __device__ __forceinline__ Vec<T, V> load_a(const T* p, bool stream)
 {
   Vec<T, V> v;
   if (stream) Ld<sizeof(T) * V>::nc(&v, p);
-  else        v = *reinterpret_cast<const Vec<T, V>*>(p);      // ld.global.nc through L1 (A is const __restrict__)
+  else        v = *reinterpret_cast<const Vec<T, V>*>(p);      // read-only path through L1 (A is const __restrict__)
   return v;
 }
 
@@ -72,8 +75,34 @@ __device__ __forceinline__ Vec<T, V> zero_vec()
 // ------------------------------------------------------------------------------------------------------------------
 // COL: column GEMV, vector of V outputs along inner per thread and unit; NU units x KU k-steps in flight.
 // ------------------------------------------------------------------------------------------------------------------
+template<class T, int V, int NU, int KU, bool PRED>
+__device__ __forceinline__ void col_batch(T (&acc)[NU][V], const T* ap, uint64_t a_ustride, uint64_t kstride, const T* sb,
+                                          uint32_t k, uint32_t tyn, uint32_t kn, int nvalid, bool stream)
+{
+  Vec<T, V> v[NU][KU];
+#pragma unroll
+  for (int u = 0; u < NU; ++u)
+#pragma unroll
+    for (int s = 0; s < KU; ++s) {
+      if constexpr (PRED)
+        v[u][s] = (u < nvalid && k + s * tyn < kn) ? load_a<T, V>(ap + u * a_ustride + s * kstride, stream) : zero_vec<T, V>();
+      else
+        v[u][s] = load_a<T, V>(ap + u * a_ustride + s * kstride, stream);
+    }
+#pragma unroll
+  for (int s = 0; s < KU; ++s) {
+    T bb;
+    if constexpr (PRED) bb = (k + s * tyn < kn) ? sb[k + s * tyn] : Num<T>::zero();
+    else bb = sb[k + s * tyn];
+#pragma unroll
+    for (int u = 0; u < NU; ++u)
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[u][j] = Num<T>::madd(v[u][s].e[j], bb, acc[u][j]);
+  }
+}
+
 template<class T, int V, int NU, int KU>
-__global__ void __launch_bounds__(256, TTVB_MIN_CTAS)
+__global__ void __launch_bounds__(256, min_ctas<NU, KU>())
 ttv_col_kernel(const TileParams P)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -130,24 +159,12 @@ ttv_col_kernel(const TileParams P)
       }
       if (nvalid > 0) {
         const T* ap = A + (o * P.nq + k0 + ty) * P.inner + i0;
-        for (uint32_t k = ty; k < kn; k += KU * P.ty, ap += KU * kstride) {
-          Vec<T, V> v[NU][KU];
-          // one batch: NU*KU independent loads, predicated at the edges
-#pragma unroll
-          for (int u = 0; u < NU; ++u)
-#pragma unroll
-            for (int s = 0; s < KU; ++s)
-              v[u][s] = (u < nvalid && k + s * P.ty < kn) ? load_a<T, V>(ap + u * P.a_ustride + s * kstride, stream)
-                                                          : zero_vec<T, V>();
-#pragma unroll
-          for (int s = 0; s < KU; ++s) {
-            const T bb = (k + s * P.ty < kn) ? sb[k + s * P.ty] : Num<T>::zero();
-#pragma unroll
-            for (int u = 0; u < NU; ++u)
-#pragma unroll
-              for (int j = 0; j < V; ++j) acc[u][j] = Num<T>::madd(v[u][s].e[j], bb, acc[u][j]);
-          }
-        }
+        uint32_t k = ty;
+        if (nvalid == NU)
+          for (; k + (KU - 1) * P.ty < kn; k += KU * P.ty, ap += KU * kstride)          // full batches
+            col_batch<T, V, NU, KU, false>(acc, ap, P.a_ustride, kstride, sb, k, P.ty, kn, nvalid, stream);
+        for (; k < kn; k += KU * P.ty, ap += KU * kstride)                              // edges
+          col_batch<T, V, NU, KU, true>(acc, ap, P.a_ustride, kstride, sb, k, P.ty, kn, nvalid, stream);
       }
     }
 
@@ -217,8 +234,72 @@ __device__ __forceinline__ T shfl_xor_elem(T v, int mask)
   return r;
 }
 
+// combines the ty partial sums of NU fibers and stores them (shared by the two DOT kernels)
+template<class T, int NU>
+__device__ __forceinline__ void dot_finish(T (&acc)[NU], const TileParams& P, T* red, T* C, uint32_t tid, uint32_t ty, bool live,
+                                           uint64_t o, uint32_t ks, int nvalid)
+{
+  if (P.ty > 1 && P.ty <= 32) {
+    // ty is a power of two <= 32 and divides the warp: butterfly inside the fiber's lane group
+    for (uint32_t h = P.ty >> 1; h > 0; h >>= 1) {
+#pragma unroll
+      for (int u = 0; u < NU; ++u) acc[u] = Num<T>::add(acc[u], shfl_xor_elem(acc[u], (int)h));
+    }
+  } else if (P.ty > 32) {
+    T* mine = red + (size_t)tid * NU;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < NU; ++u) mine[u] = acc[u];
+    __syncthreads();
+    for (uint32_t h = P.ty >> 1; h > 0; h >>= 1) {     // ty is a power of two
+      if (live && ty < h) {
+#pragma unroll
+        for (int u = 0; u < NU; ++u) mine[u] = Num<T>::add(mine[u], mine[(size_t)h * NU + u]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < NU; ++u) acc[u] = mine[u];
+  }
+  if (ty == 0) {
+    T* dst = C + (P.ksplit > 1 ? (uint64_t)ks * P.outer : 0) + o;
+#pragma unroll
+    for (int u = 0; u < NU; ++u)
+      if (u < nvalid) {
+        T* out = dst + (uint64_t)u * P.to;
+        *out = (P.accumulate && P.ksplit == 1) ? Num<T>::add(*out, acc[u]) : acc[u];
+      }
+  }
+}
+
+template<class T, int V, int NU, int KU, bool PRED>
+__device__ __forceinline__ void dot_batch(T (&acc)[NU], const T* ap, uint64_t a_ustride, uint32_t kstep, const T* sb,
+                                          uint32_t k, uint32_t kn, int nvalid, bool stream)
+{
+  Vec<T, V> v[NU][KU];
+#pragma unroll
+  for (int u = 0; u < NU; ++u)
+#pragma unroll
+    for (int s = 0; s < KU; ++s) {
+      if constexpr (PRED)
+        v[u][s] = (u < nvalid && k + s * kstep < kn) ? load_a<T, V>(ap + u * a_ustride + s * kstep, stream) : zero_vec<T, V>();
+      else
+        v[u][s] = load_a<T, V>(ap + u * a_ustride + s * kstep, stream);
+    }
+#pragma unroll
+  for (int s = 0; s < KU; ++s) {
+    Vec<T, V> bv;
+    if constexpr (PRED) bv = (k + s * kstep < kn) ? *reinterpret_cast<const Vec<T, V>*>(sb + k + s * kstep) : zero_vec<T, V>();
+    else bv = *reinterpret_cast<const Vec<T, V>*>(sb + k + s * kstep);
+#pragma unroll
+    for (int u = 0; u < NU; ++u)
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[u] = Num<T>::madd(v[u][s].e[j], bv.e[j], acc[u]);
+  }
+}
+
 template<class T, int V, int NU, int KU>
-__global__ void __launch_bounds__(256, TTVB_MIN_CTAS)
+__global__ void __launch_bounds__(256, min_ctas<NU, KU>())
 ttv_dot_kernel(const TileParams P)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -267,59 +348,114 @@ ttv_dot_kernel(const TileParams P)
       }
       if (nvalid > 0) {
         const T* ap = A + o * P.nq + k0 + (uint64_t)ty * V;
-        for (uint32_t k = ty * V; k < kn; k += KU * kstep, ap += KU * kstep) {
-          Vec<T, V> v[NU][KU];
-#pragma unroll
-          for (int u = 0; u < NU; ++u)
-#pragma unroll
-            for (int s = 0; s < KU; ++s)
-              v[u][s] = (u < nvalid && k + s * kstep < kn) ? load_a<T, V>(ap + u * P.a_ustride + s * kstep, stream)
-                                                           : zero_vec<T, V>();
-#pragma unroll
-          for (int s = 0; s < KU; ++s) {
-            const Vec<T, V> bv = (k + s * kstep < kn) ? *reinterpret_cast<const Vec<T, V>*>(sb + k + s * kstep)
-                                                      : zero_vec<T, V>();
-#pragma unroll
-            for (int u = 0; u < NU; ++u)
-#pragma unroll
-              for (int j = 0; j < V; ++j) acc[u] = Num<T>::madd(v[u][s].e[j], bv.e[j], acc[u]);
-          }
-        }
+        uint32_t k = ty * V;
+        if (nvalid == NU)
+          for (; k + (KU - 1) * kstep < kn; k += KU * kstep, ap += KU * kstep)
+            dot_batch<T, V, NU, KU, false>(acc, ap, P.a_ustride, kstep, sb, k, kn, nvalid, stream);
+        for (; k < kn; k += KU * kstep, ap += KU * kstep)
+          dot_batch<T, V, NU, KU, true>(acc, ap, P.a_ustride, kstep, sb, k, kn, nvalid, stream);
       }
     }
+    dot_finish<T, NU>(acc, P, red, C, tid, ty, live, o, ks, nvalid);
+  }
+}
 
-    if (P.ty > 1 && P.ty <= 32) {
-      // ty is a power of two <= 32 and divides the warp: butterfly inside the fiber's lane group
-      for (uint32_t h = P.ty >> 1; h > 0; h >>= 1) {
-#pragma unroll
-        for (int u = 0; u < NU; ++u) acc[u] = Num<T>::add(acc[u], shfl_xor_elem(acc[u], (int)h));
-      }
-    } else if (P.ty > 32) {
-      T* mine = red + (size_t)tid * NU;
-      __syncthreads();
-#pragma unroll
-      for (int u = 0; u < NU; ++u) mine[u] = acc[u];
-      __syncthreads();
-      for (uint32_t h = P.ty >> 1; h > 0; h >>= 1) {     // ty is a power of two
-        if (live && ty < h) {
-#pragma unroll
-          for (int u = 0; u < NU; ++u) mine[u] = Num<T>::add(mine[u], mine[(size_t)h * NU + u]);
-        }
-        __syncthreads();
-      }
-#pragma unroll
-      for (int u = 0; u < NU; ++u) acc[u] = mine[u];
+// ------------------------------------------------------------------------------------------------------------------
+// DOT with peeling: n_q is not a multiple of the vector width, so fibers start at arbitrary offsets inside a 16-byte
+// line.  Because consecutive fibers are contiguous, every fiber still consists of [head | aligned 16-byte vectors |
+// tail] with head, tail < V elements.  The aligned body is loaded with full vectors, head and tail with scalar loads
+// issued in the same batch.  b is kept in shared memory V times, copy h shifted by h elements, so that the b-vector
+// matching any aligned body vector is itself an aligned 16-byte shared-memory load.
+// Requires ksplit == 1, the whole b resident (V copies), A 16-byte aligned, ty >= 2V-2 lanes or two rounds of peel.
+// ------------------------------------------------------------------------------------------------------------------
+template<class T, int V, int NU, int KU>
+__global__ void __launch_bounds__(256, min_ctas<NU, KU>())
+ttv_dot_peel_kernel(const TileParams P)
+{
+  static_assert(V > 1, "peeling needs a vector");
+  constexpr int HT = 2;                              // head/tail rounds: HT * ty lanes must cover 2V-2 elements
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t nq   = (uint32_t)P.nq;
+  const uint32_t bpad = (nq + V - 1) / V * V + V;    // elements per shifted copy (16-byte aligned rows)
+  T* sb  = reinterpret_cast<T*>(smem_raw);           // [V][bpad]; copy h holds b[h + i] at i
+  T* red = sb + (size_t)V * bpad;                    // [threads][NU]
+
+  const T* __restrict__ A = static_cast<const T*>(P.a);
+  const T* __restrict__ B = static_cast<const T*>(P.b);
+  T* __restrict__       C = static_cast<T*>(P.c);
+
+  const uint32_t tid = threadIdx.x;
+  const uint32_t ty  = tid % P.ty;
+  const uint32_t to  = tid / P.ty;
+  const bool     live = to < P.to;
+  const bool     stream = P.stream != 0;
+  const uint32_t vstep = P.ty;                       // body vectors one pass of the fiber's lanes covers
+
+  for (uint32_t j = tid; j < V * bpad; j += blockDim.x) {
+    const uint32_t h = j / bpad, i = j - h * bpad;
+    sb[j] = (h + i < nq) ? B[h + i] : Num<T>::zero();
+  }
+  __syncthreads();
+
+  for (uint64_t tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
+    const uint64_t o = tile * NU * P.to + to;        // fiber of unit 0; unit u is fiber o + u*to
+    int nvalid = 0;
+    if (live && o < P.outer) {
+      const uint64_t room = (P.outer - o + P.to - 1) / P.to;
+      nvalid = room < (uint64_t)NU ? (int)room : NU;
     }
 
-    if (ty == 0) {
-      T* dst = C + (P.ksplit > 1 ? (uint64_t)ks * P.outer : 0) + o;
+    T acc[NU];
+    const T* body[NU];                               // first aligned vector of each fiber
+    const T* bsh[NU];                                // the shifted copy of b that matches it
+    uint32_t nbody[NU];                              // aligned vectors in each fiber
+    T hx[NU][HT], hb[NU][HT];                        // head / tail elements of A and b handled by this lane
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      acc[u] = Num<T>::zero();
+      const uint64_t e0 = (o + (uint64_t)u * P.to) * nq;               // first element of the fiber
+      const uint32_t head = (uint32_t)((V - (e0 & (V - 1))) & (V - 1));
+      const uint32_t nb = u < nvalid ? (nq - head) / V : 0;
+      const uint32_t tail = nq - head - nb * V;
+      body[u] = A + e0 + head;
+      bsh[u] = sb + (size_t)head * bpad;
+      nbody[u] = nb;
+#pragma unroll
+      for (int r = 0; r < HT; ++r) {
+        const uint32_t idx = ty + r * P.ty;          // position inside head ++ tail
+        const bool on = u < nvalid && idx < head + tail;
+        const uint32_t k = idx < head ? idx : nq - tail + (idx - head);
+        hx[u][r] = on ? A[e0 + k] : Num<T>::zero();
+        hb[u][r] = on ? sb[k] : Num<T>::zero();
+      }
+    }
+    const uint32_t nvec = nq / V;                    // upper bound of nbody[u]
+    for (uint32_t j = ty; j < nvec; j += KU * vstep) {
+      Vec<T, V> v[NU][KU];
 #pragma unroll
       for (int u = 0; u < NU; ++u)
-        if (u < nvalid) {
-          T* out = dst + (uint64_t)u * P.to;
-          *out = (P.accumulate && P.ksplit == 1) ? Num<T>::add(*out, acc[u]) : acc[u];
+#pragma unroll
+        for (int s = 0; s < KU; ++s) {
+          if (j + s * vstep < nbody[u]) v[u][s] = load_a<T, V>(body[u] + (size_t)(j + s * vstep) * V, stream);
+          else v[u][s] = zero_vec<T, V>();
+        }
+#pragma unroll
+      for (int u = 0; u < NU; ++u)
+#pragma unroll
+        for (int s = 0; s < KU; ++s) {
+          if (j + s * vstep < nbody[u]) {
+            const Vec<T, V> bv = *reinterpret_cast<const Vec<T, V>*>(bsh[u] + (size_t)(j + s * vstep) * V);
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[u] = Num<T>::madd(v[u][s].e[e], bv.e[e], acc[u]);
+          }
         }
     }
+#pragma unroll
+    for (int u = 0; u < NU; ++u)
+#pragma unroll
+      for (int r = 0; r < HT; ++r) acc[u] = Num<T>::madd(hx[u][r], hb[u][r], acc[u]);
+
+    dot_finish<T, NU>(acc, P, red, C, tid, ty, live, o, 0u, nvalid);
   }
 }
 

@@ -96,29 +96,57 @@ static cudaError_t launch_tile(Kernel kern, const TileParams& P, const Launch& l
   return cudaGetLastError();
 }
 
+// (nu, ku) pairs that are instantiated: nu*ku = 8 loads in flight with 16-byte vectors, 16 with narrower ones
+#define TTVB_BATCH_CASE(KERNEL, NU, KU) case (NU) * 100 + (KU): return launch_tile(KERNEL<T, V, NU, KU>, P, l, stream);
+
 template<class T, int V>
 static cudaError_t dispatch_batch(const TileParams& P, const Launch& l, cudaStream_t stream)
 {
+  const int key = l.nu * 100 + l.ku;
+  constexpr bool wide = sizeof(T) * V >= 16;
+  if (l.kernel == TTV_B200_KERNEL_DOT && l.peel) {
+    if constexpr (V > 1) {
+      switch (key) {
+        TTVB_BATCH_CASE(ttv_dot_peel_kernel, 1, 8) TTVB_BATCH_CASE(ttv_dot_peel_kernel, 2, 4) TTVB_BATCH_CASE(ttv_dot_peel_kernel, 4, 2)
+        default: return cudaErrorInvalidValue;
+      }
+    }
+    return cudaErrorInvalidValue;
+  }
   if (l.kernel == TTV_B200_KERNEL_DOT) {
-    switch (l.ku) {
-      case 8:  return launch_tile(ttv_dot_kernel<T, V, 1, 8>, P, l, stream);
-      case 4:  return launch_tile(ttv_dot_kernel<T, V, 2, 4>, P, l, stream);
-      case 2:  return launch_tile(ttv_dot_kernel<T, V, 4, 2>, P, l, stream);
-      case 1:  return launch_tile(ttv_dot_kernel<T, V, 8, 1>, P, l, stream);
-      default: return cudaErrorInvalidValue;
+    switch (key) {
+      TTVB_BATCH_CASE(ttv_dot_kernel, 8, 1)
+      default: break;
+    }
+    if constexpr (wide) {
+      switch (key) {
+        TTVB_BATCH_CASE(ttv_dot_kernel, 1, 8) TTVB_BATCH_CASE(ttv_dot_kernel, 2, 4) TTVB_BATCH_CASE(ttv_dot_kernel, 4, 2)
+        default: return cudaErrorInvalidValue;
+      }
+    } else {
+      switch (key) {
+        TTVB_BATCH_CASE(ttv_dot_kernel, 1, 16) TTVB_BATCH_CASE(ttv_dot_kernel, 2, 8) TTVB_BATCH_CASE(ttv_dot_kernel, 4, 4)
+        TTVB_BATCH_CASE(ttv_dot_kernel, 8, 2)
+        default: return cudaErrorInvalidValue;
+      }
     }
   }
-  switch (l.ku) {
-    case 8:  return launch_tile(ttv_col_kernel<T, V, 1, 8>, P, l, stream);
-    case 4:  return launch_tile(ttv_col_kernel<T, V, 2, 4>, P, l, stream);
-    case 2:  return launch_tile(ttv_col_kernel<T, V, 4, 2>, P, l, stream);
-    default: return cudaErrorInvalidValue;
+  if constexpr (wide) {
+    switch (key) {
+      TTVB_BATCH_CASE(ttv_col_kernel, 1, 8) TTVB_BATCH_CASE(ttv_col_kernel, 2, 4) TTVB_BATCH_CASE(ttv_col_kernel, 4, 2)
+      default: return cudaErrorInvalidValue;
+    }
+  } else {
+    switch (key) {
+      TTVB_BATCH_CASE(ttv_col_kernel, 1, 16) TTVB_BATCH_CASE(ttv_col_kernel, 2, 8) TTVB_BATCH_CASE(ttv_col_kernel, 4, 4)
+      TTVB_BATCH_CASE(ttv_col_kernel, 8, 2)
+      default: return cudaErrorInvalidValue;
+    }
   }
 }
 
 cudaError_t TTVB_CAT(tile_dtype_, TTVB_DTYPE)(const TileParams& P, const Launch& l, cudaStream_t stream)
 {
-  if (l.nu * l.ku != 8) return cudaErrorInvalidValue;
   if constexpr (kVmax >= 4) if (l.vec == 4) return dispatch_batch<elem_t, 4>(P, l, stream);
   if constexpr (kVmax >= 2) if (l.vec == 2) return dispatch_batch<elem_t, 2>(P, l, stream);
   if (l.vec == 1) return dispatch_batch<elem_t, 1>(P, l, stream);

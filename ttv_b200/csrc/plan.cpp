@@ -245,30 +245,39 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
   if (forced == TTV_B200_KERNEL_DOT && v.inner != 1) return TTV_B200_ERR_OPTS;
   l.kernel = dot ? TTV_B200_KERNEL_DOT : TTV_B200_KERNEL_COL;
 
+  int want = opts ? opts->ksplit : 0;
+  if (want < 0) return TTV_B200_ERR_OPTS;
+  if (want == 0) want = env_int("TTV_B200_KSPLIT", 0);
+
   uint64_t V = vmax;
-  uint64_t units_avail = 1;           // how many units a thread could take (before n_q splitting)
   if (dot) {
-    // vector along n_q: every fiber must start on a vector boundary and hold whole vectors
+    // vector along n_q: every fiber must start on a vector boundary and hold whole vectors ...
     while (V > 1 && !((v.nq % V) == 0 && (align_a % (V * s)) == 0 && (align_b % (V * s)) == 0)) V /= 2;
+    // ... or, for fibers of odd length, be peeled into head | aligned body | tail (needs all of b in shared memory,
+    // V shifted copies, and no n_q split)
+    const uint64_t peel_smem = vmax * (ceil_div(v.nq, vmax) * vmax + vmax) * s;
+    if (V < vmax && vmax > 1 && v.nq >= 4 * vmax && peel_smem <= 64 * 1024 && (align_a % 16) == 0 && want <= 1 &&
+        v.outer >= sms * 8 && env_int("TTV_B200_PEEL", 1)) {
+      V = vmax;
+      l.peel = 1;
+    }
     const uint64_t kv = v.nq / V;                          // vector steps per fiber
     l.tx = 1;
     // lanes per fiber: about eight vectors per lane, at most one warp (a fiber then reduces with shuffles only)
     uint64_t ty = std::min<uint64_t>(32, pow2_ceil(ceil_div(kv, 8)));
+    if (l.peel) ty = std::max<uint64_t>(ty, V == 4 ? 4 : 1);     // two rounds of ty lanes cover the 2V-2 head/tail elements
     // few fibers: put more lanes on each one, as long as every lane keeps at least four vectors
-    while (ty < NT && kv / (ty * 2) >= 4 && ceil_div(v.outer, std::max<uint64_t>(1, NT / ty)) < sms * 2) ty *= 2;
+    while (!l.peel && ty < NT && kv / (ty * 2) >= 4 && ceil_div(v.outer, std::max<uint64_t>(1, NT / ty)) < sms * 2) ty *= 2;
     const uint64_t to = std::max<uint64_t>(1, std::min<uint64_t>(NT / ty, v.outer));
     l.ty = (uint32_t)ty; l.to = (uint32_t)to;
     l.udir = 1;
-    units_avail = ceil_div(v.outer, to);
-    l.stream = ty >= 32 ? 1u : 0u;
+    l.stream = ty >= 32 ? 1u : 0u;     // long fibers: every warp walks its own 100+ KB stream, keep it out of L1
   } else {
     // vector along inner: rows must hold whole vectors and start on vector boundaries
     while (V > 1 && !((v.inner % V) == 0 && (align_a % (V * s)) == 0 && (align_c % (V * s)) == 0)) V /= 2;
     const uint64_t cv = v.inner / V;                       // vector columns
     if (cv >= NT) {
       l.tx = (uint32_t)NT; l.ty = 1; l.to = 1; l.udir = 0;
-      units_avail = ceil_div(cv, NT);
-      l.stream = 1;
     } else {
       l.tx = (uint32_t)cv;
       const uint64_t rem = NT / cv;
@@ -279,9 +288,9 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
       // few slabs: use the idle threads of the CTA along n_q
       while (ty * 2 <= rem / to && v.nq / (ty * 2) >= 8 && ceil_div(v.outer, to) < sms * 2) ty *= 2;
       l.ty = (uint32_t)ty; l.to = (uint32_t)to; l.udir = 1;
-      units_avail = ceil_div(v.outer, to);
-      l.stream = (cv >= 32 || ty * cv >= 32) ? 1u : 0u;
     }
+    // measured: 4/8-byte elements are faster through L1 unless lanes are strung along n_q; 16-byte elements bypass it
+    l.stream = (s >= 16 || l.ty > 1) ? 1u : 0u;
   }
   l.stream = (uint32_t)env_int("TTV_B200_STREAM", (int)l.stream);
   l.vec = (int)V;
@@ -292,28 +301,56 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
   const uint64_t tiles1  = itiles1 * otiles1;
   const uint64_t kstep   = (uint64_t)l.ty * (dot ? V : 1);            // n_q elements one pass of the CTA covers
   uint64_t ksplit = 1;
-  int want = opts ? opts->ksplit : 0;
-  if (want < 0) return TTV_B200_ERR_OPTS;
-  if (want == 0) want = env_int("TTV_B200_KSPLIT", 0);
   if (want > 0) ksplit = (uint64_t)want;
-  else if (tiles1 < sms) {
+  else if (tiles1 < sms && !l.peel) {
     const uint64_t max_split = std::max<uint64_t>(1, v.nq / (kstep * 16));
-    ksplit = std::min(ceil_div(sms * 4, tiles1), max_split);
+    ksplit = std::min(ceil_div(sms * 8, tiles1), max_split);
   }
+  if (l.peel) ksplit = 1;
   ksplit = std::max<uint64_t>(1, std::min(ksplit, ceil_div(v.nq, kstep)));
   uint64_t kchunk = ceil_div(ceil_div(v.nq, ksplit), kstep) * kstep;  // multiple of kstep keeps vectors aligned
   ksplit = ceil_div(v.nq, kchunk);
   l.ksplit = (uint32_t)ksplit;
   l.kchunk = kchunk;
 
-  // batch shape: ku k-steps for each of nu units, nu*ku = 8 loads in flight per thread
+  // batch shape: ku k-steps for each of nu units; nu*ku loads in flight per thread (128 bytes with 16-byte vectors,
+  // 16 loads with narrower ones)
+  const uint64_t loads = (V * s >= 16 || l.peel) ? 8 : 16;
   const uint64_t per = ceil_div(std::min(kchunk, v.nq), kstep);       // k-steps one thread makes per unit
-  int ku = per >= 5 ? 8 : per >= 3 ? 4 : (per >= 2 || !dot) ? 2 : 1;
+  // Batch depth (all rules measured on B200, tools/sweep.py).  Predicated-off slots of the last batch are wasted
+  // issue slots, so short contractions take the depth that wastes least and fill the batch with more units; long ones
+  // take the full depth with one unit.
+  auto waste = [per](uint64_t d) { return (double)(ceil_div(per, d) * d - per) / (double)(ceil_div(per, d) * d); };
+  auto least_waste = [&](uint64_t dmax, bool tie_deeper) {
+    uint64_t best = 2;
+    for (uint64_t d = 4; d <= dmax; d *= 2)
+      if (waste(d) < waste(best) - 1e-9 || (tie_deeper && waste(d) <= waste(best) + 1e-9)) best = d;
+    return best;
+  };
+  uint64_t ku;
+  if (l.peel)                       ku = per >= 5 ? 8 : per >= 3 ? 4 : 2;       // per-unit head/tail work: go deep
+  else if (dot && per <= 1)         ku = 1;
+  else if (dot && per >= 64)        ku = loads;                                 // very long fibers: one fiber per lane group
+  else if (dot && per >= 16)        ku = 4;
+  else if (!dot && per >= 16) {                                                 // deepest batch that wastes <= 10 %
+    ku = (loads > 8 && per < 64) ? 4 : loads;                                   // narrow loads: shallow, more units
+    while (ku > 2 && waste(ku) > 0.10) ku /= 2;
+  } else                            ku = least_waste(std::min<uint64_t>(loads, 8), false);
   const int ku_env = env_int("TTV_B200_KU", 0);
-  if (ku_env == 8 || ku_env == 4 || ku_env == 2 || (ku_env == 1 && dot)) ku = ku_env;
-  l.ku = ku;
-  l.nu = 8 / ku;
-  (void)units_avail;   // units beyond the available ones are predicated off inside the kernel
+  if (ku_env > 0 && (uint64_t)ku_env <= loads && pow2_ceil((uint64_t)ku_env) == (uint64_t)ku_env && (ku_env > 1 || (dot && !l.peel))) ku = (uint64_t)ku_env;
+  uint64_t nu = loads / ku;
+  if (nu > 8) nu = 8;                                                 // (16,1) is not instantiated
+  // units multiply the work of a tile: never starve the SMs of tiles for their sake
+  {
+    const uint64_t units1 = dot ? ceil_div(v.outer, l.to) : (l.udir == 0 ? ceil_div(v.inner / V, l.tx) * v.outer : ceil_div(v.outer, l.to));
+    while (nu > 1 && ceil_div(units1, nu) * ksplit < sms * 8) {
+      nu /= 2;
+      ku *= 2;
+    }
+    if (!(nu == 8 && ku == 1)) ku = loads / nu;                      // only (nu, ku) with nu*ku == loads are instantiated
+  }
+  l.ku = (int)ku;
+  l.nu = (int)nu;
 
   if (dot) {
     l.itiles = 1;
@@ -334,13 +371,14 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
   l.tiles = l.itiles * l.otiles * ksplit;
   l.ctas  = std::min<uint64_t>(l.tiles, sms * 64);
 
-  // shared memory: a chunk of b (16 KB at most) + the cross-lane reduction scratch
+  // shared memory: a chunk of b (16 KB at most; the peeled DOT keeps V shifted copies of all of b) + reduction scratch
   uint64_t kb = std::min<uint64_t>(kchunk, 16384 / s);
   kb = std::max<uint64_t>(kstep, kb / kstep * kstep);
   if (kb * s > 96 * 1024) return TTV_B200_ERR_OPTS;
   l.kb = (uint32_t)kb;
   const uint64_t red_elems = NT * (uint64_t)l.nu * (dot ? 1 : V);
-  l.smem_bytes = kb * s + red_elems * s;
+  const uint64_t b_bytes = l.peel ? V * (ceil_div(v.nq, V) * V + V) * s : kb * s;
+  l.smem_bytes = b_bytes + red_elems * s;
   l.workspace_bytes = ksplit > 1 ? ksplit * v.outer * v.inner * s : 0;
   *out = l;
   return TTV_B200_OK;

@@ -31,7 +31,8 @@ struct Launch {
   int      ku      = 8;     // k-steps of one unit in flight per thread
   int      nu      = 1;     // independent units (outputs) per thread; nu*ku vector loads are in flight per thread
   uint32_t udir    = 0;     // units run along inner (0) or along outer (1)
-  uint32_t stream  = 1;     // L1::no_allocate loads (a warp consumes whole lines by itself)
+  uint32_t stream  = 1;     // L1::no_allocate loads
+  uint32_t peel    = 0;     // DOT only: n_q is not a multiple of vec; fibers are split into head | aligned body | tail
   uint64_t a_ustride = 0, c_ustride = 0;   // element distance between two units in A / C
   uint32_t tx = 1, ty = 1, to = 1;   // threads along inner / along n_q / along outer inside one CTA
   uint32_t threads = 256;
