@@ -163,6 +163,15 @@ int ttv_b200_i64 (uint64_t q, uint64_t p, const int64_t* a, const uint64_t* na, 
                   const int64_t* b, const uint64_t* nb, int64_t* c, const uint64_t* nc, const uint64_t* wc,
                   const uint64_t* pic, const ttv_b200_opts* opts);
 
+/* Several products on ONE tensor:  C_i = A x_{q[i]} b_i,  i < count  (the reference's benchmark protocol contracts every
+ * mode q = 1..p of the same tensor, README.md:59-64).  Equivalent to `count` calls of ttv_b200_run with nb = na[q_i-1]
+ * and C_i packed in the output shape / layout of (na, pia, q_i) (detail/shape.h:126-158, detail/layout.h:175-207) --
+ * except that with HOST pointers A crosses PCIe once instead of `count` times.  a, b[i], c[i]: all host or all device. */
+int ttv_b200_multi(int dtype, uint64_t p,
+                   const void* a, const uint64_t* na, const uint64_t* wa, const uint64_t* pia,
+                   uint64_t count, const uint64_t* q, const void* const* b, void* const* c,
+                   const ttv_b200_opts* opts);
+
 /* Validation + layout folding + kernel choice without touching a device (pure host code).  Pointers a, b, c are
  * only checked for null-ness; pass any non-null value.  Returns the same status codes as ttv_b200_run. */
 int ttv_b200_plan(int dtype, uint64_t q, uint64_t p,

@@ -269,3 +269,23 @@ def test_more_than_2_to_32_elements():
         j = o * inner + i
         assert int(c[j]) == expect_marked
         assert int((c != base).sum()) == 1
+
+
+def test_multi_products_on_one_tensor(oracle):
+    """ttv_b200_multi: all modes of one tensor in one call (A staged once); identical to separate calls"""
+    import torch
+    rng = np.random.default_rng(16)
+    for dtype in (np.float64, np.int32, np.complex64):
+        na, pia = (6, 9, 4, 5), (2, 4, 1, 3)
+        a, _ = random_case(rng, na, 1, dtype)
+        qs = [1, 2, 3, 4, 2]
+        bs = [random_case(rng, na, q, dtype)[1] for q in qs]
+        want = [oracle.ttv(q, a, na, pia, b) for q, b in zip(qs, bs)]
+        got = ttv_b200.ttv_multi(qs, a, na, pia, bs)                                  # host buffers
+        assert all(np.array_equal(g, w) for g, w in zip(got, want))
+        ta = torch.from_numpy(a).cuda()
+        got = ttv_b200.ttv_multi(qs, ta, na, pia, [torch.from_numpy(b).cuda() for b in bs])   # device buffers
+        assert all(np.array_equal(g.cpu().numpy(), w) for g, w in zip(got, want))
+    with pytest.raises(ttv_b200.TTVError) as e:
+        ttv_b200.ttv_multi([1, 5], a, na, pia, [bs[0], bs[0]], cs=[np.empty(8, a.dtype), np.empty(8, a.dtype)])
+    assert e.value.status == 2

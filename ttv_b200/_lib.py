@@ -45,6 +45,8 @@ SYMBOLS = {
     "ttv_b200_c128": (C.c_int, _RUN_ARGS),
     "ttv_b200_i32": (C.c_int, _RUN_ARGS),
     "ttv_b200_i64": (C.c_int, _RUN_ARGS),
+    "ttv_b200_multi": (C.c_int, [C.c_int, C.c_uint64, C.c_void_p, u64p, u64p, u64p, C.c_uint64, u64p,
+                                 C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(Opts)]),
     "ttv_b200_plan": (C.c_int, [C.c_int] + _RUN_ARGS + [C.POINTER(Plan)]),
     "ttv_b200_view": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.POINTER(Opts)]),

@@ -175,6 +175,36 @@ def ttv_lowlevel(q: int, p: int, a, na, wa, pia, b, nb, c, nc, wc, pic, *, dtype
     _check(st)
 
 
+def ttv_multi(qs: Sequence[int], a, na, pia, bs, cs=None, *, wa=None, opts: Opts | None = None, **opt_kwargs):
+    """C_i = A x_{qs[i]} bs[i] for several modes of ONE tensor (ttv_b200_multi).  a: flat buffer (numpy = host,
+    torch CUDA = device) with shape na and layout pia; bs: vectors of the same kind.  With host buffers A is copied to
+    the device once for all products.  Returns the list of flat C_i (packed in the output layout of each q)."""
+    lib = _lib.load()
+    p = len(na)
+    wa = list(wa) if wa is not None else generate_strides(na, pia)
+    torch_in = _is_torch(a)
+    if cs is None:
+        cs = []
+        for q in qs:
+            n_out = int(np.prod(generate_output_shape(na, q), dtype=object))
+            if torch_in:
+                import torch
+                cs.append(torch.empty(n_out, dtype=a.dtype, device=a.device))
+            else:
+                cs.append(np.empty(n_out, dtype=np.asarray(a).dtype))
+    if opts is None:
+        if "stream" not in opt_kwargs and torch_in and a.is_cuda:
+            opt_kwargs["stream"] = _current_torch_stream(a)
+        opts = make_opts(**opt_kwargs)
+    keep = [_tuple(v) for v in (na, wa, pia, list(qs))]
+    n = len(qs)
+    barr = (C.c_void_p * n)(*[_ptr(b).value for b in bs])
+    carr = (C.c_void_p * n)(*[_ptr(c).value for c in cs])
+    _check(lib.ttv_b200_multi(dtype_code(a), p, _ptr(a), keep[0][1], keep[1][1], keep[2][1], n, keep[3][1], barr, carr,
+                              C.byref(opts)))
+    return cs
+
+
 def plan(q: int, na, pia, *, dtype="f32", wa=None, wc=None, pic=None, **opt_kwargs) -> dict:
     """What the layout folder and the kernel chooser decide for (na, pia, q): pure host code, needs no GPU."""
     lib = _lib.load()

@@ -13,6 +13,8 @@
 #include <mutex>
 #include <string>
 #include <utility>
+#include <vector>
+#include <algorithm>
 
 using namespace ttvb;
 
@@ -206,6 +208,94 @@ int ttv_b200_run(int dtype, uint64_t q, uint64_t p,
   View v;
   if (int rc = validate_and_fold(q, p, a, na, wa, pia, b, nb, c, nc, wc, pic, &v)) return fail(rc);
   return run_any(dtype, v, a, b, c, opts);
+}
+
+int ttv_b200_multi(int dtype, uint64_t p,
+                   const void* a, const uint64_t* na, const uint64_t* wa, const uint64_t* pia,
+                   uint64_t count, const uint64_t* q, const void* const* b, void* const* c,
+                   const ttv_b200_opts* opts)
+{
+  if (dtype_size(dtype) == 0) return fail(TTV_B200_ERR_DTYPE);
+  if (count == 0) return TTV_B200_OK;
+  if (!q || !b || !c) return fail(TTV_B200_ERR_OPTS, "ttv_b200_multi: q, b and c arrays must not be null");
+  if (p == 0) return fail(TTV_B200_ERR_ORDER_ZERO);
+  if (p > (uint64_t)kMaxOrder) return fail(TTV_B200_ERR_OPTS);
+  if (!na) return fail(TTV_B200_ERR_NA_NULL);
+  if (!pia) return fail(TTV_B200_ERR_PIA_NULL);
+
+  // fold every product first: nothing is copied or launched unless all of them are valid
+  std::vector<View> views(count);
+  for (uint64_t i = 0; i < count; ++i) {
+    if (q[i] == 0 || q[i] > p) return fail(TTV_B200_ERR_MODE);
+    if (!is_valid_shape(na, p)) return fail(TTV_B200_ERR_SHAPE_A);
+    if (!is_valid_layout(pia, p)) return fail(TTV_B200_ERR_LAYOUT_A);
+    if (p < 2) return fail(TTV_B200_ERR_SHAPE_C);
+    uint64_t nc[kMaxOrder], pic[kMaxOrder], wc[kMaxOrder];
+    output_shape(na, p, q[i], nc);
+    output_layout(pia, p, q[i], pic);
+    uint64_t stride = 1;                                   // packed strides of (nc, pic)
+    for (uint64_t r = 0; r + 1 < p; ++r) { wc[pic[r] - 1] = stride; stride *= nc[pic[r] - 1]; }
+    const uint64_t nb = na[q[i] - 1];
+    if (int rc = validate_and_fold(q[i], p, a, na, wa, pia, b[i], &nb, c[i], nc, wc, pic, &views[i])) return fail(rc);
+  }
+
+  Where wa_, wx;
+  int da = -1, dx = -1;
+  if (int rc = classify(a, &wa_, &da)) return rc;
+  for (uint64_t i = 0; i < count; ++i) {
+    if (int rc = classify(b[i], &wx, &dx)) return rc;
+    if (wx != wa_ || (wa_ == Where::Device && dx != da)) return fail(TTV_B200_ERR_MIXED_POINTERS);
+    if (int rc = classify(c[i], &wx, &dx)) return rc;
+    if (wx != wa_ || (wa_ == Where::Device && dx != da)) return fail(TTV_B200_ERR_MIXED_POINTERS);
+  }
+  cudaStream_t stream = opts ? static_cast<cudaStream_t>(opts->stream) : nullptr;
+  const bool accumulate = opts && (opts->flags & TTV_B200_FLAG_ACCUMULATE);
+
+  if (wa_ == Where::Device) {
+    DeviceGuard guard;
+    CUDA_TRY(guard.set(da), "cudaSetDevice");
+    for (uint64_t i = 0; i < count; ++i)
+      if (int rc = run_view_device(dtype, views[i], a, b[i], c[i], opts, da, false)) return rc;
+    if (!(opts && (opts->flags & TTV_B200_FLAG_ASYNC))) CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+    return TTV_B200_OK;
+  }
+
+  // host pointers: A goes to the device once; b_i / C_i are staged per product
+  int device = opts ? opts->device : -1;
+  if (device < 0) CUDA_TRY(cudaGetDevice(&device), "cudaGetDevice (is a CUDA device visible?)");
+  DeviceGuard guard;
+  CUDA_TRY(guard.set(device), "cudaSetDevice");
+  const size_t s = (size_t)dtype_size(dtype);
+  const size_t bytes_a = (size_t)(views[0].outer * views[0].nq * views[0].inner) * s;
+  size_t max_b = 0, sum_c = 0;
+  for (uint64_t i = 0; i < count; ++i) {
+    max_b = std::max(max_b, (size_t)views[i].nq * s);
+    sum_c += ((size_t)(views[i].outer * views[i].inner) * s + 255) / 256 * 256;
+  }
+  char *da_ = nullptr, *db_ = nullptr, *dc_ = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    DeviceState* st = nullptr;
+    if (int rc = device_state(device, &st)) return rc;
+    if (int rc = ensure(st->stage_a, bytes_a)) return rc;
+    if (int rc = ensure(st->stage_b, max_b * count)) return rc;
+    if (int rc = ensure(st->stage_c, sum_c)) return rc;
+    da_ = static_cast<char*>(st->stage_a.ptr); db_ = static_cast<char*>(st->stage_b.ptr); dc_ = static_cast<char*>(st->stage_c.ptr);
+  }
+  CUDA_TRY(cudaMemcpyAsync(da_, a, bytes_a, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync H2D A");
+  size_t coff = 0;
+  for (uint64_t i = 0; i < count; ++i) {
+    const size_t bytes_b = (size_t)views[i].nq * s, bytes_c = (size_t)(views[i].outer * views[i].inner) * s;
+    char* dbi = db_ + i * max_b;
+    char* dci = dc_ + coff;
+    CUDA_TRY(cudaMemcpyAsync(dbi, b[i], bytes_b, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync H2D b");
+    if (accumulate) CUDA_TRY(cudaMemcpyAsync(dci, c[i], bytes_c, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync H2D C");
+    if (int rc = run_view_device(dtype, views[i], da_, dbi, dci, opts, device, false)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c[i], dci, bytes_c, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync D2H C");
+    coff += (bytes_c + 255) / 256 * 256;
+  }
+  CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+  return TTV_B200_OK;
 }
 
 #define TTV_B200_TYPED(NAME, CODE, CT)                                                                              \
