@@ -289,3 +289,28 @@ def test_multi_products_on_one_tensor(oracle):
     with pytest.raises(ttv_b200.TTVError) as e:
         ttv_b200.ttv_multi([1, 5], a, na, pia, [bs[0], bs[0]], cs=[np.empty(8, a.dtype), np.empty(8, a.dtype)])
     assert e.value.status == 2
+
+
+@pytest.mark.parametrize("dtype", ALL_DTYPES)
+def test_stream_kernel_small_slabs(dtype, oracle):
+    """kernel="stream": slabs staged through shared memory by TMA bulk copies; odd sizes, many chunks, ragged last
+    chunk, array ends that are not a multiple of 16 bytes, accumulate"""
+    rng = np.random.default_rng(17)
+    cases = [((23, 23, 301), (1, 2, 3), 2), ((23, 1013), (1, 2), 1), ((21, 21, 77), (1, 2, 3), 1), ((3, 2, 5000), (1, 2, 3), 2),
+             ((5, 7, 3, 211), (2, 1, 3, 4), 1), ((5, 7, 3, 211), (2, 1, 3, 4), 2), ((9, 4099), (1, 2), 1), ((2, 100003), (1, 2), 1),
+             ((1, 7, 13), (1, 2, 3), 2), ((40, 5, 6000), (1, 2, 3), 1)]
+    for na, pia, q in cases:
+        a, b = random_case(rng, na, q, dtype)
+        want = oracle.ttv(q, a, na, pia, b)
+        name = {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64", np.dtype(np.complex64): "c64",
+                np.dtype(np.complex128): "c128", np.dtype(np.int32): "i32", np.dtype(np.int64): "i64"}[np.dtype(dtype)]
+        try:
+            pl = ttv_b200.plan(q, na, pia, dtype=name, kernel="stream")
+        except ttv_b200.TTVError as exc:          # slab larger than a stage for this element size: not eligible
+            assert exc.status == 32 and int(np.prod(na)) // na[-1] * np.dtype(dtype).itemsize > 8192
+            continue
+        assert pl["kernel"] == 3
+        c = run_lowlevel(q, a, na, pia, b, kernel="stream")
+        assert np.array_equal(c, want), (na, pia, q, dtype)
+        c0 = np.full(want.size, 3, dtype)
+        assert np.array_equal(run_lowlevel(q, a, na, pia, b, c0=c0, kernel="stream", flags=1), want + 3)

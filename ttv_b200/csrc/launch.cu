@@ -5,6 +5,7 @@
 //   with -DTTVB_DTYPE=k  -> the kernels of element type k (enum ttv_b200_dtype) and their dispatcher
 #include "launch.h"
 #include "kernels.cuh"
+#include "stream_kernel.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -15,11 +16,13 @@ namespace ttvb {
 using tile_fn_t   = cudaError_t (*)(const TileParams&, const Launch&, cudaStream_t);
 using reduce_fn_t = cudaError_t (*)(const void*, void*, uint64_t, uint32_t, bool, int, cudaStream_t);
 using fill_fn_t   = cudaError_t (*)(void*, uint64_t, uint64_t, uint64_t, int, cudaStream_t);
+using stream_fn_t = cudaError_t (*)(const StreamParams&, const Launch&, cudaStream_t);
 
 #define TTVB_DECLARE(k)                                                                                          \
   cudaError_t tile_dtype_##k(const TileParams&, const Launch&, cudaStream_t);                                    \
   cudaError_t reduce_dtype_##k(const void*, void*, uint64_t, uint32_t, bool, int, cudaStream_t);                 \
-  cudaError_t fill_dtype_##k(void*, uint64_t, uint64_t, uint64_t, int, cudaStream_t);
+  cudaError_t fill_dtype_##k(void*, uint64_t, uint64_t, uint64_t, int, cudaStream_t);                            \
+  cudaError_t stream_dtype_##k(const StreamParams&, const Launch&, cudaStream_t);
 TTVB_DECLARE(0) TTVB_DECLARE(1) TTVB_DECLARE(2) TTVB_DECLARE(3) TTVB_DECLARE(4) TTVB_DECLARE(5)
 #undef TTVB_DECLARE
 
@@ -34,11 +37,22 @@ void count_launch() { g_launches.fetch_add(1); }
 static const tile_fn_t   k_tile[]   = {tile_dtype_0, tile_dtype_1, tile_dtype_2, tile_dtype_3, tile_dtype_4, tile_dtype_5};
 static const reduce_fn_t k_reduce[] = {reduce_dtype_0, reduce_dtype_1, reduce_dtype_2, reduce_dtype_3, reduce_dtype_4, reduce_dtype_5};
 static const fill_fn_t   k_fill[]   = {fill_dtype_0, fill_dtype_1, fill_dtype_2, fill_dtype_3, fill_dtype_4, fill_dtype_5};
+static const stream_fn_t k_stream[] = {stream_dtype_0, stream_dtype_1, stream_dtype_2, stream_dtype_3, stream_dtype_4, stream_dtype_5};
 
 cudaError_t launch_view(int dtype, const View& v, const Launch& l, const void* a, const void* b, void* c,
                         void* workspace, bool accumulate, int sm_count, cudaStream_t stream)
 {
   if (dtype < 0 || dtype >= TTV_B200_DTYPE_COUNT) return cudaErrorInvalidValue;
+  if (l.kernel == TTV_B200_KERNEL_STREAM) {
+    StreamParams S;
+    S.a = a; S.b = b; S.c = c;
+    S.outer = v.outer; S.nq = v.nq; S.inner = v.inner;
+    S.slabs_per_chunk = l.slabs_per_chunk; S.chunks = l.chunks;
+    S.total_bytes = v.outer * v.nq * v.inner * (uint64_t)dtype_size(dtype);
+    S.stage_bytes = l.stage_bytes;
+    S.accumulate = accumulate ? 1u : 0u;
+    return k_stream[dtype](S, l, stream);
+  }
   TileParams P;
   P.a = a; P.b = b;
   P.c = l.ksplit > 1 ? workspace : c;
@@ -159,6 +173,16 @@ cudaError_t TTVB_CAT(reduce_dtype_, TTVB_DTYPE)(const void* ws, void* c, uint64_
   const uint64_t blocks = std::min<uint64_t>((n + 255) / 256, (uint64_t)sm_count * 32);
   ttv_reduce_kernel<elem_t><<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const elem_t*>(ws), static_cast<elem_t*>(c), n,
                                                                   ksplit, accumulate ? 1u : 0u);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t TTVB_CAT(stream_dtype_, TTVB_DTYPE)(const StreamParams& S, const Launch& l, cudaStream_t stream)
+{
+  auto kern = ttv_stream_kernel<elem_t, 3, 4>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes);
+  if (e != cudaSuccess) return e;
+  kern<<<(unsigned)l.ctas, l.threads, l.smem_bytes, stream>>>(S);
   count_launch();
   return cudaGetLastError();
 }

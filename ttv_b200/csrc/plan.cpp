@@ -217,6 +217,22 @@ static uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 static uint64_t pow2_floor(uint64_t x) { uint64_t r = 1; while (r * 2 <= x) r *= 2; return r; }
 static uint64_t pow2_ceil(uint64_t x) { uint64_t r = 1; while (r < x) r *= 2; return r; }
 
+static uint64_t vmax_of(uint64_t s) { return s >= 16 ? 1 : 16 / s; }
+
+// shared-memory bank conflict degree of the STREAM kernel's reads: lane u owns output (u / inner, u % inner) and reads
+// word ((u / inner) * M + u % inner) * w of the stage (w = 32-bit words per element; wide accesses go out per
+// 32/w lanes)
+static unsigned stream_conflict_degree(uint64_t M, uint64_t inner, uint64_t s)
+{
+  const uint64_t w = std::max<uint64_t>(1, s / 4), lanes = 32 / std::min<uint64_t>(w, 4);
+  unsigned count[32] = {0}, worst = 0;
+  for (uint64_t u = 0; u < lanes; ++u) {
+    const uint64_t bank = (((u / inner) * M + (u % inner)) * w) % 32;
+    worst = std::max(worst, ++count[bank]);
+  }
+  return worst;
+}
+
 static int env_int(const char* name, int fallback)
 {
   const char* s = std::getenv(name);
@@ -233,9 +249,48 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
   const uint32_t flags = opts ? opts->flags : 0u;
   int forced = opts ? opts->kernel : 0;
   if (forced < 0 || forced >= TTV_B200_KERNEL_COUNT) return TTV_B200_ERR_OPTS;
-  if (forced == TTV_B200_KERNEL_STREAM) forced = 0;   // not a separate kernel yet: falls back to the chooser
-
   Launch l;
+  // STREAM: small slabs staged through shared memory by TMA bulk copies (stream_kernel.cuh).  Eligible when a slab and
+  // b are small, A is 16-byte aligned and n_q is not split.
+  {
+    const uint64_t slab_bytes = v.nq * v.inner * s;
+    const bool eligible = slab_bytes <= 8192 && v.nq * s <= 8192 && (align_a % 16) == 0 && (!opts || opts->ksplit <= 1) &&
+                          v.outer * v.nq * v.inner * s >= 16;
+    const uint64_t max_payload = (uint64_t)env_int("TTV_B200_STAGE_KB", 36) * 1024 - 128;
+    const bool fills_cta = (max_payload / std::max<uint64_t>(1, slab_bytes)) * v.inner >= 128;   // outputs per stage vs 256 threads
+    const bool misaligned = (v.inner == 1 ? v.nq : v.inner) % vmax_of(s) != 0;      // the other kernels would fall back to narrow loads
+    const int mode = env_int("TTV_B200_USE_STREAM", -1);                               // -1 auto, 0 never, 1 whenever eligible
+    const bool pick = forced == TTV_B200_KERNEL_STREAM ? eligible
+                    : forced != 0 ? false
+                    : mode == 1 ? eligible
+                    : mode == 0 ? false
+                    : (eligible && misaligned && fills_cta && v.outer >= sms * 64 && !(flags & TTV_B200_FLAG_NO_VEC) &&
+                       stream_conflict_degree(v.nq * v.inner, v.inner, s) <= 2);
+    if (forced == TTV_B200_KERNEL_STREAM && !eligible) return TTV_B200_ERR_OPTS;
+    if (pick) {
+      // stage size: up to 36 KB (3 stages x 2 CTAs per SM = 216 KB of shared memory, all of it in flight), trimmed so
+      // that the outputs of a chunk fill whole rounds of the CTA's 256 threads (measured: 2 CTAs x 24-36 KB is best)
+      const uint64_t payload = max_payload;
+      l.kernel = TTV_B200_KERNEL_STREAM;
+      l.threads = (uint32_t)env_int("TTV_B200_STREAM_THREADS", 256);
+      l.vec = 1; l.tx = 1; l.ty = 1; l.to = 1; l.nu = 4; l.ku = 1; l.ksplit = 1; l.stream = 1;
+      uint64_t S = std::max<uint64_t>(1, std::min<uint64_t>(payload / slab_bytes, v.outer));
+      const uint64_t rounds = S * v.inner / l.threads;
+      if (rounds >= 1) S = std::max<uint64_t>(1, rounds * l.threads / v.inner);
+      l.slabs_per_chunk = S;
+      l.chunks = ceil_div(v.outer, l.slabs_per_chunk);
+      l.stage_bytes = (uint32_t)((l.slabs_per_chunk * slab_bytes + 32 + 127) / 128 * 128);
+      l.tiles = l.chunks;
+      l.ctas = std::min<uint64_t>(l.chunks, sms * (uint64_t)env_int("TTV_B200_STREAM_CTAS", 2));
+      l.kchunk = v.nq; l.kb = (uint32_t)v.nq;
+      l.smem_bytes = 3ull * l.stage_bytes + ((v.nq * s + 15) / 16 * 16) + 3 * 8;
+      l.workspace_bytes = 0;
+      *out = l;
+      return TTV_B200_OK;
+    }
+    if (forced == TTV_B200_KERNEL_STREAM) forced = 0;
+  }
+
   l.threads = (uint32_t)env_int("TTV_B200_THREADS", 256);
   if (l.threads < 32 || l.threads > 256 || (l.threads % 32)) return TTV_B200_ERR_OPTS;
   const uint64_t NT = l.threads;

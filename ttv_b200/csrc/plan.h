@@ -45,6 +45,9 @@ struct Launch {
   uint32_t kb      = 0;     // elements of b staged in shared memory per step
   uint64_t smem_bytes = 0;
   uint64_t workspace_bytes = 0;
+  // STREAM kernel only: slabs per shared-memory stage, bytes of one stage, number of chunks
+  uint64_t slabs_per_chunk = 0, chunks = 0;
+  uint32_t stage_bytes = 0;
 };
 
 int dtype_size(int dtype);          // bytes, 0 if unknown
