@@ -94,7 +94,8 @@ enum ttv_b200_kernel {
   TTV_B200_KERNEL_DOT    = 1,  /* mode q contiguous (inner == 1): cooperating lanes per fiber, shuffle reduction   */
   TTV_B200_KERNEL_COL    = 2,  /* column GEMV: thread owns contiguous outputs, streams A along inner                */
   TTV_B200_KERNEL_STREAM = 3,  /* small inner / small n_q: slab staged through shared memory with bulk copies       */
-  TTV_B200_KERNEL_COUNT  = 4
+  TTV_B200_KERNEL_COLX   = 4,  /* column GEMV for rows that start off 16-byte boundaries: phase lanes along n_q   */
+  TTV_B200_KERNEL_COUNT  = 5
 };
 
 enum ttv_b200_flags {

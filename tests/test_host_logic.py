@@ -180,6 +180,16 @@ def test_chooser_named_configs():
     # odd inner extent: scalar loads along inner; odd n_q: scalar loads along n_q
     assert ttv_b200.plan(2, [23, 23, 23], [1, 2, 3], dtype="f32")["vec"] == 1
     assert ttv_b200.plan(1, [23, 23, 23], [1, 2, 3], dtype="f32")["vec"] == 1
+    # odd WIDE rows: phase lanes along n_q keep 16-byte loads (COLX)
+    pl = ttv_b200.plan(2, [1625] * 3, [1, 2, 3], dtype="f32")
+    assert pl["kernel"] == 4 and pl["vec"] == 4 and pl["ty"] == 4 and pl["tx"] * 4 <= 256
+    pl = ttv_b200.plan(7, [21] * 7, [1, 2, 3, 4, 5, 6, 7], dtype="f64")        # short n_q: one warp per 31 vectors
+    assert pl["kernel"] == 4 and pl["vec"] == 2 and (pl["tx"], pl["ty"]) == (32, 1)
+    pl = ttv_b200.plan(3, [215] * 4, [1, 2, 3, 4], dtype="f64")
+    assert pl["kernel"] == 4 and pl["vec"] == 2 and pl["ty"] == 2
+    assert ttv_b200.plan(2, [1625] * 3, [1, 2, 3], dtype="c128")["kernel"] == 2
+    with pytest.raises(ttv_b200.TTVError):
+        ttv_b200.plan(2, [64, 64, 64], [1, 2, 3], dtype="c128", kernel="colx")
     # a single huge fiber: split n_q across CTAs
     pl = ttv_b200.plan(1, [1 << 26, 2], [1, 2], dtype="f32")
     assert pl["kernel"] == 1 and pl["ksplit"] > 64 and pl["workspace_bytes"] == pl["ksplit"] * 2 * 4
@@ -230,10 +240,20 @@ def test_chooser_only_picks_instantiated_kernels():
             if pl["kernel"] == 3:       # STREAM: slabs through shared memory, one kernel shape
                 assert nq * inner * size[dt] <= 8192 and pl["smem_bytes"] <= 227 * 1024 and pl["ksplit"] == 1
                 continue
+            if pl["kernel"] == 4:       # COLX: odd wide rows, 16-byte loads at any phase
+                assert key in {(1, 8), (2, 4), (4, 2)} and wide and size[dt] < 16, (dt, outer, nq, inner, pl)
+                assert inner * size[dt] >= 2048 and inner % (16 // size[dt]) != 0
+                if -(-nq // (16 // size[dt])) < 16:      # short contraction: warp-autonomous form, no shared memory
+                    assert (pl["tx"], pl["ty"], pl["smem_bytes"]) == (32, 1, 0) and pl["ku"] % (16 // size[dt]) == 0
+                else:
+                    assert pl["ty"] == 16 // size[dt] and pl["tx"] * pl["ty"] <= 256 and pl["smem_bytes"] <= 100 * 1024
+                continue
             if pl["kernel"] == 1:
                 allowed = {(1, 8), (2, 4), (4, 2), (8, 1)} if wide else {(1, 16), (2, 8), (4, 4), (8, 2), (8, 1)}
             else:
                 allowed = {(1, 8), (2, 4), (4, 2)} if wide else {(1, 16), (2, 8), (4, 4), (8, 2)}
+            if pl["ty"] > 1:
+                allowed = allowed | {(1, 8)}        # b read directly from L2: the one batch shape of that variant
             assert key in allowed, (dt, outer, nq, inner, pl)
             assert pl["tx"] * pl["ty"] * pl["to"] <= pl["threads"] <= 256
             assert pl["ksplit"] >= 1 and pl["ctas"] >= 1 and pl["smem_bytes"] <= 100 * 1024

@@ -314,3 +314,55 @@ def test_stream_kernel_small_slabs(dtype, oracle):
         assert np.array_equal(c, want), (na, pia, q, dtype)
         c0 = np.full(want.size, 3, dtype)
         assert np.array_equal(run_lowlevel(q, a, na, pia, b, c0=c0, kernel="stream", flags=1), want + 3)
+
+
+@pytest.mark.parametrize("form", ["cta", "warp", "auto"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.int32, np.int64])
+def test_colx_kernel_unaligned_rows(dtype, form, oracle, monkeypatch):
+    """kernel="colx", both forms (phase lanes across a CTA / all phases inside a warp): rows that start at every phase
+    of a 16-byte line (odd inner), several tiles per row, ragged last tile, a tensor whose last bytes are not a whole
+    vector, n_q shorter than the phase lanes, split n_q, accumulate; and the shapes the chooser routes there by itself"""
+    if form != "auto":
+        monkeypatch.setenv("TTV_B200_COLX_WARP", "1" if form == "warp" else "0")
+    rng = np.random.default_rng(12)
+    name = {np.float32: "f32", np.float64: "f64", np.complex64: "c64", np.int32: "i32", np.int64: "i64"}[dtype]
+    cases = [((37, 5, 3), (1, 2, 3), 2), ((1021, 9, 2), (1, 2, 3), 2), ((1021, 3), (1, 2), 2), ((333, 7, 5), (1, 2, 3), 3),
+             ((3, 1033, 6), (2, 1, 3), 3), ((2055, 70, 3), (1, 2, 3), 2), ((5, 413, 1, 9), (1, 2, 3, 4), 4), ((64, 10, 3), (1, 2, 3), 2),
+             ((2, 9, 3), (1, 2, 3), 2), ((4099, 33), (1, 2), 2)]
+    for na, pia, q in cases:
+        a, b = random_case(rng, na, q, dtype)
+        want = oracle.ttv(q, a, na, pia, b)
+        for extra in (dict(), dict(ksplit=3)):
+            pl = ttv_b200.plan(q, na, pia, dtype=name, kernel="colx", **extra)
+            assert pl["kernel"] == 4
+            c = run_lowlevel(q, a, na, pia, b, kernel="colx", **extra)
+            assert np.array_equal(c, want), (na, pia, q, extra)
+        c0 = np.full(want.size, 3, dtype)
+        assert np.array_equal(run_lowlevel(q, a, na, pia, b, c0=c0, kernel="colx", flags=1), want + 3)
+    # chosen automatically for wide odd rows
+    for na, pia, q in [((1625, 40, 3), (1, 2, 3), 2), ((23, 23, 23, 7), (1, 2, 3, 4), 4)]:
+        a, b = random_case(rng, na, q, dtype)
+        if np.dtype(dtype).itemsize * int(np.prod(na[: q - 1])) >= 2048:
+            assert ttv_b200.plan(q, na, pia, dtype=name)["kernel"] == 4
+        assert np.array_equal(run_lowlevel(q, a, na, pia, b), oracle.ttv(q, a, na, pia, b)), (na, pia, q)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex128, np.int32])
+def test_b_read_directly_from_l2(dtype, oracle, monkeypatch):
+    """lanes strung along n_q with a b that is too long to stay in shared memory read it inside the batches (no
+    re-staging, no __syncthreads in the main loop): chosen automatically for long n_q, forced on the small shapes"""
+    rng = np.random.default_rng(13)
+    name = {np.float32: "f32", np.float64: "f64", np.complex128: "c128", np.int32: "i32"}[dtype]
+    for na, pia, q in [((4, 6001, 3), (1, 2, 3), 2), ((70001, 3), (1, 2), 1), ((70004, 2), (1, 2), 1), ((2, 40000), (1, 2), 2)]:
+        a, b = random_case(rng, na, q, dtype)
+        want = oracle.ttv(q, a, na, pia, b)
+        for extra in (dict(), dict(ksplit=3)):
+            assert np.array_equal(run_lowlevel(q, a, na, pia, b, **extra), want), (na, pia, q, extra)
+    monkeypatch.setenv("TTV_B200_BDIRECT", "1")
+    for na, pia in [((8, 64, 6), (1, 2, 3)), ((300, 40), (1, 2)), ((300, 40), (2, 1)), ((2, 500, 3), (1, 2, 3)), ((16, 9, 33), (3, 1, 2)),
+                    ((4, 4100), (2, 1))]:
+        for q in range(1, len(na) + 1):
+            a, b = random_case(rng, na, q, dtype)
+            want = oracle.ttv(q, a, na, pia, b)
+            for extra in (dict(), dict(ksplit=2), dict(flags=4)):
+                assert np.array_equal(run_lowlevel(q, a, na, pia, b, **extra), want), (na, pia, q, extra)

@@ -93,6 +93,8 @@ def main():
     ap.add_argument("--only", default="", help="comma-separated config names to keep")
     ap.add_argument("--envs", default="", help="semicolon-separated env variants, e.g. 'TTV_B200_STREAM=0;TTV_B200_KU=4,TTV_B200_THREADS=128'")
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--ksplits", default="", help="comma-separated forced n_q splits to try on each config, e.g. '2,4,8'")
+    ap.add_argument("--qs", default="", help="comma-separated modes to keep")
     args = ap.parse_args()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     peak = 6553.9
@@ -107,6 +109,9 @@ def main():
             variants = [dict()]
             for spec in [e for e in args.envs.split(";") if e]:
                 variants.append(dict(env=dict(kv.split("=") for kv in spec.split(","))))
+            if args.qs and str(q) not in args.qs.split(","):
+                continue
+            variants += [dict(ksplit=int(k)) for k in args.ksplits.split(",") if k]
             if args.variants:
                 variants += [dict(env=dict(TTV_B200_THREADS=t, TTV_B200_KU=ku), ksplit=ks)
                              for t in ("128", "256") for ku in ("4", "8") for ks in (0, 1, 2, 4)]

@@ -45,7 +45,7 @@ struct TileParams {
   uint64_t kchunk;        // n_q elements per partition
   uint64_t itiles, otiles, tiles;
   uint64_t a_ustride;     // elements between two units of one thread in A
-  uint64_t c_ustride;     // ... and in C
+  uint64_t c_ustride;     // ... and in C  (COLX: the output columns owned by one tile)
   uint32_t tx, ty, to;
   uint32_t ksplit;
   uint32_t kb;            // elements of b per shared-memory chunk
@@ -101,13 +101,41 @@ __device__ __forceinline__ void col_batch(T (&acc)[NU][V], const T* ap, uint64_t
   }
 }
 
-template<class T, int V, int NU, int KU>
+// The same batch with b taken straight from global memory / L2 (bg = B + k0): lanes strung along n_q read consecutive
+// elements of b, and these loads are issued together with those of A.
+template<class T, int V, int NU, int KU, bool PRED>
+__device__ __forceinline__ void col_batch_bg(T (&acc)[NU][V], const T* ap, uint64_t a_ustride, uint64_t kstride, const T* bg,
+                                             uint32_t k, uint32_t tyn, uint32_t kn, int nvalid, bool stream)
+{
+  Vec<T, V> v[NU][KU];
+  T bb[KU];
+#pragma unroll
+  for (int s = 0; s < KU; ++s) {
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      if constexpr (PRED)
+        v[u][s] = (u < nvalid && k + s * tyn < kn) ? load_a<T, V>(ap + u * a_ustride + s * kstride, stream) : zero_vec<T, V>();
+      else
+        v[u][s] = load_a<T, V>(ap + u * a_ustride + s * kstride, stream);
+    }
+    if constexpr (PRED) bb[s] = (k + s * tyn < kn) ? bg[k + s * tyn] : Num<T>::zero();
+    else bb[s] = bg[k + s * tyn];
+  }
+#pragma unroll
+  for (int s = 0; s < KU; ++s)
+#pragma unroll
+    for (int u = 0; u < NU; ++u)
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[u][j] = Num<T>::madd(v[u][s].e[j], bb[s], acc[u][j]);
+}
+
+template<class T, int V, int NU, int KU, bool BG = false>
 __global__ void __launch_bounds__(256, min_ctas<NU, KU>())
 ttv_col_kernel(const TileParams P)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* sb  = reinterpret_cast<T*>(smem_raw);          // [kb]
-  T* red = sb + P.kb;                               // [threads][NU*V]
+  T* sb  = reinterpret_cast<T*>(smem_raw);          // [kb]   (nothing when b is read directly)
+  T* red = sb + (BG ? 0u : P.kb);                   // [threads][NU*V]
 
   const T* __restrict__ A = static_cast<const T*>(P.a);
   const T* __restrict__ B = static_cast<const T*>(P.b);
@@ -120,7 +148,8 @@ ttv_col_kernel(const TileParams P)
   const bool     live = to < P.to;
   const bool     stream = P.stream != 0;
   const uint64_t kstride = (uint64_t)P.ty * P.inner;      // elements between two k visited by one thread
-  const bool     b_resident = (P.ksplit == 1) && (P.nq <= P.kb);   // b fits: stage it once per CTA
+  constexpr bool bdirect = BG;                                     // b is not staged: kb spans the whole partition
+  const bool     b_resident = !bdirect && (P.ksplit == 1) && (P.nq <= P.kb);   // b fits: stage it once per CTA
 
   if (b_resident) {
     for (uint32_t j = tid; j < (uint32_t)P.nq; j += blockDim.x) sb[j] = B[j];
@@ -152,7 +181,7 @@ ttv_col_kernel(const TileParams P)
 
     for (uint64_t k0 = kbeg; k0 < kend; k0 += P.kb) {
       const uint32_t kn = (uint32_t)min((uint64_t)P.kb, kend - k0);
-      if (!b_resident) {
+      if (!b_resident && !bdirect) {       // (b_resident is false when bdirect)
         __syncthreads();
         for (uint32_t j = tid; j < kn; j += blockDim.x) sb[j] = B[k0 + j];
         __syncthreads();
@@ -160,11 +189,20 @@ ttv_col_kernel(const TileParams P)
       if (nvalid > 0) {
         const T* ap = A + (o * P.nq + k0 + ty) * P.inner + i0;
         uint32_t k = ty;
-        if (nvalid == NU)
-          for (; k + (KU - 1) * P.ty < kn; k += KU * P.ty, ap += KU * kstride)          // full batches
-            col_batch<T, V, NU, KU, false>(acc, ap, P.a_ustride, kstride, sb, k, P.ty, kn, nvalid, stream);
-        for (; k < kn; k += KU * P.ty, ap += KU * kstride)                              // edges
-          col_batch<T, V, NU, KU, true>(acc, ap, P.a_ustride, kstride, sb, k, P.ty, kn, nvalid, stream);
+        if constexpr (bdirect) {
+          const T* bg = B + k0;
+          if (nvalid == NU)
+            for (; k + (KU - 1) * P.ty < kn; k += KU * P.ty, ap += KU * kstride)
+              col_batch_bg<T, V, NU, KU, false>(acc, ap, P.a_ustride, kstride, bg, k, P.ty, kn, nvalid, stream);
+          for (; k < kn; k += KU * P.ty, ap += KU * kstride)
+            col_batch_bg<T, V, NU, KU, true>(acc, ap, P.a_ustride, kstride, bg, k, P.ty, kn, nvalid, stream);
+        } else {
+          if (nvalid == NU)
+            for (; k + (KU - 1) * P.ty < kn; k += KU * P.ty, ap += KU * kstride)          // full batches
+              col_batch<T, V, NU, KU, false>(acc, ap, P.a_ustride, kstride, sb, k, P.ty, kn, nvalid, stream);
+          for (; k < kn; k += KU * P.ty, ap += KU * kstride)                              // edges
+            col_batch<T, V, NU, KU, true>(acc, ap, P.a_ustride, kstride, sb, k, P.ty, kn, nvalid, stream);
+        }
       }
     }
 
@@ -234,6 +272,19 @@ __device__ __forceinline__ T shfl_xor_elem(T v, int mask)
   return r;
 }
 
+template<class T>
+__device__ __forceinline__ T shfl_down_elem(T v, int delta)
+{
+  static_assert(sizeof(T) % 4 == 0, "element size");
+  uint32_t w[sizeof(T) / 4];
+  memcpy(w, &v, sizeof(T));
+#pragma unroll
+  for (unsigned i = 0; i < sizeof(T) / 4; ++i) w[i] = __shfl_down_sync(0xffffffffu, w[i], delta);
+  T r;
+  memcpy(&r, w, sizeof(T));
+  return r;
+}
+
 // combines the ty partial sums of NU fibers and stores them (shared by the two DOT kernels)
 template<class T, int NU>
 __device__ __forceinline__ void dot_finish(T (&acc)[NU], const TileParams& P, T* red, T* C, uint32_t tid, uint32_t ty, bool live,
@@ -298,13 +349,40 @@ __device__ __forceinline__ void dot_batch(T (&acc)[NU], const T* ap, uint64_t a_
   }
 }
 
-template<class T, int V, int NU, int KU>
+// b vectors straight from global memory / L2 (bg = B + k0), issued together with the loads of A
+template<class T, int V, int NU, int KU, bool PRED>
+__device__ __forceinline__ void dot_batch_bg(T (&acc)[NU], const T* ap, uint64_t a_ustride, uint32_t kstep, const T* bg,
+                                             uint32_t k, uint32_t kn, int nvalid, bool stream)
+{
+  Vec<T, V> v[NU][KU];
+  Vec<T, V> bv[KU];
+#pragma unroll
+  for (int s = 0; s < KU; ++s) {
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      if constexpr (PRED)
+        v[u][s] = (u < nvalid && k + s * kstep < kn) ? load_a<T, V>(ap + u * a_ustride + s * kstep, stream) : zero_vec<T, V>();
+      else
+        v[u][s] = load_a<T, V>(ap + u * a_ustride + s * kstep, stream);
+    }
+    if constexpr (PRED) bv[s] = (k + s * kstep < kn) ? *reinterpret_cast<const Vec<T, V>*>(bg + k + s * kstep) : zero_vec<T, V>();
+    else bv[s] = *reinterpret_cast<const Vec<T, V>*>(bg + k + s * kstep);
+  }
+#pragma unroll
+  for (int s = 0; s < KU; ++s)
+#pragma unroll
+    for (int u = 0; u < NU; ++u)
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[u] = Num<T>::madd(v[u][s].e[j], bv[s].e[j], acc[u]);
+}
+
+template<class T, int V, int NU, int KU, bool BG = false>
 __global__ void __launch_bounds__(256, min_ctas<NU, KU>())
 ttv_dot_kernel(const TileParams P)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* sb  = reinterpret_cast<T*>(smem_raw);          // [kb]
-  T* red = sb + P.kb;                               // [threads][NU]
+  T* sb  = reinterpret_cast<T*>(smem_raw);          // [kb]   (nothing when b is read directly)
+  T* red = sb + (BG ? 0u : P.kb);                   // [threads][NU]
 
   const T* __restrict__ A = static_cast<const T*>(P.a);
   const T* __restrict__ B = static_cast<const T*>(P.b);
@@ -316,7 +394,8 @@ ttv_dot_kernel(const TileParams P)
   const bool     live = to < P.to;
   const bool     stream = P.stream != 0;
   const uint32_t kstep = P.ty * V;                   // n_q elements one pass of the fiber's lanes covers
-  const bool     b_resident = (P.ksplit == 1) && (P.nq <= P.kb);
+  constexpr bool bdirect = BG;
+  const bool     b_resident = !bdirect && (P.ksplit == 1) && (P.nq <= P.kb);
 
   if (b_resident) {
     for (uint32_t j = tid; j < (uint32_t)P.nq; j += blockDim.x) sb[j] = B[j];
@@ -341,7 +420,7 @@ ttv_dot_kernel(const TileParams P)
 
     for (uint64_t k0 = kbeg; k0 < kend; k0 += P.kb) {
       const uint32_t kn = (uint32_t)min((uint64_t)P.kb, kend - k0);   // multiple of V (nq % V == 0, kb % V == 0)
-      if (!b_resident) {
+      if (!b_resident && !bdirect) {       // (b_resident is false when bdirect)
         __syncthreads();
         for (uint32_t j = tid; j < kn; j += blockDim.x) sb[j] = B[k0 + j];
         __syncthreads();
@@ -349,11 +428,20 @@ ttv_dot_kernel(const TileParams P)
       if (nvalid > 0) {
         const T* ap = A + o * P.nq + k0 + (uint64_t)ty * V;
         uint32_t k = ty * V;
-        if (nvalid == NU)
-          for (; k + (KU - 1) * kstep < kn; k += KU * kstep, ap += KU * kstep)
-            dot_batch<T, V, NU, KU, false>(acc, ap, P.a_ustride, kstep, sb, k, kn, nvalid, stream);
-        for (; k < kn; k += KU * kstep, ap += KU * kstep)
-          dot_batch<T, V, NU, KU, true>(acc, ap, P.a_ustride, kstep, sb, k, kn, nvalid, stream);
+        if constexpr (bdirect) {
+          const T* bg = B + k0;
+          if (nvalid == NU)
+            for (; k + (KU - 1) * kstep < kn; k += KU * kstep, ap += KU * kstep)
+              dot_batch_bg<T, V, NU, KU, false>(acc, ap, P.a_ustride, kstep, bg, k, kn, nvalid, stream);
+          for (; k < kn; k += KU * kstep, ap += KU * kstep)
+            dot_batch_bg<T, V, NU, KU, true>(acc, ap, P.a_ustride, kstep, bg, k, kn, nvalid, stream);
+        } else {
+          if (nvalid == NU)
+            for (; k + (KU - 1) * kstep < kn; k += KU * kstep, ap += KU * kstep)
+              dot_batch<T, V, NU, KU, false>(acc, ap, P.a_ustride, kstep, sb, k, kn, nvalid, stream);
+          for (; k < kn; k += KU * kstep, ap += KU * kstep)
+            dot_batch<T, V, NU, KU, true>(acc, ap, P.a_ustride, kstep, sb, k, kn, nvalid, stream);
+        }
       }
     }
     dot_finish<T, NU>(acc, P, red, C, tid, ty, live, o, ks, nvalid);

@@ -6,6 +6,7 @@
 #include "launch.h"
 #include "kernels.cuh"
 #include "stream_kernel.cuh"
+#include "colx_kernel.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -64,6 +65,7 @@ cudaError_t launch_view(int dtype, const View& v, const Launch& l, const void* a
   P.ksplit = l.ksplit; P.kb = l.kb;
   P.accumulate = accumulate ? 1u : 0u;
   P.udir = l.udir; P.stream = l.stream;
+  if (l.kernel == TTV_B200_KERNEL_COLX) P.c_ustride = l.wcols;
 
   cudaError_t e = k_tile[dtype](P, l, stream);
   if (e != cudaSuccess || l.ksplit <= 1) return e;
@@ -125,6 +127,36 @@ static cudaError_t dispatch_batch(const TileParams& P, const Launch& l, cudaStre
         default: return cudaErrorInvalidValue;
       }
     }
+    return cudaErrorInvalidValue;
+  }
+  if (l.kernel == TTV_B200_KERNEL_COLX && l.warp) {
+    if constexpr (V > 1 && wide) {
+      switch (key) {
+        TTVB_BATCH_CASE(ttv_colw_kernel, 1, 8) TTVB_BATCH_CASE(ttv_colw_kernel, 2, 4)
+        default: break;
+      }
+      if constexpr (V == 2) {
+        switch (key) {
+          TTVB_BATCH_CASE(ttv_colw_kernel, 4, 2)
+          default: break;
+        }
+      }
+    }
+    return cudaErrorInvalidValue;
+  }
+  if (l.kernel == TTV_B200_KERNEL_COLX) {
+    if constexpr (V > 1 && wide) {
+      switch (key) {
+        TTVB_BATCH_CASE(ttv_colx_kernel, 1, 8) TTVB_BATCH_CASE(ttv_colx_kernel, 2, 4) TTVB_BATCH_CASE(ttv_colx_kernel, 4, 2)
+        default: return cudaErrorInvalidValue;
+      }
+    }
+    return cudaErrorInvalidValue;
+  }
+  if (l.bdirect) {      // b straight from L2 inside the batches: one batch shape, (1, 8)
+    if (key != 108) return cudaErrorInvalidValue;
+    if (l.kernel == TTV_B200_KERNEL_DOT) return launch_tile(ttv_dot_kernel<T, V, 1, 8, true>, P, l, stream);
+    if (l.kernel == TTV_B200_KERNEL_COL) return launch_tile(ttv_col_kernel<T, V, 1, 8, true>, P, l, stream);
     return cudaErrorInvalidValue;
   }
   if (l.kernel == TTV_B200_KERNEL_DOT) {

@@ -239,6 +239,96 @@ static int env_int(const char* name, int fallback)
   return (s && *s) ? std::atoi(s) : fallback;
 }
 
+// COLX launch shape.  TY = V lanes along n_q (one per phase), TX lanes along inner; a tile owns W output columns and
+// loads W/V + 1 vectors per row; W is chosen so that the tiles of a row are of (nearly) equal width.
+static int choose_colx(uint64_t s, const View& v, const ttv_b200_opts* opts, uint64_t sms, Launch* out)
+{
+  Launch l;
+  const uint64_t V = vmax_of(s), NT = 256;
+  uint64_t TY = (uint64_t)env_int("TTV_B200_COLX_TY", (int)V);
+  if (TY < V || TY > 32 || TY % V) return TTV_B200_ERR_OPTS;
+  const uint64_t txmax = NT / TY;
+  int want = opts ? opts->ksplit : 0;
+  if (want < 0) return TTV_B200_ERR_OPTS;
+  if (want == 0) want = env_int("TTV_B200_KSPLIT", 0);
+
+  l.kernel = TTV_B200_KERNEL_COLX;
+  l.threads = (uint32_t)NT;
+  l.vec = (int)V; l.ty = (uint32_t)TY; l.to = 1; l.udir = 0;
+  l.stream = (uint32_t)env_int("TTV_B200_STREAM", 1);
+
+  // Short contractions (fewer than 16 rows per phase lane): the per-tile prologue / shared-memory epilogue of the CTA
+  // form dominates (measured 23^7 q=4: 4.0 TB/s against 6.4 TB/s), so the warp-autonomous form runs them; long
+  // contractions are faster in the CTA form (1625^3 q=2: 7.3 against 6.8 TB/s), which keeps 3 CTAs per SM.
+  const int warp_mode = env_int("TTV_B200_COLX_WARP", -1);
+  if (warp_mode == 1 || (warp_mode == -1 && ceil_div(v.nq, TY) < 16)) {
+    // a warp owns 31*V columns per unit and all rows of its n_q partition
+    l.warp = 1; l.tx = 32; l.ty = 1;
+    uint64_t ku = v.nq <= 2 && V == 2 ? 2 : 4;
+    const int ku_env = env_int("TTV_B200_KU", 0);
+    if ((ku_env == 2 || ku_env == 4 || ku_env == 8) && (uint64_t)ku_env % V == 0) ku = (uint64_t)ku_env;
+    uint64_t nu = 8 / ku;
+    l.ku = (int)ku; l.nu = (int)nu;
+    l.wcols = 31 * V;
+    l.itiles = ceil_div(v.inner, nu * l.wcols);
+    l.otiles = v.outer;
+    const uint64_t tiles1 = l.itiles * l.otiles;
+    uint64_t ksplit = 1;
+    if (want > 0) ksplit = (uint64_t)want;
+    else if (tiles1 < sms * 8) ksplit = std::min(ceil_div(sms * 64, tiles1), std::max<uint64_t>(1, v.nq / (ku * 4)));
+    ksplit = std::max<uint64_t>(1, std::min(ksplit, v.nq));
+    const uint64_t kchunk = ceil_div(v.nq, ksplit);
+    ksplit = ceil_div(v.nq, kchunk);
+    l.ksplit = (uint32_t)ksplit; l.kchunk = kchunk;
+    l.tiles = tiles1 * ksplit;
+    l.ctas = std::min<uint64_t>(ceil_div(l.tiles, NT / 32), sms * 32);
+    l.kb = 0; l.smem_bytes = 0;
+    l.workspace_bytes = ksplit > 1 ? ksplit * v.outer * v.inner * s : 0;
+    *out = l;
+    return TTV_B200_OK;
+  }
+
+  // batch shape: 8 vector loads in flight per thread; short contractions take the depth that wastes least
+  const uint64_t per = ceil_div(v.nq, TY);
+  auto waste = [per](uint64_t d) { return (double)(ceil_div(per, d) * d - per) / (double)(ceil_div(per, d) * d); };
+  uint64_t ku = 8;
+  if (per >= 16) { while (ku > 2 && waste(ku) > 0.10) ku /= 2; }
+  else { ku = 2; for (uint64_t d = 4; d <= 8; d *= 2) if (waste(d) < waste(ku) - 1e-9) ku = d; }
+  const int ku_env = env_int("TTV_B200_KU", 0);
+  if (ku_env == 2 || ku_env == 4 || ku_env == 8) ku = (uint64_t)ku_env;
+  uint64_t nu = 8 / ku;
+  // units widen a tile: never starve the SMs of tiles for their sake
+  while (nu > 1 && ceil_div(v.inner, (txmax * nu - 1) * V) * v.outer < sms * 8) { nu /= 2; ku *= 2; }
+  l.ku = (int)ku; l.nu = (int)nu;
+
+  const uint64_t wmax = (txmax * nu - 1) * V;
+  l.itiles = ceil_div(v.inner, wmax);
+  l.wcols = ceil_div(ceil_div(v.inner, l.itiles), V) * V;              // <= wmax, multiple of V
+  l.tx = (uint32_t)ceil_div(l.wcols / V + 1, nu);                      // tx*nu vectors cover W columns at any phase
+  l.otiles = v.outer;
+  l.a_ustride = (uint64_t)l.tx * V;
+  l.c_ustride = (uint64_t)l.tx * V;
+
+  const uint64_t tiles1 = l.itiles * l.otiles, kstep = TY;
+  uint64_t ksplit = 1;
+  if (want > 0) ksplit = (uint64_t)want;
+  else if (tiles1 < sms) ksplit = std::min(ceil_div(sms * 8, tiles1), std::max<uint64_t>(1, v.nq / (kstep * 16)));
+  ksplit = std::max<uint64_t>(1, std::min(ksplit, ceil_div(v.nq, kstep)));
+  const uint64_t kchunk = ceil_div(ceil_div(v.nq, ksplit), kstep) * kstep;
+  ksplit = ceil_div(v.nq, kchunk);
+  l.ksplit = (uint32_t)ksplit; l.kchunk = kchunk;
+  l.tiles = tiles1 * ksplit;
+  l.ctas = std::min<uint64_t>(l.tiles, sms * 64);
+
+  uint64_t kb = std::min<uint64_t>(kchunk, 16384 / s);
+  kb = std::max<uint64_t>(kstep, kb / kstep * kstep);
+  l.kb = (uint32_t)kb;
+  l.smem_bytes = kb * s + TY * l.wcols * s;
+  l.workspace_bytes = ksplit > 1 ? ksplit * v.outer * v.inner * s : 0;
+  *out = l;
+  return TTV_B200_OK;
+}
+
 int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t align_a, uint64_t align_b,
                   uint64_t align_c, int sm_count, Launch* out)
 {
@@ -289,6 +379,22 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
       return TTV_B200_OK;
     }
     if (forced == TTV_B200_KERNEL_STREAM) forced = 0;
+  }
+
+  // COLX: wide rows that start off 16-byte boundaries (odd inner extent): phase lanes along n_q keep the loads at
+  // 16 bytes (colx_kernel.cuh).  Needs a 16-byte aligned A and an element type narrower than 16 bytes.
+  {
+    const uint64_t Vx = vmax_of(s);
+    const bool eligible = Vx > 1 && v.inner > 1 && (align_a % 16) == 0 && !(flags & TTV_B200_FLAG_NO_VEC);
+    if (forced == TTV_B200_KERNEL_COLX && !eligible) return TTV_B200_ERR_OPTS;
+    const int mode = env_int("TTV_B200_USE_COLX", -1);                                 // -1 auto, 0 never, 1 whenever eligible
+    const bool odd = (v.inner % Vx) != 0 || (align_c % 16) != 0;                       // the plain kernel would load narrow
+    const bool pick = forced == TTV_B200_KERNEL_COLX ? true
+                    : forced != 0 ? false
+                    : mode == 1 ? eligible
+                    : mode == 0 ? false
+                    : (eligible && odd && v.inner * s >= 2048);
+    if (pick) return choose_colx(s, v, opts, sms, out);
   }
 
   l.threads = (uint32_t)env_int("TTV_B200_THREADS", 256);
@@ -361,12 +467,27 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
     const uint64_t max_split = std::max<uint64_t>(1, v.nq / (kstep * 16));
     ksplit = std::min(ceil_div(sms * 8, tiles1), max_split);
   }
+  // Warp-per-fiber DOT on very long fibers: the resident warps all sit at the same offset of fibers that lie a large
+  // power of two apart, which camps on a few DRAM partitions (65536^2 fp32, q=1: 6.9 TB/s; 7.3 TB/s when the fibers
+  // are cut into ~8 KB pieces, because neighbouring CTAs then walk neighbouring pieces of the same fibers).
+  if (want == 0 && dot && !l.peel && l.ty == 32 && ksplit == 1 && v.nq * s >= 64 * 1024)
+    ksplit = std::min<uint64_t>(64, v.nq * s / 8192);
   if (l.peel) ksplit = 1;
   ksplit = std::max<uint64_t>(1, std::min(ksplit, ceil_div(v.nq, kstep)));
   uint64_t kchunk = ceil_div(ceil_div(v.nq, ksplit), kstep) * kstep;  // multiple of kstep keeps vectors aligned
   ksplit = ceil_div(v.nq, kchunk);
   l.ksplit = (uint32_t)ksplit;
   l.kchunk = kchunk;
+
+  // Lanes strung along n_q consume b as fast as rows of A; when b is too long to stay resident, re-staging it chunk by
+  // chunk puts two __syncthreads around every couple of batches (measured [1024, 262144, 4] fp32: 4.2 TB/s against
+  // 7.0 TB/s).  Those lanes read consecutive elements of b anyway, so they take them straight from L2 inside the batch.
+  {
+    const int mode = env_int("TTV_B200_BDIRECT", -1);
+    const bool can = l.ty > 1 && !l.peel && kchunk < (1ull << 31) && (!dot || (align_b % (V * s)) == 0);
+    const bool resident = ksplit == 1 && v.nq * s <= 16384;
+    if (can && (mode == 1 || (mode == -1 && !resident))) l.bdirect = 1;
+  }
 
   // batch shape: ku k-steps for each of nu units; nu*ku loads in flight per thread (128 bytes with 16-byte vectors,
   // 16 loads with narrower ones)
@@ -404,6 +525,7 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
     }
     if (!(nu == 8 && ku == 1)) ku = loads / nu;                      // only (nu, ku) with nu*ku == loads are instantiated
   }
+  if (l.bdirect) { ku = 8; nu = 1; }                                  // the one batch shape instantiated with direct b
   l.ku = (int)ku;
   l.nu = (int)nu;
 
@@ -430,9 +552,10 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
   uint64_t kb = std::min<uint64_t>(kchunk, 16384 / s);
   kb = std::max<uint64_t>(kstep, kb / kstep * kstep);
   if (kb * s > 96 * 1024) return TTV_B200_ERR_OPTS;
+  if (l.bdirect) kb = kchunk;
   l.kb = (uint32_t)kb;
   const uint64_t red_elems = NT * (uint64_t)l.nu * (dot ? 1 : V);
-  const uint64_t b_bytes = l.peel ? V * (ceil_div(v.nq, V) * V + V) * s : kb * s;
+  const uint64_t b_bytes = l.peel ? V * (ceil_div(v.nq, V) * V + V) * s : l.bdirect ? 0 : kb * s;
   l.smem_bytes = b_bytes + red_elems * s;
   l.workspace_bytes = ksplit > 1 ? ksplit * v.outer * v.inner * s : 0;
   *out = l;

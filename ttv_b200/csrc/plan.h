@@ -48,6 +48,10 @@ struct Launch {
   // STREAM kernel only: slabs per shared-memory stage, bytes of one stage, number of chunks
   uint64_t slabs_per_chunk = 0, chunks = 0;
   uint32_t stage_bytes = 0;
+  // COLX kernel only: output columns owned by one tile
+  uint64_t wcols = 0;
+  uint32_t bdirect = 0;     // b read straight from global memory / L2 (lanes along n_q, b too long to stay resident)
+  uint32_t warp = 0;        // COLX: warp-autonomous form (ttv_colw_kernel)
 };
 
 int dtype_size(int dtype);          // bytes, 0 if unknown
