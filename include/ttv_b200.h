@@ -95,7 +95,8 @@ enum ttv_b200_kernel {
   TTV_B200_KERNEL_COL    = 2,  /* column GEMV: thread owns contiguous outputs, streams A along inner                */
   TTV_B200_KERNEL_STREAM = 3,  /* small inner / small n_q: slab staged through shared memory with bulk copies       */
   TTV_B200_KERNEL_COLX   = 4,  /* column GEMV for rows that start off 16-byte boundaries: phase lanes along n_q   */
-  TTV_B200_KERNEL_COUNT  = 5
+  TTV_B200_KERNEL_DOTF   = 5,  /* mode q contiguous, short fibers: A read as one flat stream, partials via smem    */
+  TTV_B200_KERNEL_COUNT  = 6
 };
 
 enum ttv_b200_flags {

@@ -190,6 +190,9 @@ def test_chooser_named_configs():
     assert ttv_b200.plan(2, [1625] * 3, [1, 2, 3], dtype="c128")["kernel"] == 2
     with pytest.raises(ttv_b200.TTVError):
         ttv_b200.plan(2, [64, 64, 64], [1, 2, 3], dtype="c128", kernel="colx")
+    # many short aligned fibers: one flat stream (DOTF); long ones keep a lane group per fiber (DOT)
+    assert ttv_b200.plan(1, [40] * 6, [1, 2, 3, 4, 5, 6], dtype="f32")["kernel"] == 5
+    assert ttv_b200.plan(1, [256] * 4, [1, 2, 3, 4], dtype="f32")["kernel"] == 1
     # a single huge fiber: split n_q across CTAs
     pl = ttv_b200.plan(1, [1 << 26, 2], [1, 2], dtype="f32")
     assert pl["kernel"] == 1 and pl["ksplit"] > 64 and pl["workspace_bytes"] == pl["ksplit"] * 2 * 4
@@ -239,6 +242,11 @@ def test_chooser_only_picks_instantiated_kernels():
             key = (pl["nu"], pl["ku"])
             if pl["kernel"] == 3:       # STREAM: slabs through shared memory, one kernel shape
                 assert nq * inner * size[dt] <= 8192 and pl["smem_bytes"] <= 227 * 1024 and pl["ksplit"] == 1
+                continue
+            if pl["kernel"] == 5:       # DOTF: short aligned fibers as one flat stream
+                vec = 16 // size[dt]
+                assert inner == 1 and nq % vec == 0 and nq // vec <= 48 and pl["vec"] == vec and pl["ksplit"] == 1
+                assert pl["smem_bytes"] == (nq + 2048) * size[dt]
                 continue
             if pl["kernel"] == 4:       # COLX: odd wide rows, 16-byte loads at any phase
                 assert key in {(1, 8), (2, 4), (4, 2)} and wide and size[dt] < 16, (dt, outer, nq, inner, pl)

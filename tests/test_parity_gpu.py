@@ -298,7 +298,9 @@ def test_stream_kernel_small_slabs(dtype, oracle):
     rng = np.random.default_rng(17)
     cases = [((23, 23, 301), (1, 2, 3), 2), ((23, 1013), (1, 2), 1), ((21, 21, 77), (1, 2, 3), 1), ((3, 2, 5000), (1, 2, 3), 2),
              ((5, 7, 3, 211), (2, 1, 3, 4), 1), ((5, 7, 3, 211), (2, 1, 3, 4), 2), ((9, 4099), (1, 2), 1), ((2, 100003), (1, 2), 1),
-             ((1, 7, 13), (1, 2, 3), 2), ((40, 5, 6000), (1, 2, 3), 1)]
+             ((1, 7, 13), (1, 2, 3), 2), ((40, 5, 6000), (1, 2, 3), 1),
+             # fibers of even length are walked skewed (bank conflicts otherwise)
+             ((84, 3001), (1, 2), 1), ((4, 70001), (1, 2), 1), ((24, 5003), (1, 2), 1), ((128, 1001), (1, 2), 1), ((2, 3, 4099), (1, 2, 3), 1)]
     for na, pia, q in cases:
         a, b = random_case(rng, na, q, dtype)
         want = oracle.ttv(q, a, na, pia, b)
@@ -366,3 +368,28 @@ def test_b_read_directly_from_l2(dtype, oracle, monkeypatch):
             want = oracle.ttv(q, a, na, pia, b)
             for extra in (dict(), dict(ksplit=2), dict(flags=4)):
                 assert np.array_equal(run_lowlevel(q, a, na, pia, b, **extra), want), (na, pia, q, extra)
+
+
+@pytest.mark.parametrize("dtype", ALL_DTYPES)
+def test_dotf_kernel_short_fibers_as_one_stream(dtype, oracle):
+    """kernel="dotf": fibers of 1 ... 256 vectors read as one flat stream, warp-private partial sums; ragged last chunk,
+    fewer fibers than a chunk, odd and even vector counts (rotated summation), accumulate"""
+    rng = np.random.default_rng(21)
+    name = {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64", np.dtype(np.complex64): "c64",
+            np.dtype(np.complex128): "c128", np.dtype(np.int32): "i32", np.dtype(np.int64): "i64"}[np.dtype(dtype)]
+    vec = 16 // np.dtype(dtype).itemsize
+    for nv, fibers in [(1, 5000), (2, 3001), (3, 777), (5, 10000), (10, 2561), (21, 1300), (24, 999), (40, 650), (64, 300), (100, 70),
+                       (255, 40), (256, 33), (7, 3), (12, 1)]:
+        na, pia, q = (nv * vec, fibers), (1, 2), 1
+        a, b = random_case(rng, na, q, dtype)
+        want = oracle.ttv(q, a, na, pia, b)
+        assert ttv_b200.plan(q, na, pia, dtype=name, kernel="dotf")["kernel"] == 5
+        assert np.array_equal(run_lowlevel(q, a, na, pia, b, kernel="dotf"), want), (na, dtype)
+        c0 = np.full(want.size, 3, dtype)
+        assert np.array_equal(run_lowlevel(q, a, na, pia, b, c0=c0, kernel="dotf", flags=1), want + 3)
+    # order 3, mode q first in the layout but not mode 1
+    na, pia, q = (6, 4 * vec, 50), (2, 1, 3), 2
+    a, b = random_case(rng, na, q, dtype)
+    assert np.array_equal(run_lowlevel(q, a, na, pia, b, kernel="dotf"), oracle.ttv(q, a, na, pia, b))
+    with pytest.raises(ttv_b200.TTVError):
+        ttv_b200.plan(1, (vec + 1, 9), (1, 2), dtype=name, kernel="dotf") if vec > 1 else ttv_b200.plan(2, (4, 9), (1, 2), dtype=name, kernel="dotf")

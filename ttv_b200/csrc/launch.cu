@@ -7,6 +7,7 @@
 #include "kernels.cuh"
 #include "stream_kernel.cuh"
 #include "colx_kernel.cuh"
+#include "dotf_kernel.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -18,12 +19,14 @@ using tile_fn_t   = cudaError_t (*)(const TileParams&, const Launch&, cudaStream
 using reduce_fn_t = cudaError_t (*)(const void*, void*, uint64_t, uint32_t, bool, int, cudaStream_t);
 using fill_fn_t   = cudaError_t (*)(void*, uint64_t, uint64_t, uint64_t, int, cudaStream_t);
 using stream_fn_t = cudaError_t (*)(const StreamParams&, const Launch&, cudaStream_t);
+using dotf_fn_t   = cudaError_t (*)(const DotfParams&, const Launch&, cudaStream_t);
 
 #define TTVB_DECLARE(k)                                                                                          \
   cudaError_t tile_dtype_##k(const TileParams&, const Launch&, cudaStream_t);                                    \
   cudaError_t reduce_dtype_##k(const void*, void*, uint64_t, uint32_t, bool, int, cudaStream_t);                 \
   cudaError_t fill_dtype_##k(void*, uint64_t, uint64_t, uint64_t, int, cudaStream_t);                            \
-  cudaError_t stream_dtype_##k(const StreamParams&, const Launch&, cudaStream_t);
+  cudaError_t stream_dtype_##k(const StreamParams&, const Launch&, cudaStream_t);                               \
+  cudaError_t dotf_dtype_##k(const DotfParams&, const Launch&, cudaStream_t);
 TTVB_DECLARE(0) TTVB_DECLARE(1) TTVB_DECLARE(2) TTVB_DECLARE(3) TTVB_DECLARE(4) TTVB_DECLARE(5)
 #undef TTVB_DECLARE
 
@@ -39,6 +42,7 @@ static const tile_fn_t   k_tile[]   = {tile_dtype_0, tile_dtype_1, tile_dtype_2,
 static const reduce_fn_t k_reduce[] = {reduce_dtype_0, reduce_dtype_1, reduce_dtype_2, reduce_dtype_3, reduce_dtype_4, reduce_dtype_5};
 static const fill_fn_t   k_fill[]   = {fill_dtype_0, fill_dtype_1, fill_dtype_2, fill_dtype_3, fill_dtype_4, fill_dtype_5};
 static const stream_fn_t k_stream[] = {stream_dtype_0, stream_dtype_1, stream_dtype_2, stream_dtype_3, stream_dtype_4, stream_dtype_5};
+static const dotf_fn_t   k_dotf[]   = {dotf_dtype_0, dotf_dtype_1, dotf_dtype_2, dotf_dtype_3, dotf_dtype_4, dotf_dtype_5};
 
 cudaError_t launch_view(int dtype, const View& v, const Launch& l, const void* a, const void* b, void* c,
                         void* workspace, bool accumulate, int sm_count, cudaStream_t stream)
@@ -53,6 +57,16 @@ cudaError_t launch_view(int dtype, const View& v, const Launch& l, const void* a
     S.stage_bytes = l.stage_bytes;
     S.accumulate = accumulate ? 1u : 0u;
     return k_stream[dtype](S, l, stream);
+  }
+  if (l.kernel == TTV_B200_KERNEL_DOTF) {
+    DotfParams D;
+    D.a = a; D.b = b; D.c = c;
+    D.outer = v.outer; D.chunks = l.chunks;
+    D.nq = (uint32_t)v.nq; D.nv = (uint32_t)(v.nq / (uint64_t)l.vec); D.fw = (uint32_t)l.slabs_per_chunk;
+    D.accumulate = accumulate ? 1u : 0u;
+    D.lpf = 1;
+    while (D.lpf * 2 * (D.fw < 32 ? D.fw : 32) <= 32 && D.lpf * 2 <= D.nv) D.lpf *= 2;
+    return k_dotf[dtype](D, l, stream);
   }
   TileParams P;
   P.a = a; P.b = b;
@@ -211,10 +225,23 @@ cudaError_t TTVB_CAT(reduce_dtype_, TTVB_DTYPE)(const void* ws, void* c, uint64_
 
 cudaError_t TTVB_CAT(stream_dtype_, TTVB_DTYPE)(const StreamParams& S, const Launch& l, cudaStream_t stream)
 {
-  auto kern = ttv_stream_kernel<elem_t, 3, 4>;
+  // fibers (inner == 1) of even length are walked skewed: bank conflicts otherwise (stream_fibers_skewed)
+  auto kern = (S.inner == 1 && (S.nq & 1) == 0) ? ttv_stream_kernel<elem_t, 3, 4, true> : ttv_stream_kernel<elem_t, 3, 4, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes);
   if (e != cudaSuccess) return e;
   kern<<<(unsigned)l.ctas, l.threads, l.smem_bytes, stream>>>(S);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t TTVB_CAT(dotf_dtype_, TTVB_DTYPE)(const DotfParams& D, const Launch& l, cudaStream_t stream)
+{
+  auto kern = ttv_dotf_kernel<elem_t, kVmax>;
+  if (l.smem_bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes);
+    if (e != cudaSuccess) return e;
+  }
+  kern<<<(unsigned)l.ctas, l.threads, l.smem_bytes, stream>>>(D);
   count_launch();
   return cudaGetLastError();
 }

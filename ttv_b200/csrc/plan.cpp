@@ -226,6 +226,7 @@ static unsigned stream_conflict_degree(uint64_t M, uint64_t inner, uint64_t s)
 {
   const uint64_t w = std::max<uint64_t>(1, s / 4), lanes = 32 / std::min<uint64_t>(w, 4);
   unsigned count[32] = {0}, worst = 0;
+  if (inner == 1 && M % 2 == 0) M += 1;          // even fibers are walked skewed (stream_fibers_skewed): odd lane stride
   for (uint64_t u = 0; u < lanes; ++u) {
     const uint64_t bank = (((u / inner) * M + (u % inner)) * w) % 32;
     worst = std::max(worst, ++count[bank]);
@@ -381,6 +382,37 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
     if (forced == TTV_B200_KERNEL_STREAM) forced = 0;
   }
 
+  // DOTF: short contiguous fibers read as one flat stream (dotf_kernel.cuh).  Measured against the lane-group DOT kernel:
+  // 40 floats 7.0 against 6.0 TB/s, 84 floats 6.95 / 6.4, 40 complex<double> 6.4 / 5.5, 4 floats 6.9 / 6.4; from 64
+  // vectors per fiber on the lane groups are as good or better (256 floats: 6.9 / 7.2), so they keep those.
+  {
+    const uint64_t Vf = vmax_of(s);
+    const uint64_t nvf = v.nq / Vf;
+    const bool eligible = v.inner == 1 && v.nq % Vf == 0 && nvf >= 1 && nvf <= 256 && (align_a % 16) == 0 && (align_b % 16) == 0 &&
+                          (!opts || opts->ksplit <= 1) && !(flags & TTV_B200_FLAG_NO_VEC);
+    if (forced == TTV_B200_KERNEL_DOTF && !eligible) return TTV_B200_ERR_OPTS;
+    const int mode = env_int("TTV_B200_USE_DOTF", -1);
+    const bool pick = forced == TTV_B200_KERNEL_DOTF ? true
+                    : forced != 0 ? false
+                    : mode == 1 ? eligible
+                    : mode == 0 ? false
+                    : (eligible && nvf <= (uint64_t)env_int("TTV_B200_DOTF_NV", 48) && v.outer >= sms * 64);
+    if (pick) {
+      l.kernel = TTV_B200_KERNEL_DOTF;
+      l.threads = 256;
+      l.vec = (int)Vf; l.tx = 1; l.ty = 1; l.to = 1; l.nu = 1; l.ku = 8; l.ksplit = 1; l.stream = 0; l.udir = 1;
+      l.slabs_per_chunk = 256 / nvf;                                  // whole fibers per chunk of 256 vectors
+      l.chunks = ceil_div(v.outer, l.slabs_per_chunk);
+      l.tiles = l.chunks;
+      l.ctas = std::min<uint64_t>(ceil_div(l.chunks, 8), sms * 24);
+      l.kchunk = v.nq; l.kb = (uint32_t)v.nq;
+      l.smem_bytes = v.nq * s + 8 * 256 * s;
+      l.workspace_bytes = 0;
+      *out = l;
+      return TTV_B200_OK;
+    }
+  }
+
   // COLX: wide rows that start off 16-byte boundaries (odd inner extent): phase lanes along n_q keep the loads at
   // 16 bytes (colx_kernel.cuh).  Needs a 16-byte aligned A and an element type narrower than 16 bytes.
   {
@@ -429,6 +461,10 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
     if (l.peel) ty = std::max<uint64_t>(ty, V == 4 ? 4 : 1);     // two rounds of ty lanes cover the 2V-2 head/tail elements
     // few fibers: put more lanes on each one, as long as every lane keeps at least four vectors
     while (!l.peel && ty < NT && kv / (ty * 2) >= 4 && ceil_div(v.outer, std::max<uint64_t>(1, NT / ty)) < sms * 2) ty *= 2;
+    {
+      const int ty_env = env_int("TTV_B200_DOT_TY", 0);                 // experiments: lanes per fiber (power of two)
+      if (ty_env > 0 && !l.peel && pow2_ceil((uint64_t)ty_env) == (uint64_t)ty_env && (uint64_t)ty_env <= NT) ty = (uint64_t)ty_env;
+    }
     const uint64_t to = std::max<uint64_t>(1, std::min<uint64_t>(NT / ty, v.outer));
     l.ty = (uint32_t)ty; l.to = (uint32_t)to;
     l.udir = 1;

@@ -97,7 +97,39 @@ __device__ __forceinline__ void stream_outputs(const T* slab0, const T* sb, T* c
   }
 }
 
-template<class T, int NS, int UO>
+// Fibers (inner == 1) of EVEN length: lane u reading element k of fiber u hits bank (u*nq + k) % 32, which collides
+// for even nq.  Each lane therefore starts its fiber at k = u % nq and wraps around: lane u then reads word
+// u*(nq + 1) + t, an odd stride, conflict-free.  b is read per lane at the same rotated index.
+template<class T, int UO>
+__device__ __forceinline__ void stream_fibers_skewed(const T* slab0, const T* sb, T* cbase, uint32_t u0, uint32_t step, uint32_t nq,
+                                                     uint32_t accumulate)
+{
+  T acc[UO];
+  const T* base[UO];
+  uint32_t kk[UO];
+#pragma unroll
+  for (int j = 0; j < UO; ++j) {
+    const uint32_t u = u0 + j * step;
+    base[j] = slab0 + (size_t)u * nq;
+    kk[j] = u % nq;
+    acc[j] = Num<T>::zero();
+  }
+#pragma unroll 4
+  for (uint32_t t = 0; t < nq; ++t) {
+#pragma unroll
+    for (int j = 0; j < UO; ++j) {
+      acc[j] = Num<T>::madd(base[j][kk[j]], sb[kk[j]], acc[j]);
+      kk[j] = (kk[j] + 1 == nq) ? 0u : kk[j] + 1;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < UO; ++j) {
+    T* out = cbase + u0 + j * step;
+    *out = accumulate ? Num<T>::add(*out, acc[j]) : acc[j];
+  }
+}
+
+template<class T, int NS, int UO, bool SKEW = false>
 __global__ void __launch_bounds__(256, 2)
 ttv_stream_kernel(const StreamParams P)
 {
@@ -169,11 +201,19 @@ ttv_stream_kernel(const StreamParams P)
     }
 
     const uint32_t outs = ns * inner;                               // outputs of this chunk
-    for (uint32_t u0 = tid; u0 < outs; u0 += UO * blockDim.x) {
-      // outputs u0, u0 + NT, ... of this thread; a full set of UO shares every b[k], stragglers go one by one
-      if (u0 + (UO - 1) * blockDim.x < outs) stream_outputs<T, UO>(slab0, sb, C + o0 * inner, u0, blockDim.x, nq, inner, M, P.accumulate);
-      else
-        for (uint32_t u = u0; u < outs; u += blockDim.x) stream_outputs<T, 1>(slab0, sb, C + o0 * inner, u, blockDim.x, nq, inner, M, P.accumulate);
+    if constexpr (SKEW) {                                           // inner == 1, even n_q (chosen by the launcher)
+      for (uint32_t u0 = tid; u0 < outs; u0 += UO * blockDim.x) {
+        if (u0 + (UO - 1) * blockDim.x < outs) stream_fibers_skewed<T, UO>(slab0, sb, C + o0, u0, blockDim.x, nq, P.accumulate);
+        else
+          for (uint32_t u = u0; u < outs; u += blockDim.x) stream_fibers_skewed<T, 1>(slab0, sb, C + o0, u, blockDim.x, nq, P.accumulate);
+      }
+    } else {
+      for (uint32_t u0 = tid; u0 < outs; u0 += UO * blockDim.x) {
+        // outputs u0, u0 + NT, ... of this thread; a full set of UO shares every b[k], stragglers go one by one
+        if (u0 + (UO - 1) * blockDim.x < outs) stream_outputs<T, UO>(slab0, sb, C + o0 * inner, u0, blockDim.x, nq, inner, M, P.accumulate);
+        else
+          for (uint32_t u = u0; u < outs; u += blockDim.x) stream_outputs<T, 1>(slab0, sb, C + o0 * inner, u, blockDim.x, nq, inner, M, P.accumulate);
+      }
     }
 
     // everybody is done with this stage: hand it back to the TMA unit for chunk it + NS
