@@ -71,8 +71,10 @@ enum ttv_b200_status {
   TTV_B200_ERR_LAYOUT_BEGIN    = 20,  /* tensor_times_vector.h:160 */
   TTV_B200_ERR_LAYOUT_END      = 21,  /* tensor_times_vector.h:164 */
   /* not in the reference: conditions it leaves undefined or cannot meet */
-  TTV_B200_ERR_NOT_PACKED      = 30,  /* wa/wc/nc are not the packed strides/shape of (na, pia, q); the reference
-                                         asserts or silently assumes this (tensor_times_vector.h:956, mtv ignores wa) */
+  TTV_B200_ERR_NOT_PACKED      = 30,  /* non-packed strides whose free modes cannot be matched between A and C (nc is not
+                                         na without q, or more than 8 unfoldable free modes).  Valid non-packed strides
+                                         ARE honoured in case 8, like the reference's slice variants do
+                                         (tensor_times_vector.h:189-216); cases 1-7 ignore wa/wc like mtv does */
   TTV_B200_ERR_DTYPE           = 31,
   TTV_B200_ERR_OPTS            = 32,
   TTV_B200_ERR_CUDA            = 40,  /* no device, launch or runtime failure; text in ttv_b200_last_error() */
@@ -96,13 +98,19 @@ enum ttv_b200_kernel {
   TTV_B200_KERNEL_STREAM = 3,  /* small inner / small n_q: slab staged through shared memory with bulk copies       */
   TTV_B200_KERNEL_COLX   = 4,  /* column GEMV for rows that start off 16-byte boundaries: phase lanes along n_q   */
   TTV_B200_KERNEL_DOTF   = 5,  /* mode q contiguous, short fibers: A read as one flat stream, partials via smem    */
+  TTV_B200_KERNEL_STRIDED = 6, /* reported only: non-packed strides (case 8), general-stride kernel; cannot be forced  */
   TTV_B200_KERNEL_COUNT  = 6
 };
 
 enum ttv_b200_flags {
   TTV_B200_FLAG_ACCUMULATE = 1,   /* C += A x_q b                                                        */
   TTV_B200_FLAG_ASYNC      = 2,   /* device pointers only: return after enqueueing on opts->stream       */
-  TTV_B200_FLAG_NO_VEC     = 4    /* testing: force scalar loads                                          */
+  TTV_B200_FLAG_NO_VEC     = 4,   /* testing: force scalar loads                                          */
+  TTV_B200_FLAG_HONOR_STRIDES = 8 /* take wa, wc and pic at their word in EVERY case: the reference (and this library
+                                     by default) ignores them in cases 1-7 (mtv, matrix_times_vector.h:314-336).  With
+                                     it, padded tensors and a C with a layout of its own work for any q; packed
+                                     inputs still take the fast kernels.  The numpy / torch front ends set it for
+                                     arrays that are not contiguous. */
 };
 
 typedef struct ttv_b200_opts {

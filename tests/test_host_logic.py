@@ -140,9 +140,17 @@ def test_layout_end_mismatch():
     assert st == 21 and "end of layout tuples" in msg
 
 
-def test_non_packed_strides_are_rejected_in_case_8_only():
+def test_non_packed_strides_take_the_general_stride_kernel_in_case_8_only():
     one = C.c_void_p(64)
+    # padded leading dimension of A (ld 8 for 4 rows), packed C: honoured like the reference's slice variants do
     st, msg = _plan_status(2, 3, one, [4, 3, 2], [1, 8, 24], [1, 2, 3], one, [3], one, [4, 2], [1, 4], [1, 2])
+    assert st == 0, msg
+    pl = ttv_b200.plan(2, [4, 3, 2], [1, 2, 3], dtype="f64", wa=[1, 8, 24])
+    assert pl["kernel"] == 6 and (pl["outer"], pl["nq"], pl["inner"]) == (2, 3, 4)
+    assert ttv_b200.plan(2, [4, 3, 2], [1, 2, 3], dtype="f64", wc=[1, 6])["kernel"] == 6
+    assert ttv_b200.plan(2, [4, 3, 2], [1, 2, 3], dtype="f64")["kernel"] == 2
+    # C's shape must be A's without mode q when the strides have to be matched up
+    st, msg = _plan_status(2, 3, one, [4, 3, 2], [1, 8, 24], [1, 2, 3], one, [3], one, [4, 3], [1, 4], [1, 2])
     assert st == 30, msg
     # cases 1-7 ignore wa / wc exactly like the reference's mtv (matrix_times_vector.h:314-336)
     st, _ = _plan_status(1, 3, one, [4, 3, 2], [1, 8, 24], [1, 2, 3], one, [4], one, [3, 2], [1, 3], [1, 2])
@@ -267,3 +275,19 @@ def test_chooser_only_picks_instantiated_kernels():
             assert pl["ksplit"] >= 1 and pl["ctas"] >= 1 and pl["smem_bytes"] <= 100 * 1024
             if pl["kernel"] == 2:
                 assert inner % pl["vec"] == 0
+
+
+def test_layout_and_strides_of_numpy_arrays():
+    """the front end reads arrays in place: layout = order of the strides, wa = the strides, and the honour-strides
+    flag only when they are not the packed strides of that layout"""
+    from ttv_b200.api import _layout_of
+    x = np.zeros((4, 5, 6))
+    assert _layout_of(x, None) == ([3, 2, 1], [30, 6, 1], False)                       # C order = last-order
+    assert _layout_of(np.asfortranarray(x), None) == ([1, 2, 3], [1, 4, 20], False)    # F order = first-order
+    assert _layout_of(x.transpose(1, 0, 2), None) == ([3, 1, 2], [6, 30, 1], False)    # a permuted, still packed layout
+    assert _layout_of(x[:, :3, :], None) == ([3, 2, 1], [30, 6, 1], True)              # slice: padded
+    assert _layout_of(x[:, :, ::2], None) == ([3, 2, 1], [30, 6, 2], True)             # fastest mode strided
+    assert _layout_of(x[::-1], None) is None                                           # reversed axis: copy
+    assert _layout_of(np.broadcast_to(np.zeros(6), (4, 5, 6)), None) is None           # broadcast axes: copy
+    pia, wa, honor = _layout_of(np.zeros((4, 1, 6)), None)
+    assert ttv_b200.is_valid_strides(pia, wa) and not honor

@@ -393,3 +393,86 @@ def test_dotf_kernel_short_fibers_as_one_stream(dtype, oracle):
     assert np.array_equal(run_lowlevel(q, a, na, pia, b, kernel="dotf"), oracle.ttv(q, a, na, pia, b))
     with pytest.raises(ttv_b200.TTVError):
         ttv_b200.plan(1, (vec + 1, 9), (1, 2), dtype=name, kernel="dotf") if vec > 1 else ttv_b200.plan(2, (4, 9), (1, 2), dtype=name, kernel="dotf")
+
+
+def _padded(rng, na, wa, dtype):
+    """a logical tensor X of shape na and the flat buffer that holds it with element strides wa (padding = 77)"""
+    x = rng.integers(-8, 9, na).astype(dtype)
+    span = 1 + sum((n - 1) * w for n, w in zip(na, wa))
+    buf = np.full(span, 77, dtype)
+    view = np.lib.stride_tricks.as_strided(buf, shape=na, strides=[w * buf.itemsize for w in wa])
+    view[...] = x
+    return x, buf
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex128, np.int32])
+def test_non_packed_strides(dtype, oracle):
+    """padded strides in case 8: honoured like the reference's slice variants
+    (tensor_times_vector.h:189-216), results against the oracle's slice nest on the same padded buffers and against the
+    definition; the padding of C comes back untouched; host and device buffers"""
+    import torch
+    rng = np.random.default_rng(31)
+    code = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.complex128): 3, np.dtype(np.int32): 4}[np.dtype(dtype)]
+    cases = [
+        # na, pia, q, wa, wc   (pic is derived; strides are valid = non-decreasing along the layout)
+        ((4, 3, 2), (1, 2, 3), 2, (1, 8, 24), (1, 4)),             # padded leading dimension of A
+        ((4, 3, 2), (1, 2, 3), 2, (1, 4, 12), (1, 6)),             # padded C only
+        ((5, 6, 7, 3), (1, 2, 3, 4), 3, (1, 8, 50, 400), (1, 7, 45)),
+        ((5, 6, 7, 3), (2, 1, 4, 3), 4, (9, 1, 200, 60), (7, 1, 50)),
+        ((33, 5, 40, 2), (1, 2, 3, 4), 2, (1, 40, 200, 8000), (1, 40, 1600)),      # folds partly: modes 3, 4 stay packed
+        ((3, 300, 4), (1, 2, 3), 2, (1, 4, 1300), (1, 5)),
+    ]
+    for na, pia, q, wa, wc in cases:
+        p = len(na)
+        nc = ttv_b200.generate_output_shape(na, q); pic = ttv_b200.generate_output_layout(pia, q)
+        x, a = _padded(rng, na, wa, dtype)
+        b = rng.integers(-8, 9, na[q - 1]).astype(dtype)
+        want = np.tensordot(x, b, axes=([q - 1], [0]))
+        span_c = 1 + sum((n - 1) * w for n, w in zip(nc, wc))
+        assert ttv_b200.plan(q, na, pia, dtype=code, wa=list(wa), wc=list(wc))["kernel"] == 6
+        for where in ("host", "device"):
+            c = np.full(span_c, 55, dtype)
+            if where == "host":
+                ttv_b200.ttv_lowlevel(q, p, a, na, wa, pia, b, [len(b)], c, nc, wc, pic)
+            else:
+                ta, tb, tc = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), torch.from_numpy(c).cuda()
+                ttv_b200.ttv_lowlevel(q, p, ta, na, wa, pia, tb, [len(b)], tc, nc, wc, pic)
+                c = tc.cpu().numpy()
+            got = np.lib.stride_tricks.as_strided(c, shape=nc, strides=[w * c.itemsize for w in wc])
+            assert np.array_equal(got, want), (na, pia, q, wa, wc, where)
+            touched = np.zeros(span_c, bool)
+            np.lib.stride_tricks.as_strided(touched, shape=nc, strides=list(wc))[...] = True
+            assert np.all(c[~touched] == 55), "padding of C was written"
+        # the oracle's slice nest (the reference's algorithm) on the same buffers; it accumulates into a zeroed C
+        c_or = np.zeros(span_c, dtype)
+        u = lambda t: np.asarray(t, np.uint64)
+        assert oracle.run_raw(code, 0, q, p, a, u(na), u(wa), u(pia), b, u([len(b)]), c_or, u(nc), u(wc), u(pic)) == 0
+        assert np.array_equal(np.lib.stride_tricks.as_strided(c_or, shape=nc, strides=[w * c_or.itemsize for w in wc]), want)
+        # accumulate
+        c = np.full(span_c, 3, dtype)
+        ttv_b200.ttv_lowlevel(q, p, a, na, wa, pia, b, [len(b)], c, nc, wc, pic, flags=1)
+        assert np.array_equal(np.lib.stride_tricks.as_strided(c, shape=nc, strides=[w * c.itemsize for w in wc]), want + 3)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int64])
+def test_arrays_that_are_not_contiguous_are_read_in_place(dtype):
+    """numpy / torch front end: transposes, slices and strided views for EVERY q -- also the cases
+    1-7 in which the C-ABI ignores strides by default (TTV_B200_FLAG_HONOR_STRIDES) -- against np.tensordot"""
+    import torch
+    rng = np.random.default_rng(41)
+    base = rng.integers(-8, 9, (9, 10, 11, 6)).astype(dtype)
+    views = [base, base.transpose(2, 0, 3, 1), base[1:8, :, 2:9, :], base[:, ::2, :, ::3], base[:, 3, :, :], base[..., 0],
+             np.asfortranarray(base)[:, 2:7], base[:, :, :, 1:2], base[::-1], base[2, :, :, 4].T]
+    for x in views:
+        for q in range(1, x.ndim + 1):
+            b = rng.integers(-8, 9, x.shape[q - 1]).astype(dtype)
+            want = np.tensordot(x, b, axes=([q - 1], [0]))
+            got = ttv_b200.ttv(q, x, b)
+            assert got.shape == want.shape and np.array_equal(got, want), (x.shape, x.strides, q)
+            assert np.array_equal(ttv_b200.ttvpy.ttv(q, x, b), want)
+            if min(x.strides) > 0:
+                tx = torch.from_numpy(base).cuda().as_strided(x.shape, [s // x.itemsize for s in x.strides],
+                                                              (x.__array_interface__["data"][0] - base.__array_interface__["data"][0]) // x.itemsize) \
+                    if np.shares_memory(x, base) else torch.from_numpy(np.ascontiguousarray(x)).cuda()
+                tg = ttv_b200.ttv(q, tx, torch.from_numpy(b).cuda())
+                assert np.array_equal(tg.cpu().numpy(), want), (x.shape, x.strides, q, "device")

@@ -250,26 +250,55 @@ def fill(x, seed: int, first: int = 0, count: int | None = None) -> None:
 
 
 # ---- the tensor-level interface ----------------------------------------------------------------------------------------
-def _layout_of(x, layout) -> list[int]:
+def _element_strides(x):
+    """strides of a numpy array / torch tensor in elements, or None when they are not whole positive element counts"""
+    if _is_torch(x):
+        st = [int(v) for v in x.stride()]
+    else:
+        if any(v % x.itemsize for v in x.strides):
+            return None
+        st = [int(v) // x.itemsize for v in x.strides]
+    if any(v <= 0 and n > 1 for v, n in zip(st, x.shape)):
+        return None                                   # reversed or broadcast axes: not a layout
+    return st
+
+
+def _layout_of(x, layout):
+    """(pia, wa, honor) for an array.  A C-contiguous array is a last-order tensor (what ttvpy assumes,
+    wrapped_ttv.cpp:44-45), an F-contiguous one a first-order tensor; any other array with positive strides that do not
+    overlap is a tensor whose layout is the order of its strides, possibly padded (slices, transposes): it is read IN
+    PLACE through wa with TTV_B200_FLAG_HONOR_STRIDES.  Returns None when the array has to be copied first."""
     p = x.ndim
+    shape = [int(v) for v in x.shape]
     if layout is not None:
         layout = [int(v) for v in layout]
         if len(layout) != p:
             raise TTVError(16, "Error in tlib::tensor: shape vector and layout vector must have the same length.")
-        return layout
-    # a C-contiguous array is a last-order tensor (what ttvpy assumes, wrapped_ttv.cpp:44-45); an F-contiguous one
-    # is a first-order tensor
-    if _is_torch(x):
-        if x.is_contiguous():
-            return generate_k_order_layout(p, 0)
-        if x.permute(*reversed(range(p))).is_contiguous():
-            return generate_k_order_layout(p, 1)
-    else:
-        if x.flags.c_contiguous:
-            return generate_k_order_layout(p, 0)
-        if x.flags.f_contiguous:
-            return generate_k_order_layout(p, 1)
-    raise TTVError(30, "Error in ttv_b200: the array is neither C- nor F-contiguous; pass a packed array.")
+        return layout, generate_strides(shape, layout), False
+    c_contig = x.is_contiguous() if _is_torch(x) else x.flags.c_contiguous
+    if c_contig:
+        pia = generate_k_order_layout(p, 0)
+        return pia, generate_strides(shape, pia), False
+    st = _element_strides(x)
+    if st is None:
+        return None
+    # layout = modes by ascending stride (extent-1 modes last: their stride is meaningless)
+    order = sorted(range(p), key=lambda m: (shape[m] == 1, st[m], m))
+    need = 1
+    for m in order:
+        if shape[m] > 1:
+            if st[m] < need:
+                return None                           # overlapping elements
+            need = st[m] * shape[m]
+    pia = [m + 1 for m in order]
+    wa = [max(1, v) for v in st]
+    top = 1
+    for m in order:                                   # extent-1 modes: give them a stride that keeps wa valid
+        if shape[m] == 1:
+            wa[m] = top
+        top = max(top, wa[m] * shape[m])
+    packed = wa == generate_strides(shape, pia) or all(shape[m] == 1 or wa[m] == w for m, w in enumerate(generate_strides(shape, pia)))
+    return pia, wa, not packed
 
 
 def ttv(q: int, A, b, *, layout: Sequence[int] | None = None, out=None, **opt_kwargs):
@@ -279,9 +308,18 @@ def ttv(q: int, A, b, *, layout: Sequence[int] | None = None, out=None, **opt_kw
     Returns an array of the same kind with shape A.shape minus mode q, stored in the output layout."""
     shape = opt_kwargs.pop("shape", None)
     torch_in = _is_torch(A)
+    if not torch_in:
+        A = np.asarray(A)
+    wa = None
     if shape is None:
         shape = [int(s) for s in A.shape]
-        pia = _layout_of(A, layout)
+        desc = _layout_of(A, layout)
+        if desc is None:                               # reversed / broadcast / overlapping axes: pack a copy
+            A = A.contiguous() if torch_in else np.ascontiguousarray(A)
+            desc = _layout_of(A, None)
+        pia, wa, honor = desc
+        if honor:
+            opt_kwargs["flags"] = int(opt_kwargs.get("flags", 0)) | 8        # TTV_B200_FLAG_HONOR_STRIDES
     else:
         shape = [int(s) for s in shape]
         pia = [int(v) for v in layout] if layout is not None else generate_k_order_layout(len(shape), 1)
@@ -294,7 +332,8 @@ def ttv(q: int, A, b, *, layout: Sequence[int] | None = None, out=None, **opt_kw
         raise TTVError(15, _lib.load().ttv_b200_strerror(15).decode())
     nc = generate_output_shape(shape, q)
     pic = generate_output_layout(pia, q)
-    wa = generate_strides(shape, pia)
+    if wa is None:
+        wa = generate_strides(shape, pia)
     wc = generate_strides(nc, pic)
     n_out = int(np.prod(nc, dtype=object))
     nb = [int(b.shape[0])] if b.ndim >= 1 else [1]

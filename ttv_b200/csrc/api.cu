@@ -124,6 +124,11 @@ int run_view_device(int dtype, const View& v, const void* a, const void* b, void
   DeviceState* st = nullptr;
   if (int rc = device_state(device, &st)) return rc;
 
+  if (v.strided) {
+    CUDA_TRY(launch_strided(dtype, v, a, b, c, accumulate, st->sm_count, stream), "kernel launch");
+    if (sync) CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+    return TTV_B200_OK;
+  }
   Launch l;
   int rc = choose_launch(dtype, v, opts, alignment_of(a), alignment_of(b), alignment_of(c), st->sm_count, &l);
   if (rc) return fail(rc);
@@ -152,11 +157,12 @@ int run_view_host(int dtype, const View& v, const void* a, const void* b, void* 
   CUDA_TRY(guard.set(device), "cudaSetDevice");
 
   const size_t s = (size_t)dtype_size(dtype);
-  const size_t bytes_a = (size_t)(v.outer * v.nq * v.inner) * s;
+  // non-packed strides: the whole span goes across, padding included (C's padding must come back unchanged)
+  const size_t bytes_a = (size_t)(v.strided ? v.span_a : v.outer * v.nq * v.inner) * s;
   const size_t bytes_b = (size_t)v.nq * s;
-  const size_t bytes_c = (size_t)(v.outer * v.inner) * s;
+  const size_t bytes_c = (size_t)(v.strided ? v.span_c : v.outer * v.inner) * s;
   cudaStream_t stream = opts ? static_cast<cudaStream_t>(opts->stream) : nullptr;
-  const bool accumulate = opts && (opts->flags & TTV_B200_FLAG_ACCUMULATE);
+  const bool c_goes_up = (opts && (opts->flags & TTV_B200_FLAG_ACCUMULATE)) || v.strided;   // C is read (accumulate) or has padding to keep
 
   void *da = nullptr, *db = nullptr, *dc = nullptr;
   {
@@ -170,7 +176,7 @@ int run_view_host(int dtype, const View& v, const void* a, const void* b, void* 
   }
   CUDA_TRY(cudaMemcpyAsync(da, a, bytes_a, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync H2D A");
   CUDA_TRY(cudaMemcpyAsync(db, b, bytes_b, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync H2D b");
-  if (accumulate) CUDA_TRY(cudaMemcpyAsync(dc, c, bytes_c, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync H2D C");
+  if (c_goes_up) CUDA_TRY(cudaMemcpyAsync(dc, c, bytes_c, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync H2D C");
   if (int rc = run_view_device(dtype, v, da, db, dc, opts, device, false)) return rc;
   CUDA_TRY(cudaMemcpyAsync(c, dc, bytes_c, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync D2H C");
   CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
@@ -206,7 +212,7 @@ int ttv_b200_run(int dtype, uint64_t q, uint64_t p,
 {
   if (dtype_size(dtype) == 0) return fail(TTV_B200_ERR_DTYPE);
   View v;
-  if (int rc = validate_and_fold(q, p, a, na, wa, pia, b, nb, c, nc, wc, pic, &v)) return fail(rc);
+  if (int rc = validate_and_fold(q, p, a, na, wa, pia, b, nb, c, nc, wc, pic, opts ? opts->flags : 0u, &v)) return fail(rc);
   return run_any(dtype, v, a, b, c, opts);
 }
 
@@ -236,7 +242,7 @@ int ttv_b200_multi(int dtype, uint64_t p,
     uint64_t stride = 1;                                   // packed strides of (nc, pic)
     for (uint64_t r = 0; r + 1 < p; ++r) { wc[pic[r] - 1] = stride; stride *= nc[pic[r] - 1]; }
     const uint64_t nb = na[q[i] - 1];
-    if (int rc = validate_and_fold(q[i], p, a, na, wa, pia, b[i], &nb, c[i], nc, wc, pic, &views[i])) return fail(rc);
+    if (int rc = validate_and_fold(q[i], p, a, na, wa, pia, b[i], &nb, c[i], nc, wc, pic, opts ? opts->flags : 0u, &views[i])) return fail(rc);
   }
 
   Where wa_, wx;
@@ -266,7 +272,9 @@ int ttv_b200_multi(int dtype, uint64_t p,
   DeviceGuard guard;
   CUDA_TRY(guard.set(device), "cudaSetDevice");
   const size_t s = (size_t)dtype_size(dtype);
-  const size_t bytes_a = (size_t)(views[0].outer * views[0].nq * views[0].inner) * s;
+  size_t bytes_a = (size_t)(views[0].outer * views[0].nq * views[0].inner) * s;
+  for (uint64_t i = 0; i < count; ++i)
+    if (views[i].strided) bytes_a = std::max(bytes_a, (size_t)views[i].span_a * s);     // padded A: the whole span
   size_t max_b = 0, sum_c = 0;
   for (uint64_t i = 0; i < count; ++i) {
     max_b = std::max(max_b, (size_t)views[i].nq * s);
@@ -320,9 +328,10 @@ int ttv_b200_plan(int dtype, uint64_t q, uint64_t p,
 {
   if (dtype_size(dtype) == 0) return fail(TTV_B200_ERR_DTYPE);
   View v;
-  if (int rc = validate_and_fold(q, p, a, na, wa, pia, b, nb, c, nc, wc, pic, &v)) return fail(rc);
+  if (int rc = validate_and_fold(q, p, a, na, wa, pia, b, nb, c, nc, wc, pic, opts ? opts->flags : 0u, &v)) return fail(rc);
   Launch l;
-  if (int rc = choose_launch(dtype, v, opts, 256, 256, 256, 148, &l)) return fail(rc);
+  if (!v.strided)
+    if (int rc = choose_launch(dtype, v, opts, 256, 256, 256, 148, &l)) return fail(rc);
   if (plan) fill_plan(dtype, v, l, plan);
   return TTV_B200_OK;
 }

@@ -8,6 +8,7 @@
 #include "stream_kernel.cuh"
 #include "colx_kernel.cuh"
 #include "dotf_kernel.cuh"
+#include "strided_kernel.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -20,13 +21,15 @@ using reduce_fn_t = cudaError_t (*)(const void*, void*, uint64_t, uint32_t, bool
 using fill_fn_t   = cudaError_t (*)(void*, uint64_t, uint64_t, uint64_t, int, cudaStream_t);
 using stream_fn_t = cudaError_t (*)(const StreamParams&, const Launch&, cudaStream_t);
 using dotf_fn_t   = cudaError_t (*)(const DotfParams&, const Launch&, cudaStream_t);
+using strided_fn_t = cudaError_t (*)(const StridedParams&, int, cudaStream_t);
 
 #define TTVB_DECLARE(k)                                                                                          \
   cudaError_t tile_dtype_##k(const TileParams&, const Launch&, cudaStream_t);                                    \
   cudaError_t reduce_dtype_##k(const void*, void*, uint64_t, uint32_t, bool, int, cudaStream_t);                 \
   cudaError_t fill_dtype_##k(void*, uint64_t, uint64_t, uint64_t, int, cudaStream_t);                            \
   cudaError_t stream_dtype_##k(const StreamParams&, const Launch&, cudaStream_t);                               \
-  cudaError_t dotf_dtype_##k(const DotfParams&, const Launch&, cudaStream_t);
+  cudaError_t dotf_dtype_##k(const DotfParams&, const Launch&, cudaStream_t);                                   \
+  cudaError_t strided_dtype_##k(const StridedParams&, int, cudaStream_t);
 TTVB_DECLARE(0) TTVB_DECLARE(1) TTVB_DECLARE(2) TTVB_DECLARE(3) TTVB_DECLARE(4) TTVB_DECLARE(5)
 #undef TTVB_DECLARE
 
@@ -43,6 +46,24 @@ static const reduce_fn_t k_reduce[] = {reduce_dtype_0, reduce_dtype_1, reduce_dt
 static const fill_fn_t   k_fill[]   = {fill_dtype_0, fill_dtype_1, fill_dtype_2, fill_dtype_3, fill_dtype_4, fill_dtype_5};
 static const stream_fn_t k_stream[] = {stream_dtype_0, stream_dtype_1, stream_dtype_2, stream_dtype_3, stream_dtype_4, stream_dtype_5};
 static const dotf_fn_t   k_dotf[]   = {dotf_dtype_0, dotf_dtype_1, dotf_dtype_2, dotf_dtype_3, dotf_dtype_4, dotf_dtype_5};
+static const strided_fn_t k_strided[] = {strided_dtype_0, strided_dtype_1, strided_dtype_2, strided_dtype_3, strided_dtype_4, strided_dtype_5};
+
+cudaError_t launch_strided(int dtype, const View& v, const void* a, const void* b, void* c, bool accumulate, int sm_count,
+                           cudaStream_t stream)
+{
+  if (dtype < 0 || dtype >= TTV_B200_DTYPE_COUNT || !v.strided || v.nfree > (uint32_t)kMaxFree) return cudaErrorInvalidValue;
+  StridedParams S;
+  S.a = a; S.b = b; S.c = c;
+  S.nq = v.nq; S.wq = v.wq;
+  S.total = 1;
+  for (uint32_t d = 0; d < (uint32_t)kMaxFree; ++d) {
+    S.n[d] = d < v.nfree ? v.fn[d] : 1; S.wa[d] = d < v.nfree ? v.fwa[d] : 0; S.wc[d] = d < v.nfree ? v.fwc[d] : 0;
+    S.total *= S.n[d];
+  }
+  S.nfree = v.nfree;
+  S.accumulate = accumulate ? 1u : 0u;
+  return k_strided[dtype](S, sm_count, stream);
+}
 
 cudaError_t launch_view(int dtype, const View& v, const Launch& l, const void* a, const void* b, void* c,
                         void* workspace, bool accumulate, int sm_count, cudaStream_t stream)
@@ -242,6 +263,14 @@ cudaError_t TTVB_CAT(dotf_dtype_, TTVB_DTYPE)(const DotfParams& D, const Launch&
     if (e != cudaSuccess) return e;
   }
   kern<<<(unsigned)l.ctas, l.threads, l.smem_bytes, stream>>>(D);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t TTVB_CAT(strided_dtype_, TTVB_DTYPE)(const StridedParams& S, int sm_count, cudaStream_t stream)
+{
+  const uint64_t blocks = std::max<uint64_t>(1, std::min<uint64_t>((S.total + 255) / 256, (uint64_t)sm_count * 32));
+  ttv_strided_kernel<elem_t><<<(unsigned)blocks, 256, 0, stream>>>(S);
   count_launch();
   return cudaGetLastError();
 }

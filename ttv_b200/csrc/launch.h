@@ -10,6 +10,10 @@ namespace ttvb {
 cudaError_t launch_view(int dtype, const View& v, const Launch& l, const void* a, const void* b, void* c,
                         void* workspace, bool accumulate, int sm_count, cudaStream_t stream);
 
+// General strides (v.strided): one thread per output, DEVICE pointers (strided_kernel.cuh).
+cudaError_t launch_strided(int dtype, const View& v, const void* a, const void* b, void* c, bool accumulate, int sm_count,
+                           cudaStream_t stream);
+
 // x[i] = synth(seed, first + i) for i < count, on the device (same generator as oracle/ttv_oracle.c).
 cudaError_t launch_fill(int dtype, void* x, uint64_t first, uint64_t count, uint64_t seed, int sm_count, cudaStream_t stream);
 

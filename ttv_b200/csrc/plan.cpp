@@ -135,7 +135,7 @@ const char* status_message(int status)
     case TTV_B200_ERR_STRIDES_C:       return "Error in tlib::tensor_times_vector: stride vector of C is not valid.";
     case TTV_B200_ERR_LAYOUT_BEGIN:    return "Error in tlib::detail::compute_inverse_pia_m: beginning of layout tuples of both tensors are not correct.";
     case TTV_B200_ERR_LAYOUT_END:      return "Error in tlib::detail::compute_inverse_pia_m: end of layout tuples of both tensors are not correct.";
-    case TTV_B200_ERR_NOT_PACKED:      return "Error in ttv_b200: strides of A or C are not the packed strides of their shape and layout.";
+    case TTV_B200_ERR_NOT_PACKED:      return "Error in ttv_b200: strides / shape of A and C do not describe the same free modes (or more than 8 unfoldable ones).";
     case TTV_B200_ERR_DTYPE:           return "Error in ttv_b200: unknown element type.";
     case TTV_B200_ERR_OPTS:            return "Error in ttv_b200: invalid options.";
     case TTV_B200_ERR_CUDA:            return "Error in ttv_b200: CUDA failure (no CPU fallback exists).";
@@ -149,7 +149,7 @@ int validate_and_fold(uint64_t q, uint64_t p,
                       const void* a, const uint64_t* na, const uint64_t* wa, const uint64_t* pia,
                       const void* b, const uint64_t* nb,
                       const void* c, const uint64_t* nc, const uint64_t* wc, const uint64_t* pic,
-                      View* view)
+                      uint32_t flags, View* view)
 {
   // the checks of the low-level interface in its order (reference ttv.h:64-89)
   if (p == 0)                                 return TTV_B200_ERR_ORDER_ZERO;
@@ -182,30 +182,54 @@ int validate_and_fold(uint64_t q, uint64_t p,
   for (uint64_t r = 0; r < k; ++r)     v.inner *= na[pia[r] - 1];
   for (uint64_t r = k + 1; r < p; ++r) v.outer *= na[pia[r] - 1];
 
-  if (v.ref_case == 8) {
+  const bool honor = (flags & TTV_B200_FLAG_HONOR_STRIDES) != 0;
+  if (v.ref_case == 8 || honor) {
     // C's layout must be A's layout without q (reference detail/tensor_times_vector.h:147-168).  In cases 1-7 the
     // reference never looks at pic, wa, wc: it runs one GEMV on the packed tensor and writes C packed in the derived
-    // layout (detail/matrix_times_vector.h:314-336) -- and so does this library.
+    // layout (detail/matrix_times_vector.h:314-336) -- and so does this library, unless TTV_B200_FLAG_HONOR_STRIDES
+    // asks for wa / wc / pic to be taken at their word in every case (then C may even have a layout of its own).
+    bool derived = true;                                   // pic is pia without q
     for (uint64_t i = 0; i < k; ++i)
-      if (pic[i] != pia[i] - (pia[i] > q ? 1 : 0)) return TTV_B200_ERR_LAYOUT_BEGIN;
+      if (pic[i] != pia[i] - (pia[i] > q ? 1 : 0)) { if (!honor) return TTV_B200_ERR_LAYOUT_BEGIN; derived = false; }
     for (uint64_t i = k; i + 1 < p; ++i)
-      if (pic[i] != pia[i + 1] - (pia[i + 1] > q ? 1 : 0)) return TTV_B200_ERR_LAYOUT_END;
+      if (pic[i] != pia[i + 1] - (pia[i + 1] > q ? 1 : 0)) { if (!honor) return TTV_B200_ERR_LAYOUT_END; derived = false; }
 
     // The loop nest of the reference walks A and C with wa / wc (tensor_times_vector.h:189-216) and asserts
-    // wa[q-1] == inner in the subtensor variants (:956).  Packed strides are the documented input (README.md:41);
-    // anything else is rejected instead of being silently mis-read.  Extent-1 modes may carry any stride.
+    // wa[q-1] == inner in the subtensor variants (:956).  Packed strides are the documented input (README.md:41) and
+    // take the fast kernels; any other valid strides are honoured the way the slice variants do, by the general-stride
+    // kernel (strided_kernel.cuh).  Extent-1 modes may carry any stride.
+    bool packed = derived;
     uint64_t expect = 1;
     for (uint64_t r = 0; r < p; ++r) {
       const uint64_t m = pia[r] - 1;
-      if (na[m] > 1 && wa[m] != expect) return TTV_B200_ERR_NOT_PACKED;
+      if (na[m] > 1 && wa[m] != expect) packed = false;
       expect *= na[m];
     }
     expect = 1;
     for (uint64_t r = 0; r + 1 < p; ++r) {
       const uint64_t mc = pic[r] - 1;                 // mode of C
       const uint64_t ma = mc + (mc + 1 >= q ? 1 : 0); // the same mode in A
-      if (na[ma] > 1 && wc[mc] != expect) return TTV_B200_ERR_NOT_PACKED;
+      if (na[ma] > 1 && wc[mc] != expect) packed = false;
       expect *= na[ma];
+    }
+    if (!packed) {
+      v.strided = true;
+      v.wq = wa[q - 1];
+      v.span_a = 1; v.span_c = 1;
+      for (uint64_t m = 0; m < p; ++m) v.span_a += (na[m] - 1) * wa[m];
+      for (uint64_t r = 0; r + 1 < p; ++r) {
+        const uint64_t mc = pic[r] - 1, ma = mc + (mc + 1 >= q ? 1 : 0);
+        if (nc[mc] != na[ma]) return TTV_B200_ERR_NOT_PACKED;          // C's shape must be A's without mode q
+        v.span_c += (nc[mc] - 1) * wc[mc];
+        if (na[ma] == 1) continue;
+        if (v.nfree > 0 && v.fwa[v.nfree - 1] * v.fn[v.nfree - 1] == wa[ma] && v.fwc[v.nfree - 1] * v.fn[v.nfree - 1] == wc[mc]) {
+          v.fn[v.nfree - 1] *= na[ma];                                   // packed against its neighbour in A and in C
+          continue;
+        }
+        if (v.nfree == (uint32_t)kMaxFreeDims) return TTV_B200_ERR_NOT_PACKED;
+        v.fn[v.nfree] = na[ma]; v.fwa[v.nfree] = wa[ma]; v.fwc[v.nfree] = wc[mc];
+        ++v.nfree;
+      }
     }
   }
   *view = v;
@@ -604,7 +628,7 @@ void fill_plan(int dtype, const View& v, const Launch& l, ttv_b200_plan_t* plan)
   const uint64_t s = (uint64_t)dtype_size(dtype);
   plan->outer = v.outer; plan->nq = v.nq; plan->inner = v.inner;
   plan->k = v.k; plan->ref_case = v.ref_case;
-  plan->kernel = l.kernel; plan->vec = l.vec; plan->tx = (int32_t)l.tx; plan->ty = (int32_t)l.ty; plan->to = (int32_t)l.to;
+  plan->kernel = v.strided ? TTV_B200_KERNEL_STRIDED : l.kernel; plan->vec = v.strided ? 1 : l.vec; plan->tx = (int32_t)l.tx; plan->ty = (int32_t)l.ty; plan->to = (int32_t)l.to;
   plan->nu = l.nu; plan->ku = l.ku; plan->stream = (int32_t)l.stream;
   plan->ksplit = (int32_t)l.ksplit; plan->threads = (int32_t)l.threads; plan->ctas = l.ctas;
   plan->smem_bytes = l.smem_bytes;

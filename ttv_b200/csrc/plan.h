@@ -18,10 +18,19 @@ namespace ttvb {
 
 constexpr int kMaxOrder = 64;
 
+constexpr int kMaxFreeDims = 8;
+
 struct View {
   uint64_t outer = 1, nq = 1, inner = 1;
   uint32_t k = 0;          // 1-based position of q in pia
   uint32_t ref_case = 0;   // 1..8
+  // General strides (case 8 only, like the reference's slice variants): the free modes in the order of C's layout,
+  // fastest first, neighbours that are packed against each other in both tensors folded into one.
+  bool     strided = false;
+  uint32_t nfree = 0;
+  uint64_t fn[kMaxFreeDims] = {0}, fwa[kMaxFreeDims] = {0}, fwc[kMaxFreeDims] = {0};
+  uint64_t wq = 0;                     // stride of mode q in A
+  uint64_t span_a = 0, span_c = 0;     // elements from the first to one past the last element touched
 };
 
 // How one launch of the tile kernel is shaped.  See kernels.cuh for the meaning of the thread tile.
@@ -72,7 +81,7 @@ int validate_and_fold(uint64_t q, uint64_t p,
                       const void* a, const uint64_t* na, const uint64_t* wa, const uint64_t* pia,
                       const void* b, const uint64_t* nb,
                       const void* c, const uint64_t* nc, const uint64_t* wc, const uint64_t* pic,
-                      View* view);
+                      uint32_t flags, View* view);
 
 // Kernel choice for a canonical view.  align_a / align_c are the byte alignments of the device pointers (use 256
 // when unknown, e.g. in ttv_b200_plan).  sm_count = number of SMs of the target device (148 on B200).

@@ -4,8 +4,9 @@
     ttvs(q, A, bs, order="optimal")   the chain of p-1 products that leaves mode q; order in
                                       {"optimal", "backward", "forward"}      wrapped_ttv.cpp:83-198
 
-Like the reference, A is read as a C-contiguous (last-order) array; unlike the reference (float64 only,
-wrapped_ttv.cpp:205-206) every element type of the C-ABI is accepted.  Errors the reference raises as
+Like the reference, a C-contiguous A is a last-order tensor; unlike the reference (float64 only,
+wrapped_ttv.cpp:205-206; strides ignored, :44-45) every element type of the C-ABI is accepted and arrays that are not
+C-contiguous (transposes, slices, Fortran order) are read in place through their strides.  Errors the reference raises as
 std::invalid_argument surface as ValueError with the same text.
 
 ttvs keeps the intermediates in HBM: A and the vectors are uploaded once, the p-1 kernels run back to back on the
@@ -27,6 +28,15 @@ def _as_c_array(x):
     return np.ascontiguousarray(a)
 
 
+def _as_array(x):
+    """like _as_c_array but WITHOUT packing: slices and transposes are read in place through their strides (the
+    reference silently reads them as if they were C-contiguous, wrapped_ttv.cpp:44-45)"""
+    a = np.asarray(x)
+    if a.dtype not in api._NP_CODES:
+        a = a.astype(np.float64)
+    return a
+
+
 def ttv(q: int, A, b):
     """Tensor-times-vector for the q-th mode (1-based) of a numpy array (host) or a torch CUDA tensor (device)."""
     if api._is_torch(A):
@@ -35,8 +45,8 @@ def ttv(q: int, A, b):
             raise ValueError("Error calling ttvpy::ttv: input tensor order should be greater than zero.")
         if q == 0 or q > p:
             raise ValueError("Error calling ttvpy::ttv: contraction mode should be greater than zero or less than or equal to p.")
-        return api.ttv(q, A.contiguous(), b.contiguous())
-    A = _as_c_array(A)
+        return api.ttv(q, A, b.contiguous())
+    A = _as_array(A)
     b = np.ascontiguousarray(np.asarray(b), dtype=A.dtype)
     p = A.ndim
     if p == 0:
