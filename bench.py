@@ -421,9 +421,15 @@ def measure_e2e(torch, dist, ttv_b200, args, a, bs, cs, shards, na_global, pia, 
         hb = torch.tensor([h2d, d2h], device=dev, dtype=torch.int64)
         dist.all_reduce(hb)
         h2d, d2h = int(hb[0].item()), int(hb[1].item())
-    # the result of the last product must be the device-resident one
-    if world == 1 and not torch.equal(c_host[2], cs[2].cpu()):
-        raise SystemExit("bench.py: e2e result differs from the device-resident result")
+    # the host-path results must be the device-resident ones up to summation order (the host path streams A in chunks, so
+    # its tiles differ): |diff| <= 2 n_q (eps/2) sum_k |a_k||b_k| <= n_q eps sum_k |b_k| because |a| < 1
+    if world == 1:
+        for q in qs:
+            nq = na_global[q - 1]
+            tol = nq * float(np.finfo(np.float32).eps) * float(b_host[q].abs().sum())
+            err = float((c_host[q] - cs[q].cpu()).abs().max())
+            if not err <= tol:
+                raise SystemExit(f"bench.py: e2e result of q={q} differs from the device-resident result: {err} > {tol}")
     out = {"value": round(total_bytes / (dt / steps) / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "ms_per_step": round(dt / steps * 1e3, 2), "steps": steps,
            "path": ("ttv_b200_multi with pinned host buffers: A crosses PCIe once per step, four products" if world == 1

@@ -476,3 +476,33 @@ def test_arrays_that_are_not_contiguous_are_read_in_place(dtype):
                     if np.shares_memory(x, base) else torch.from_numpy(np.ascontiguousarray(x)).cuda()
                 tg = ttv_b200.ttv(q, tx, torch.from_numpy(b).cuda())
                 assert np.array_equal(tg.cpu().numpy(), want), (x.shape, x.strides, q, "device")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.complex64])
+def test_host_tensors_are_streamed_in_chunks(dtype, oracle, monkeypatch):
+    """host-pointer calls on large tensors stream A across PCIe in chunks of slabs of the slowest mode, kernels of one
+    chunk overlapping the copy of the next: free split and n_q split, ragged last chunk, accumulate,
+    several products per pass (ttv_multi); chunk size forced down to 1 MiB so that a few MB exercise the ring"""
+    monkeypatch.setenv("TTV_B200_H2D_CHUNK_MB", "1")
+    rng = np.random.default_rng(51)
+    item = np.dtype(dtype).itemsize
+    for na, pia in [((64, 50, 203), (1, 2, 3)), ((40, 30, 100, 9), (2, 1, 3, 4)), ((3000, 211), (1, 2)), ((211, 3000), (2, 1)),
+                    ((16, 1, 300, 151, 1), (1, 2, 3, 4, 5))]:
+        n = int(np.prod(na))
+        assert n * item >= 2 << 20
+        a = rng.integers(-8, 9, n).astype(dtype)
+        bs, wants = [], []
+        for q in range(1, len(na) + 1):
+            b = rng.integers(-8, 9, na[q - 1]).astype(dtype)
+            want = oracle.ttv(q, a, na, pia, b)
+            bs.append(b); wants.append(want)
+            before = ttv_b200.launch_count()
+            got = run_lowlevel(q, a, na, pia, b)
+            assert np.array_equal(got, want), (na, pia, q)
+            if na[q - 1] > 1:         # (contracting an extent-1 slowest mode leaves nothing to split: plain path)
+                assert ttv_b200.launch_count() - before >= 2, ("expected one launch per chunk", na, pia, q)
+            c0 = np.full(want.size, 3, dtype)
+            assert np.array_equal(run_lowlevel(q, a, na, pia, b, c0=c0, flags=1), want + 3), (na, pia, q, "accumulate")
+        cs = ttv_b200.ttv_multi(list(range(1, len(na) + 1)), a, list(na), list(pia), bs)
+        for q, (c, want) in enumerate(zip(cs, wants), 1):
+            assert np.array_equal(c, want), (na, pia, q, "multi")

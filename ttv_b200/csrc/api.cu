@@ -8,6 +8,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -56,6 +57,10 @@ struct DeviceState {
   int sm_count = 0;
   std::map<cudaStream_t, Buffer> workspace;   // split-n_q partials, one per stream so that streams do not share it
   Buffer stage_a, stage_b, stage_c;           // staging for host-pointer calls
+  // chunked host path: a copy stream and a ring of chunk buffers with their events
+  cudaStream_t copy_stream = nullptr;
+  Buffer ring[3];
+  cudaEvent_t ready[3] = {nullptr, nullptr, nullptr}, freed[3] = {nullptr, nullptr, nullptr};
 };
 
 std::mutex g_mutex;
@@ -148,6 +153,125 @@ int run_view_device(int dtype, const View& v, const void* a, const void* b, void
   return TTV_B200_OK;
 }
 
+int env_mb(const char* name, int fallback)
+{
+  const char* e = std::getenv(name);
+  return (e && *e) ? std::atoi(e) : fallback;
+}
+
+// Host pointers, large A: stream A across PCIe in chunks of whole slabs of its slowest mode and run the kernels of chunk
+// i while chunk i+1 is still in flight.  A product whose mode q is NOT the slowest mode gets the
+// matching rows of C from every chunk (free split, C chunk goes back right away: PCIe is full duplex); a product that
+// contracts the slowest mode accumulates its chunk of n_q into the whole C, which goes back at the end.  Only three chunk
+// buffers of A live on the device, so the tensor may be larger than what is free in HBM.
+// Returns -1 when the call is not eligible (small, strided, one indivisible slab): the caller takes the plain path.
+int run_host_pipelined(int dtype, uint64_t count, const View* views, const void* a, const void* const* b, void* const* c,
+                       const ttv_b200_opts* opts, int device)
+{
+  const size_t s = (size_t)dtype_size(dtype);
+  const View& v0 = views[0];
+  const uint64_t total = v0.outer * v0.nq * v0.inner;
+  const uint64_t slow = v0.slow_extent ? v0.slow_extent : (v0.outer > 1 ? v0.outer : v0.nq);
+  const size_t chunk_target = (size_t)env_mb("TTV_B200_H2D_CHUNK_MB", 128) << 20;
+  const bool debug = env_mb("TTV_B200_DEBUG", 0) != 0;
+  if (debug) fprintf(stderr, "[ttv_b200] host path: total=%llu slow=%llu chunk_target=%zu count=%llu\n", (unsigned long long)total,
+                     (unsigned long long)slow, chunk_target, (unsigned long long)count);
+  if (chunk_target == 0 || slow < 2 || total * s < 2 * chunk_target) return -1;
+  const uint64_t slab = total / slow;                                       // elements per index of the slowest mode
+  if (slab * s > 4 * chunk_target) return -1;
+  for (uint64_t i = 0; i < count; ++i) {
+    const View& v = views[i];
+    if (v.strided || v.outer * v.nq * v.inner != total) return -1;
+    const bool nq_split = v.outer == 1 || (v.outer % slow) != 0;             // mode q is the slowest mode
+    if (nq_split && !(v.outer == 1 && v.nq == slow)) return -1;
+  }
+  const uint64_t per = std::max<uint64_t>(1, chunk_target / (slab * s));     // slabs per chunk
+  const uint64_t chunks = (slow + per - 1) / per;
+  if (debug) fprintf(stderr, "[ttv_b200] host path: pipelined, %llu chunks of %llu slabs\n", (unsigned long long)chunks, (unsigned long long)per);
+  const size_t chunk_bytes = (size_t)(per * slab) * s;
+
+  cudaStream_t stream = opts ? static_cast<cudaStream_t>(opts->stream) : nullptr;
+  const bool accumulate = opts && (opts->flags & TTV_B200_FLAG_ACCUMULATE);
+  ttv_b200_opts local = opts ? *opts : ttv_b200_opts{-1, 0, 0, 0, 0, 0, 0, 0, nullptr};
+
+  DeviceState* st = nullptr;
+  char *db_ = nullptr, *dc_ = nullptr;
+  size_t max_b = 0, sum_c = 0;
+  for (uint64_t i = 0; i < count; ++i) {
+    max_b = std::max(max_b, ((size_t)views[i].nq * s + 255) / 256 * 256);
+    sum_c += ((size_t)(views[i].outer * views[i].inner) * s + 255) / 256 * 256;
+  }
+  {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (int rc = device_state(device, &st)) return rc;
+    if (!st->copy_stream) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&st->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+      for (int r = 0; r < 3; ++r) {
+        CUDA_TRY(cudaEventCreateWithFlags(&st->ready[r], cudaEventDisableTiming), "cudaEventCreate");
+        CUDA_TRY(cudaEventCreateWithFlags(&st->freed[r], cudaEventDisableTiming), "cudaEventCreate");
+      }
+    }
+    for (int r = 0; r < 3; ++r) if (int rc = ensure(st->ring[r], chunk_bytes)) return rc;
+    if (int rc = ensure(st->stage_b, max_b * count)) return rc;
+    if (int rc = ensure(st->stage_c, sum_c)) return rc;
+    db_ = static_cast<char*>(st->stage_b.ptr); dc_ = static_cast<char*>(st->stage_c.ptr);
+  }
+  // the vectors (and C when it is accumulated into) go first, on the compute stream
+  std::vector<char*> dci(count);
+  size_t coff = 0;
+  for (uint64_t i = 0; i < count; ++i) {
+    const size_t bytes_c = (size_t)(views[i].outer * views[i].inner) * s;
+    dci[i] = dc_ + coff;
+    coff += (bytes_c + 255) / 256 * 256;
+    CUDA_TRY(cudaMemcpyAsync(db_ + i * max_b, b[i], (size_t)views[i].nq * s, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync H2D b");
+    if (accumulate) CUDA_TRY(cudaMemcpyAsync(dci[i], c[i], bytes_c, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync H2D C");
+  }
+  // the copy stream must not run ahead of work already queued on the caller's stream that still reads the ring
+  CUDA_TRY(cudaEventRecord(st->freed[0], stream), "cudaEventRecord");
+  CUDA_TRY(cudaStreamWaitEvent(st->copy_stream, st->freed[0], 0), "cudaStreamWaitEvent");
+
+  const char* ah = static_cast<const char*>(a);
+  for (uint64_t ch = 0; ch < chunks; ++ch) {
+    const int r = (int)(ch % 3);
+    const uint64_t s0 = ch * per, s1 = std::min(slow, s0 + per), ns = s1 - s0;
+    if (ch >= 3) CUDA_TRY(cudaStreamWaitEvent(st->copy_stream, st->freed[r], 0), "cudaStreamWaitEvent");
+    CUDA_TRY(cudaMemcpyAsync(st->ring[r].ptr, ah + (size_t)(s0 * slab) * s, (size_t)(ns * slab) * s, cudaMemcpyHostToDevice,
+                             st->copy_stream), "cudaMemcpyAsync H2D A chunk");
+    CUDA_TRY(cudaEventRecord(st->ready[r], st->copy_stream), "cudaEventRecord");
+    CUDA_TRY(cudaStreamWaitEvent(stream, st->ready[r], 0), "cudaStreamWaitEvent");
+    for (uint64_t i = 0; i < count; ++i) {
+      View v = views[i];
+      const bool nq_split = v.outer == 1;
+      char* cdst = dci[i];
+      const char* bsrc = db_ + i * max_b;
+      if (nq_split) {
+        v.nq = ns;
+        bsrc += (size_t)s0 * s;
+        local.flags = (opts ? opts->flags : 0u) | ((ch > 0 || accumulate) ? (uint32_t)TTV_B200_FLAG_ACCUMULATE : 0u);
+      } else {
+        const uint64_t rows = v.outer / slow;                               // rows of `outer` per slab
+        v.outer = ns * rows;
+        cdst += (size_t)(s0 * rows * v.inner) * s;
+        local.flags = opts ? opts->flags : 0u;
+      }
+      local.flags &= ~(uint32_t)TTV_B200_FLAG_ASYNC;
+      local.stream = stream;
+      if (int rc = run_view_device(dtype, v, st->ring[r].ptr, bsrc, cdst, &local, device, false)) return rc;
+      if (!nq_split) {
+        const size_t bytes = (size_t)(v.outer * v.inner) * s;
+        CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(c[i]) + (cdst - dci[i]), cdst, bytes, cudaMemcpyDeviceToHost, stream),
+                 "cudaMemcpyAsync D2H C chunk");
+      }
+    }
+    CUDA_TRY(cudaEventRecord(st->freed[r], stream), "cudaEventRecord");
+  }
+  for (uint64_t i = 0; i < count; ++i)
+    if (views[i].outer == 1)
+      CUDA_TRY(cudaMemcpyAsync(c[i], dci[i], (size_t)views[i].inner * s, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync D2H C");
+  CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+  return TTV_B200_OK;
+}
+
 // host pointers: H2D(A, b) -> kernel -> D2H(C), all on one stream, then wait
 int run_view_host(int dtype, const View& v, const void* a, const void* b, void* c, const ttv_b200_opts* opts)
 {
@@ -156,6 +280,12 @@ int run_view_host(int dtype, const View& v, const void* a, const void* b, void* 
   DeviceGuard guard;
   CUDA_TRY(guard.set(device), "cudaSetDevice");
 
+  {
+    const void* bs[1] = {b};
+    void* cs[1] = {c};
+    const int rc = run_host_pipelined(dtype, 1, &v, a, bs, cs, opts, device);
+    if (rc >= 0) return rc;
+  }
   const size_t s = (size_t)dtype_size(dtype);
   // non-packed strides: the whole span goes across, padding included (C's padding must come back unchanged)
   const size_t bytes_a = (size_t)(v.strided ? v.span_a : v.outer * v.nq * v.inner) * s;
@@ -271,6 +401,10 @@ int ttv_b200_multi(int dtype, uint64_t p,
   if (device < 0) CUDA_TRY(cudaGetDevice(&device), "cudaGetDevice (is a CUDA device visible?)");
   DeviceGuard guard;
   CUDA_TRY(guard.set(device), "cudaSetDevice");
+  {
+    const int rc = run_host_pipelined(dtype, count, views.data(), a, b, c, opts, device);
+    if (rc >= 0) return rc;
+  }
   const size_t s = (size_t)dtype_size(dtype);
   size_t bytes_a = (size_t)(views[0].outer * views[0].nq * views[0].inner) * s;
   for (uint64_t i = 0; i < count; ++i)
@@ -422,7 +556,7 @@ void ttv_b200_release(void)
     cudaSetDevice(kv.first);
     for (auto& w : kv.second.workspace) if (w.second.ptr) cudaFree(w.second.ptr);
     kv.second.workspace.clear();
-    for (Buffer* b : {&kv.second.stage_a, &kv.second.stage_b, &kv.second.stage_c})
+    for (Buffer* b : {&kv.second.stage_a, &kv.second.stage_b, &kv.second.stage_c, &kv.second.ring[0], &kv.second.ring[1], &kv.second.ring[2]})
       if (b->ptr) { cudaFree(b->ptr); b->ptr = nullptr; b->bytes = 0; }
     cudaSetDevice(prev);
   }

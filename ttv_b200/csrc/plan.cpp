@@ -179,6 +179,8 @@ int validate_and_fold(uint64_t q, uint64_t p,
   while (pia[k] != q) ++k;                    // 0-based position of q in the layout
   v.k  = (uint32_t)(k + 1);
   v.nq = na[q - 1];
+  for (uint64_t r = p; r-- > 0;)
+    if (na[pia[r] - 1] > 1) { v.slow_extent = na[pia[r] - 1]; break; }
   for (uint64_t r = 0; r < k; ++r)     v.inner *= na[pia[r] - 1];
   for (uint64_t r = k + 1; r < p; ++r) v.outer *= na[pia[r] - 1];
 

@@ -24,6 +24,9 @@ struct View {
   uint64_t outer = 1, nq = 1, inner = 1;
   uint32_t k = 0;          // 1-based position of q in pia
   uint32_t ref_case = 0;   // 1..8
+  // the slowest mode of A's layout with extent > 1: along it A (and C, or n_q when it is mode q) splits into contiguous
+  // slabs -- what the host-pointer path streams chunk by chunk.  0 = derive from the view (outer, else n_q).
+  uint64_t slow_extent = 0;
   // General strides (case 8 only, like the reference's slice variants): the free modes in the order of C's layout,
   // fastest first, neighbours that are packed against each other in both tensors folded into one.
   bool     strided = false;
