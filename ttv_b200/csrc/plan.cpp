@@ -460,6 +460,7 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
   const uint64_t NT = l.threads;
   const uint64_t vmax = (flags & TTV_B200_FLAG_NO_VEC) ? 1 : std::max<uint64_t>(1, 16 / s);
 
+  uint64_t row_units = 0;      // COL with a row of 1..8 CTA-widths: the units it is spread over
   const bool dot = (v.inner == 1) && forced != TTV_B200_KERNEL_COL;
   if (forced == TTV_B200_KERNEL_DOT && v.inner != 1) return TTV_B200_ERR_OPTS;
   l.kernel = dot ? TTV_B200_KERNEL_DOT : TTV_B200_KERNEL_COL;
@@ -500,7 +501,13 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
     while (V > 1 && !((v.inner % V) == 0 && (align_a % (V * s)) == 0 && (align_c % (V * s)) == 0)) V /= 2;
     const uint64_t cv = v.inner / V;                       // vector columns
     if (cv >= NT) {
-      l.tx = (uint32_t)NT; l.ty = 1; l.to = 1; l.udir = 0;
+      // a row is only a few CTA-widths long: the units of a thread must not outnumber the units of a row, or most of
+      // its loads are predicated off (480 columns, 4 units of 256: measured [13200, 25, 480] c128 5.8 -> 6.7 TB/s with 2).
+      // Spreading the row evenly over the units (2 x 240 instead of 256 + 224) measured no better, so tx stays the CTA.
+      const uint64_t U = ceil_div(cv, NT);
+      l.tx = (uint32_t)(U <= 8 && env_int("TTV_B200_EVEN_UNITS", 0) ? ceil_div(cv, U) : NT);
+      row_units = U <= 8 ? U : 0;
+      l.ty = 1; l.to = 1; l.udir = 0;
     } else {
       l.tx = (uint32_t)cv;
       const uint64_t rem = NT / cv;
@@ -586,6 +593,10 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
       ku *= 2;
     }
     if (!(nu == 8 && ku == 1)) ku = loads / nu;                      // only (nu, ku) with nu*ku == loads are instantiated
+  }
+  if (row_units) {                                                    // units per thread must divide the units of a row
+    while (nu > 1 && row_units % nu) nu /= 2;
+    ku = loads / nu;
   }
   if (l.bdirect) { ku = 8; nu = 1; }                                  // the one batch shape instantiated with direct b
   l.ku = (int)ku;
