@@ -44,9 +44,10 @@ def algo_bytes(na, q, elem=ELEM):
     return elem * (n + na[q - 1] + n // na[q - 1])
 
 
-def workload_name(n):
+def workload_name(n, nccl_reduce=False):
+    how = "n_q split + NCCL reduce" if nccl_reduce else "n_q split, exchange fused into the kernel's stores over NVLink peer memory"
     return (f"cfg2 symmetric sweep: order-4 fp32 n=(256,256,256,{EXT * n}) first-order, one step = q=1..4; "
-            f"{'single GPU' if n == 1 else f'sharded along mode 4 over {n} GPUs (q=1..3 free split, q=4 n_q split + NCCL reduce)'}")
+            f"{'single GPU' if n == 1 else f'sharded along mode 4 over {n} GPUs (q=1..3 free split, q=4 {how})'}")
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -217,9 +218,18 @@ def run_own_arm(args):
         ttv_b200.fill(bs[q], SEED_B + q)
     cs = {q: torch.full((shards[q].c_count,), float("nan"), dtype=torch.float32, device=dev) for q in range(1, ORDER + 1)}
 
+    # N > 1: the n_q-split product (q = 4) exchanges its partials through the kernel's own stores into the owners' memory
+    # (NVLink peer memory, ttv_b200.sharded.PeerExchange) and leaves C distributed like the free splits do; --nccl-reduce
+    # takes the plain kernel + ncclReduce-to-rank-0 instead.
+    exchange = None
+    if world > 1 and not args.nccl_reduce:
+        from ttv_b200.sharded import PeerExchange
+        exchange = PeerExchange(shards[ORDER].c_count, torch.float32, dev)
+    live = {}          # what the last step produced: q -> (C of this rank, its shard)
+
     def step():
         for q in range(1, ORDER + 1):
-            ttv_sharded(q, a, na_global, pia, bs[q], rank=rank, world=world, c_local=cs[q], reduce_to=0)
+            live[q] = ttv_sharded(q, a, na_global, pia, bs[q], rank=rank, world=world, c_local=cs[q], reduce_to=0, exchange=exchange)
 
     def barrier():
         if world > 1:
@@ -229,7 +239,7 @@ def run_own_arm(args):
     # ---- smoke check of one product against the oracle on sampled fibers (the checker, not the thing measured) ----
     step()
     torch.cuda.synchronize()
-    verify_sample(torch, cs, shards, na_global, bs, rank, world)
+    verify_sample(torch, {q: live[q][0] for q in live}, {q: live[q][1] for q in live}, na_global, bs, rank, world)
 
     total_bytes = sum(algo_bytes(na_global, q) for q in range(1, ORDER + 1))
     total_flops = 2 * int(np.prod(na_global, dtype=object)) * ORDER
@@ -299,7 +309,7 @@ def run_own_arm(args):
     # ---- end to end through the public API with host buffers --------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        e2e = measure_e2e(torch, dist, ttv_b200, args, a, bs, cs, shards, na_global, pia, rank, world, dev, total_bytes)
+        e2e = measure_e2e(torch, dist, ttv_b200, args, a, bs, cs, shards, na_global, pia, rank, world, dev, total_bytes, exchange)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -316,7 +326,7 @@ def run_own_arm(args):
         line = {"metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
-                "config": {"workload": workload_name(world), "layout": "first-order", "per_gpu_tensor_bytes": sh.a_count * ELEM,
+                "config": {"workload": workload_name(world, args.nccl_reduce), "layout": "first-order", "per_gpu_tensor_bytes": sh.a_count * ELEM,
                            "l2": "inputs (16 GiB per GPU) are larger than L2; no flush needed",
                            "timing": "CUDA events on the launching stream, max over ranks"},
                 "gflops": round(total_flops / (ms_per_step * 1e-3) / 1e9, 1),
@@ -344,7 +354,7 @@ def verify_sample(torch, cs, shards, na_global, bs, rank, world):
     rng = np.random.default_rng(1234 + rank)
     for q in range(1, ORDER + 1):
         sh = shards[q]
-        if sh.kind == "nq" and (world > 1 and rank != 0):
+        if (sh.kind == "nq" and (world > 1 and rank != 0)) or sh.c_count == 0:
             continue
         c = cs[q]
         inner = int(np.prod(na_global[: q - 1], dtype=object)) if q > 1 else 1
@@ -362,7 +372,7 @@ def verify_sample(torch, cs, shards, na_global, bs, rank, world):
                 raise SystemExit(f"bench.py: parity check failed for q={q}, output {jg}: got {got}, want {want}, tol {tol}")
 
 
-def measure_e2e(torch, dist, ttv_b200, args, a, bs, cs, shards, na_global, pia, rank, world, dev, total_bytes):
+def measure_e2e(torch, dist, ttv_b200, args, a, bs, cs, shards, na_global, pia, rank, world, dev, total_bytes, exchange=None):
     """Same step, inputs in pinned HOST memory; every step copies its inputs (this rank's slab of A and the four
     vectors) to the device and reads the four results back inside the timed region.  N = 1 is ONE C-ABI call with host
     buffers, ttv_b200_multi, which moves A across PCIe once and runs the four products on it; the strict variant -- four
@@ -375,7 +385,10 @@ def measure_e2e(torch, dist, ttv_b200, args, a, bs, cs, shards, na_global, pia, 
     b_host = {q: bs[q].cpu().pin_memory() for q in bs}
     c_host = {q: torch.empty(shards[q].c_count, dtype=torch.float32, pin_memory=True) for q in cs}
     h2d = sh.a_count * ELEM + sum((shards[q].count if shards[q].kind == "nq" else na_global[q - 1]) * ELEM for q in range(1, ORDER + 1))
-    d2h = sum(shards[q].c_count * ELEM for q in range(1, ORDER + 1) if not (shards[q].kind == "nq" and rank != 0))
+    if exchange is not None:      # fused exchange: every rank reads back its block of the n_q-split product
+        d2h = sum((shards[q].c_count // world if shards[q].kind == "nq" else shards[q].c_count) * ELEM for q in range(1, ORDER + 1))
+    else:
+        d2h = sum(shards[q].c_count * ELEM for q in range(1, ORDER + 1) if not (shards[q].kind == "nq" and rank != 0))
 
     qs = list(range(1, ORDER + 1))
     a_np = a_host.numpy()
@@ -390,10 +403,11 @@ def measure_e2e(torch, dist, ttv_b200, args, a, bs, cs, shards, na_global, pia, 
             from ttv_b200.sharded import ttv_sharded
             a.copy_(a_host, non_blocking=True)                      # this rank's slab, once per step
             for q in qs:
-                s = shards[q]
                 bs[q].copy_(b_host[q], non_blocking=True)
-                ttv_sharded(q, a, na_global, pia, bs[q], rank=rank, world=world, c_local=cs[q], reduce_to=0)
-                if not (s.kind == "nq" and rank != 0):
+                c, s = ttv_sharded(q, a, na_global, pia, bs[q], rank=rank, world=world, c_local=cs[q], reduce_to=0, exchange=exchange)
+                if s.kind == "nq-scattered":
+                    c_host[q][: s.c_count].copy_(c, non_blocking=True)          # this rank's block of C
+                elif not (s.kind == "nq" and rank != 0):
                     c_host[q].copy_(cs[q], non_blocking=True)
             torch.cuda.synchronize()
 
@@ -456,6 +470,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--nccl-reduce", action="store_true", help="N > 1: plain kernel + ncclReduce for the n_q-split product instead of the fused exchange")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -198,6 +198,19 @@ int ttv_b200_view(int dtype, uint64_t outer, uint64_t nq, uint64_t inner,
 int ttv_b200_plan_view(int dtype, uint64_t outer, uint64_t nq, uint64_t inner,
                        const ttv_b200_opts* opts, ttv_b200_plan_t* plan);
 
+/* Multi-GPU, n_q split (mode q is the slowest mode; every GPU holds a range of the contraction rows): the product of the
+ * canonical view FUSED with its exchange step.  The flat index space of C (outer*inner elements) is cut into `world`
+ * blocks of `blk` elements (blk a multiple of 16 bytes' worth of elements, world*blk >= outer*inner); this GPU's partial
+ * sums for block j are written by the kernel's own stores into peer_ws[j] + rank*blk, where peer_ws[j] is GPU j's
+ * workspace of world*blk elements mapped into this process (NVLink peer memory, e.g. torch symmetric memory).  After a
+ * barrier across the GPUs, ttv_b200_reduce_slots on every GPU sums the `world` slots of its own workspace in rank order
+ * into its block of C (n <= blk elements): a deterministic reduce-scatter.  DEVICE pointers only; a, b, peer_ws[rank]
+ * live on the current device.  Replaces the ncclReduce of SURVEY 8(e) for this case. */
+int ttv_b200_view_scatter(int dtype, uint64_t outer, uint64_t nq, uint64_t inner, const void* a, const void* b,
+                          void* const* peer_ws, uint32_t world, uint32_t rank, uint64_t blk, const ttv_b200_opts* opts);
+int ttv_b200_reduce_slots(int dtype, const void* ws, void* c, uint64_t n, uint64_t blk, uint32_t slots,
+                          const ttv_b200_opts* opts);
+
 /* x[i] = synth(seed, first + i), i < count, written on the device by a kernel (x is a DEVICE pointer).  The generator
  * is the counter-based splitmix64 one of SURVEY 8(d); oracle/ttv_oracle.c carries the identical host version, so
  * tensors too large for host memory can be checked by sampling. */

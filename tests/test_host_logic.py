@@ -257,10 +257,10 @@ def test_chooser_only_picks_instantiated_kernels():
                 assert pl["smem_bytes"] == (nq + 2048) * size[dt]
                 continue
             if pl["kernel"] == 4:       # COLX: odd wide rows, 16-byte loads at any phase
-                assert key in {(1, 8), (2, 4), (4, 2)} and wide and size[dt] < 16, (dt, outer, nq, inner, pl)
+                assert (key in {(1, 8), (2, 4), (4, 2)} and wide or key == (8, 2) and size[dt] == 4) and size[dt] < 16, (dt, outer, nq, inner, pl)
                 assert inner * size[dt] >= 2048 and inner % (16 // size[dt]) != 0
                 if -(-nq // (16 // size[dt])) < 16:      # short contraction: warp-autonomous form, no shared memory
-                    assert (pl["tx"], pl["ty"], pl["smem_bytes"]) == (32, 1, 0) and pl["ku"] % (16 // size[dt]) == 0
+                    assert (pl["tx"], pl["ty"], pl["smem_bytes"]) == (32, 1, 0) and pl["ku"] % pl["vec"] == 0 and pl["vec"] == 2
                 else:
                     assert pl["ty"] == 16 // size[dt] and pl["tx"] * pl["ty"] <= 256 and pl["smem_bytes"] <= 100 * 1024
                 continue

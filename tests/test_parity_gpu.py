@@ -506,3 +506,38 @@ def test_host_tensors_are_streamed_in_chunks(dtype, oracle, monkeypatch):
         cs = ttv_b200.ttv_multi(list(range(1, len(na) + 1)), a, list(na), list(pia), bs)
         for q, (c, want) in enumerate(zip(cs, wants), 1):
             assert np.array_equal(c, want), (na, pia, q, "multi")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex128, np.int32])
+def test_fused_scatter_exchange_emulated_on_one_gpu(dtype, oracle):
+    """ttv_b200_view_scatter + ttv_b200_reduce_slots (the n_q-split product fused with its exchange): `world` ranks are
+    emulated on one device -- each "rank" owns a range of the contraction rows and writes its partial block by block into
+    every owner's workspace; the owners sum their slots.  Peer memory over NVLink only changes what the pointers point to
+    (that part runs in tools/sharded_bench.py --fused on N GPUs)."""
+    import torch
+    from ttv_b200.sharded import PeerExchange, split_range
+    rng = np.random.default_rng(61)
+    for (outer, nq, inner), world in [((1, 37, 5000), 3), ((1, 64, 1031), 4), ((5, 29, 700), 2), ((1, 8, 77), 8), ((3, 40, 256), 5)]:
+        na, pia = (inner, nq, outer), (1, 2, 3)                  # A[outer][nq][inner] is this first-order tensor, q = 2
+        a = rng.integers(-8, 9, outer * nq * inner).astype(dtype)
+        b = rng.integers(-8, 9, nq).astype(dtype)
+        want = oracle.ttv(2, a, na, pia, b)
+        n = outer * inner
+        blk = PeerExchange.block(n, world)
+        assert blk % 256 == 0 and blk * world >= n
+        a3 = torch.from_numpy(a).cuda().view(outer, nq, inner)
+        tb = torch.from_numpy(b).cuda()
+        ws = [torch.full((world * blk,), 99, dtype=a3.dtype, device="cuda") for _ in range(world)]
+        before = ttv_b200.launch_count()
+        for r in range(world):
+            k0, kc = split_range(nq, world, r)
+            a_r = a3[:, k0:k0 + kc, :].contiguous()
+            ttv_b200.ttv_view_scatter(outer, kc, inner, a_r, tb[k0:k0 + kc].contiguous(), [w.data_ptr() for w in ws], r, blk)
+        got = torch.empty(n, dtype=a3.dtype, device="cuda")
+        for j in range(world):
+            first = min(n, j * blk); cnt = max(0, min(blk, n - first))
+            if cnt:
+                ttv_b200.reduce_slots(ws[j], got[first:first + cnt], cnt, blk, world)
+        torch.cuda.synchronize()
+        assert ttv_b200.launch_count() - before >= world + 1
+        assert np.array_equal(got.cpu().numpy(), want), ((outer, nq, inner), world, dtype)

@@ -241,6 +241,31 @@ def ttv_view(outer: int, nq: int, inner: int, a, b, c, **opt_kwargs) -> None:
     _check(lib.ttv_b200_view(dtype_code(a), outer, nq, inner, _ptr(a), _ptr(b), _ptr(c), C.byref(opts)))
 
 
+def ttv_view_scatter(outer: int, nq: int, inner: int, a, b, peer_ptrs, rank: int, blk: int, **opt_kwargs) -> None:
+    """This GPU's partial of C[outer][inner] written block by block into the peers' workspaces (ttv_b200_view_scatter):
+    peer_ptrs[j] = address of GPU j's workspace [world][blk] as seen from this process.  Asynchronous on the current
+    torch stream (a barrier across the GPUs has to follow anyway)."""
+    lib = _lib.load()
+    if "stream" not in opt_kwargs and _is_torch(a):
+        opt_kwargs["stream"] = _current_torch_stream(a)
+    opt_kwargs["flags"] = int(opt_kwargs.get("flags", 0)) | 2
+    opts = make_opts(**opt_kwargs)
+    world = len(peer_ptrs)
+    arr = (C.c_void_p * world)(*[int(p) for p in peer_ptrs])
+    _check(lib.ttv_b200_view_scatter(dtype_code(a), outer, nq, inner, _ptr(a), _ptr(b), arr, world, rank, blk, C.byref(opts)))
+
+
+def reduce_slots(ws, c, n: int, blk: int, slots: int, **opt_kwargs) -> None:
+    """c[j] = sum over the `slots` rows of ws [slots][blk], j < n, in row order (ttv_b200_reduce_slots); asynchronous on the
+    current torch stream."""
+    lib = _lib.load()
+    if "stream" not in opt_kwargs and _is_torch(c):
+        opt_kwargs["stream"] = _current_torch_stream(c)
+    opt_kwargs["flags"] = int(opt_kwargs.get("flags", 0)) | 2
+    opts = make_opts(**opt_kwargs)
+    _check(lib.ttv_b200_reduce_slots(dtype_code(c), _ptr(ws), _ptr(c), n, blk, slots, C.byref(opts)))
+
+
 def fill(x, seed: int, first: int = 0, count: int | None = None) -> None:
     """x[i] = synth(seed, first + i) on the device (torch CUDA tensor, flat)."""
     lib = _lib.load()

@@ -498,6 +498,68 @@ int ttv_b200_view(int dtype, uint64_t outer, uint64_t nq, uint64_t inner, const 
   return run_any(dtype, v, a, b, c, opts);
 }
 
+int ttv_b200_view_scatter(int dtype, uint64_t outer, uint64_t nq, uint64_t inner, const void* a, const void* b,
+                          void* const* peer_ws, uint32_t world, uint32_t rank, uint64_t blk, const ttv_b200_opts* opts)
+{
+  const uint64_t s = (uint64_t)dtype_size(dtype);
+  if (s == 0) return fail(TTV_B200_ERR_DTYPE);
+  if (outer == 0 || nq == 0 || inner == 0) return fail(TTV_B200_ERR_SHAPE_A);
+  if (!a) return fail(TTV_B200_ERR_A_NULL);
+  if (!b) return fail(TTV_B200_ERR_B_NULL);
+  if (!peer_ws) return fail(TTV_B200_ERR_C_NULL);
+  if (world == 0 || world > 16 || rank >= world || blk == 0 || blk * world < outer * inner)
+    return fail(TTV_B200_ERR_OPTS, "ttv_b200_view_scatter: need 1 <= world <= 16, rank < world, world*blk >= outer*inner");
+  for (uint32_t j = 0; j < world; ++j) if (!peer_ws[j]) return fail(TTV_B200_ERR_C_NULL);
+  Where w; int dev = -1;
+  if (int rc = classify(a, &w, &dev)) return rc;
+  if (w != Where::Device) return fail(TTV_B200_ERR_MIXED_POINTERS, "ttv_b200_view_scatter needs device pointers");
+  // widest vector that divides inner and blk and fits every alignment
+  uint64_t align = std::min(alignment_of(a), (uint64_t)256);
+  for (uint32_t j = 0; j < world; ++j) align = std::min(align, alignment_of(peer_ws[j]));
+  uint64_t vec = s >= 16 ? 1 : 16 / s;
+  while (vec > 1 && !((inner % vec) == 0 && (blk % vec) == 0 && (align % (vec * s)) == 0)) vec /= 2;
+  DeviceGuard guard;
+  CUDA_TRY(guard.set(dev), "cudaSetDevice");
+  cudaStream_t stream = opts ? static_cast<cudaStream_t>(opts->stream) : nullptr;
+  int sm = 148;
+  {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    DeviceState* st = nullptr;
+    if (int rc = device_state(dev, &st)) return rc;
+    sm = st->sm_count;
+  }
+  View v;
+  v.outer = outer; v.nq = nq; v.inner = inner;
+  CUDA_TRY(launch_scatter(dtype, v, a, b, peer_ws, world, rank, blk, (int)vec, sm, stream), "scatter launch");
+  if (!(opts && (opts->flags & TTV_B200_FLAG_ASYNC))) CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+  return TTV_B200_OK;
+}
+
+int ttv_b200_reduce_slots(int dtype, const void* ws, void* c, uint64_t n, uint64_t blk, uint32_t slots, const ttv_b200_opts* opts)
+{
+  if (dtype_size(dtype) == 0) return fail(TTV_B200_ERR_DTYPE);
+  if (!ws) return fail(TTV_B200_ERR_A_NULL);
+  if (!c) return fail(TTV_B200_ERR_C_NULL);
+  if (slots == 0 || n > blk) return fail(TTV_B200_ERR_OPTS, "ttv_b200_reduce_slots: need slots >= 1 and n <= blk");
+  Where w; int dev = -1;
+  if (int rc = classify(c, &w, &dev)) return rc;
+  if (w != Where::Device) return fail(TTV_B200_ERR_MIXED_POINTERS, "ttv_b200_reduce_slots needs device pointers");
+  DeviceGuard guard;
+  CUDA_TRY(guard.set(dev), "cudaSetDevice");
+  cudaStream_t stream = opts ? static_cast<cudaStream_t>(opts->stream) : nullptr;
+  const bool accumulate = opts && (opts->flags & TTV_B200_FLAG_ACCUMULATE);
+  int sm = 148;
+  {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    DeviceState* st = nullptr;
+    if (int rc = device_state(dev, &st)) return rc;
+    sm = st->sm_count;
+  }
+  CUDA_TRY(launch_reduce_slots(dtype, ws, c, n, blk, slots, accumulate, sm, stream), "reduce launch");
+  if (!(opts && (opts->flags & TTV_B200_FLAG_ASYNC))) CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+  return TTV_B200_OK;
+}
+
 int ttv_b200_fill(int dtype, void* x, uint64_t first, uint64_t count, uint64_t seed, const ttv_b200_opts* opts)
 {
   if (dtype_size(dtype) == 0) return fail(TTV_B200_ERR_DTYPE);

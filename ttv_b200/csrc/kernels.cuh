@@ -552,11 +552,12 @@ ttv_dot_peel_kernel(const TileParams P)
 // ------------------------------------------------------------------------------------------------------------------
 template<class T>
 __global__ void __launch_bounds__(256)
-ttv_reduce_kernel(const T* __restrict__ ws, T* __restrict__ c, uint64_t n, uint32_t ksplit, uint32_t accumulate)
+ttv_reduce_kernel(const T* __restrict__ ws, T* __restrict__ c, uint64_t n, uint32_t ksplit, uint32_t accumulate, uint64_t stride)
 {
+  // ws is [ksplit][stride], the first n entries of every row are summed (stride == n for the split-n_q workspace)
   for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (uint64_t)gridDim.x * blockDim.x) {
     T s = accumulate ? c[j] : Num<T>::zero();
-    for (uint32_t p = 0; p < ksplit; ++p) s = Num<T>::add(s, ws[(uint64_t)p * n + j]);
+    for (uint32_t p = 0; p < ksplit; ++p) s = Num<T>::add(s, ws[(uint64_t)p * stride + j]);
     c[j] = s;
   }
 }

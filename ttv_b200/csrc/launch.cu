@@ -9,6 +9,7 @@
 #include "colx_kernel.cuh"
 #include "dotf_kernel.cuh"
 #include "strided_kernel.cuh"
+#include "scatter_kernel.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -17,7 +18,8 @@ namespace ttvb {
 
 // one dispatcher per element type, defined in the TTVB_DTYPE translation units
 using tile_fn_t   = cudaError_t (*)(const TileParams&, const Launch&, cudaStream_t);
-using reduce_fn_t = cudaError_t (*)(const void*, void*, uint64_t, uint32_t, bool, int, cudaStream_t);
+using reduce_fn_t = cudaError_t (*)(const void*, void*, uint64_t, uint32_t, bool, uint64_t, int, cudaStream_t);
+using scatter_fn_t = cudaError_t (*)(const ScatterParams&, int, uint64_t, uint64_t, cudaStream_t);
 using fill_fn_t   = cudaError_t (*)(void*, uint64_t, uint64_t, uint64_t, int, cudaStream_t);
 using stream_fn_t = cudaError_t (*)(const StreamParams&, const Launch&, cudaStream_t);
 using dotf_fn_t   = cudaError_t (*)(const DotfParams&, const Launch&, cudaStream_t);
@@ -25,7 +27,8 @@ using strided_fn_t = cudaError_t (*)(const StridedParams&, int, cudaStream_t);
 
 #define TTVB_DECLARE(k)                                                                                          \
   cudaError_t tile_dtype_##k(const TileParams&, const Launch&, cudaStream_t);                                    \
-  cudaError_t reduce_dtype_##k(const void*, void*, uint64_t, uint32_t, bool, int, cudaStream_t);                 \
+  cudaError_t reduce_dtype_##k(const void*, void*, uint64_t, uint32_t, bool, uint64_t, int, cudaStream_t);       \
+  cudaError_t scatter_dtype_##k(const ScatterParams&, int, uint64_t, uint64_t, cudaStream_t);                    \
   cudaError_t fill_dtype_##k(void*, uint64_t, uint64_t, uint64_t, int, cudaStream_t);                            \
   cudaError_t stream_dtype_##k(const StreamParams&, const Launch&, cudaStream_t);                               \
   cudaError_t dotf_dtype_##k(const DotfParams&, const Launch&, cudaStream_t);                                   \
@@ -46,6 +49,7 @@ static const reduce_fn_t k_reduce[] = {reduce_dtype_0, reduce_dtype_1, reduce_dt
 static const fill_fn_t   k_fill[]   = {fill_dtype_0, fill_dtype_1, fill_dtype_2, fill_dtype_3, fill_dtype_4, fill_dtype_5};
 static const stream_fn_t k_stream[] = {stream_dtype_0, stream_dtype_1, stream_dtype_2, stream_dtype_3, stream_dtype_4, stream_dtype_5};
 static const dotf_fn_t   k_dotf[]   = {dotf_dtype_0, dotf_dtype_1, dotf_dtype_2, dotf_dtype_3, dotf_dtype_4, dotf_dtype_5};
+static const scatter_fn_t k_scatter[] = {scatter_dtype_0, scatter_dtype_1, scatter_dtype_2, scatter_dtype_3, scatter_dtype_4, scatter_dtype_5};
 static const strided_fn_t k_strided[] = {strided_dtype_0, strided_dtype_1, strided_dtype_2, strided_dtype_3, strided_dtype_4, strided_dtype_5};
 
 cudaError_t launch_strided(int dtype, const View& v, const void* a, const void* b, void* c, bool accumulate, int sm_count,
@@ -104,7 +108,36 @@ cudaError_t launch_view(int dtype, const View& v, const Launch& l, const void* a
 
   cudaError_t e = k_tile[dtype](P, l, stream);
   if (e != cudaSuccess || l.ksplit <= 1) return e;
-  return k_reduce[dtype](workspace, c, v.outer * v.inner, l.ksplit, accumulate, sm_count, stream);
+  return k_reduce[dtype](workspace, c, v.outer * v.inner, l.ksplit, accumulate, v.outer * v.inner, sm_count, stream);
+}
+
+// Fused n_q-split product + exchange (scatter_kernel.cuh): this GPU's partial of C goes block by block into the peers'
+// workspaces.  vec = elements per 16-byte vector usable for (inner, alignments, blk).
+cudaError_t launch_scatter(int dtype, const View& v, const void* a, const void* b, void* const* peers, uint32_t world, uint32_t rank,
+                           uint64_t blk, int vec, int sm_count, cudaStream_t stream)
+{
+  if (dtype < 0 || dtype >= TTV_B200_DTYPE_COUNT || world == 0 || world > (uint32_t)kMaxPeers || rank >= world) return cudaErrorInvalidValue;
+  ScatterParams S;
+  S.a = a; S.b = b;
+  for (uint32_t j = 0; j < (uint32_t)kMaxPeers; ++j) S.peer[j] = j < world ? peers[j] : nullptr;
+  S.outer = v.outer; S.nq = v.nq; S.inner = v.inner;
+  S.blk = blk;
+  S.itiles = (v.inner / (uint64_t)vec + 255) / 256;
+  S.tiles = S.itiles * v.outer;
+  S.world = world; S.rank = rank;
+  const uint64_t s = (uint64_t)dtype_size(dtype);
+  S.kb = (uint32_t)std::min<uint64_t>(v.nq, 16384 / s);
+  S.stream = s >= 16 ? 1u : 0u;
+  const uint64_t ctas = std::max<uint64_t>(1, std::min<uint64_t>(S.tiles, (uint64_t)sm_count * 64));
+  return k_scatter[dtype](S, vec, ctas, (uint64_t)S.kb * s, stream);
+}
+
+cudaError_t launch_reduce_slots(int dtype, const void* ws, void* c, uint64_t n, uint64_t stride, uint32_t slots, bool accumulate,
+                                int sm_count, cudaStream_t stream)
+{
+  if (dtype < 0 || dtype >= TTV_B200_DTYPE_COUNT) return cudaErrorInvalidValue;
+  if (n == 0) return cudaSuccess;
+  return k_reduce[dtype](ws, c, n, slots, accumulate, stride, sm_count, stream);
 }
 
 cudaError_t launch_fill(int dtype, void* x, uint64_t first, uint64_t count, uint64_t seed, int sm_count, cudaStream_t stream)
@@ -165,6 +198,12 @@ static cudaError_t dispatch_batch(const TileParams& P, const Launch& l, cudaStre
     return cudaErrorInvalidValue;
   }
   if (l.kernel == TTV_B200_KERNEL_COLX && l.warp) {
+    if constexpr (V == 2 && sizeof(T) == 4) {      // 4-byte elements as 8-byte vectors: 2 phases, 4 accumulators per unit
+      switch (key) {
+        TTVB_BATCH_CASE(ttv_colw_kernel, 4, 4) TTVB_BATCH_CASE(ttv_colw_kernel, 2, 8) TTVB_BATCH_CASE(ttv_colw_kernel, 8, 2)
+        default: return cudaErrorInvalidValue;
+      }
+    }
     if constexpr (V > 1 && wide) {
       switch (key) {
         TTVB_BATCH_CASE(ttv_colw_kernel, 1, 8) TTVB_BATCH_CASE(ttv_colw_kernel, 2, 4)
@@ -235,11 +274,11 @@ cudaError_t TTVB_CAT(tile_dtype_, TTVB_DTYPE)(const TileParams& P, const Launch&
 }
 
 cudaError_t TTVB_CAT(reduce_dtype_, TTVB_DTYPE)(const void* ws, void* c, uint64_t n, uint32_t ksplit, bool accumulate,
-                                                 int sm_count, cudaStream_t stream)
+                                                 uint64_t stride, int sm_count, cudaStream_t stream)
 {
   const uint64_t blocks = std::min<uint64_t>((n + 255) / 256, (uint64_t)sm_count * 32);
   ttv_reduce_kernel<elem_t><<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const elem_t*>(ws), static_cast<elem_t*>(c), n,
-                                                                  ksplit, accumulate ? 1u : 0u);
+                                                                  ksplit, accumulate ? 1u : 0u, stride);
   count_launch();
   return cudaGetLastError();
 }
@@ -265,6 +304,14 @@ cudaError_t TTVB_CAT(dotf_dtype_, TTVB_DTYPE)(const DotfParams& D, const Launch&
   kern<<<(unsigned)l.ctas, l.threads, l.smem_bytes, stream>>>(D);
   count_launch();
   return cudaGetLastError();
+}
+
+cudaError_t TTVB_CAT(scatter_dtype_, TTVB_DTYPE)(const ScatterParams& S, int vec, uint64_t ctas, uint64_t smem, cudaStream_t stream)
+{
+  if constexpr (kVmax >= 4) if (vec == 4) { ttv_col_scatter_kernel<elem_t, 4><<<(unsigned)ctas, 256, smem, stream>>>(S); count_launch(); return cudaGetLastError(); }
+  if constexpr (kVmax >= 2) if (vec == 2) { ttv_col_scatter_kernel<elem_t, 2><<<(unsigned)ctas, 256, smem, stream>>>(S); count_launch(); return cudaGetLastError(); }
+  if (vec == 1) { ttv_col_scatter_kernel<elem_t, 1><<<(unsigned)ctas, 256, smem, stream>>>(S); count_launch(); return cudaGetLastError(); }
+  return cudaErrorInvalidValue;
 }
 
 cudaError_t TTVB_CAT(strided_dtype_, TTVB_DTYPE)(const StridedParams& S, int sm_count, cudaStream_t stream)

@@ -291,12 +291,16 @@ static int choose_colx(uint64_t s, const View& v, const ttv_b200_opts* opts, uin
   if (warp_mode == 1 || (warp_mode == -1 && ceil_div(v.nq, TY) < 16)) {
     // a warp owns 31*V columns per unit and all rows of its n_q partition
     l.warp = 1; l.tx = 32; l.ty = 1;
-    uint64_t ku = v.nq <= 2 && V == 2 ? 2 : 4;
+    // Measured (23^7 q=4,7 fp32; 21^7 q=7 fp64): two rows in flight for many units beat deeper batches (6.5 against 6.3
+    // TB/s), and 4-byte elements do best as 8-byte vectors (2 phases: 4 accumulators per unit instead of 16).
+    uint64_t Vw = V, loads = 8;
+    if (s == 4 && env_int("TTV_B200_COLW_V", 2) == 2) { Vw = 2; loads = 16; l.vec = 2; }
+    uint64_t ku = Vw == 2 ? 2 : 4;
     const int ku_env = env_int("TTV_B200_KU", 0);
-    if ((ku_env == 2 || ku_env == 4 || ku_env == 8) && (uint64_t)ku_env % V == 0) ku = (uint64_t)ku_env;
-    uint64_t nu = 8 / ku;
+    if ((ku_env == 2 || ku_env == 4 || ku_env == 8) && (uint64_t)ku_env % Vw == 0) ku = (uint64_t)ku_env;
+    uint64_t nu = loads / ku;
     l.ku = (int)ku; l.nu = (int)nu;
-    l.wcols = 31 * V;
+    l.wcols = 31 * Vw;
     l.itiles = ceil_div(v.inner, nu * l.wcols);
     l.otiles = v.outer;
     const uint64_t tiles1 = l.itiles * l.otiles;

@@ -13,6 +13,11 @@ so that every rank owns one contiguous slab of A:
               computes a full-size partial C, and the partials are summed with ONE reduce / all-reduce (NCCL).
               Integer sums are exact; float sums change order, which the n_q*eps tolerance covers.
 
+              With a PeerExchange (symmetric memory over NVLink / NVSwitch) the exchange is FUSED into the kernel: every
+              rank's kernel stores its partial block by block straight into the owners' memory, a device-side barrier
+              follows, and each rank sums the slots it received -- a deterministic reduce-scatter that leaves C
+              distributed like the free split does (ttv_b200_view_scatter / ttv_b200_reduce_slots).
+
 The arithmetic is always the C-ABI kernel on the local slab; nothing here computes on the CPU.
 """
 from __future__ import annotations
@@ -35,6 +40,52 @@ class Shard:
     a_count: int              # elements of the slab
     c_offset: int             # element offset of the local C inside the global C (free split); 0 for the n_q split
     c_count: int              # elements of the local C
+
+
+class PeerExchange:
+    """Workspaces in symmetric memory for the fused n_q-split exchange: on every GPU two halves (rounds alternate, which
+    orders the reuse of a half behind the barrier of the round in between) of [world][blk_cap] elements, all mapped into
+    every process of the group (torch.distributed._symmetric_memory: peer pointers over NVLink)."""
+
+    def __init__(self, max_c_elems: int, dtype, device, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.dtype = dtype
+        self.itemsize = torch.empty(0, dtype=dtype).element_size()
+        self.blk_cap = self.block(max_c_elems, self.world)
+        self.buf = symm_mem.empty(2 * self.world * self.blk_cap, dtype=dtype, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group.group_name)
+        self.round = 0
+
+    @staticmethod
+    def block(n: int, world: int) -> int:
+        """elements of C's flat index space per rank: equal blocks, rounded up to 256 elements (whole 16-byte vectors)"""
+        return -(-(-(-n // world)) // 256) * 256
+
+    def exchange(self, outer: int, nq: int, inner: int, a_local, b_local):
+        """partial product of this rank -> peers' slots -> barrier -> sum of the received slots.  Returns (c_block, first,
+        count): this rank's block [first, first + count) of the flat C."""
+        import torch
+        from . import api
+        n = outer * inner
+        blk = self.block(n, self.world)
+        if blk > self.blk_cap or a_local.dtype != self.dtype:
+            raise ValueError("PeerExchange: workspace too small or element type differs")
+        half = (self.round % 2) * self.world * self.blk_cap
+        self.round += 1
+        peers = [int(p) + half * self.itemsize for p in self.hdl.buffer_ptrs]
+        api.ttv_view_scatter(outer, nq, inner, a_local, b_local, peers, self.rank, blk)
+        self.hdl.barrier(channel=0)                      # every rank's partials have landed in every owner's slots
+        first = min(n, self.rank * blk)
+        count = max(0, min(blk, n - first))
+        c_block = torch.empty(count, dtype=self.dtype, device=a_local.device)
+        if count:
+            api.reduce_slots(self.buf[half: half + self.world * blk], c_block, count, blk, self.world)
+        return c_block, first, count
 
 
 def split_range(extent: int, world: int, rank: int) -> tuple[int, int]:
@@ -66,7 +117,7 @@ def make_shard(q: int, na: Sequence[int], pia: Sequence[int], rank: int, world: 
 
 
 def ttv_sharded(q: int, a_local, na: Sequence[int], pia: Sequence[int], b, *, rank: int, world: int, c_local=None,
-                group=None, reduce_to: int | None = 0, compute: Callable | None = None):
+                group=None, reduce_to: int | None = 0, compute: Callable | None = None, exchange: PeerExchange | None = None):
     """One sharded TTV.  a_local: this rank's slab (flat, packed, see make_shard); b: the FULL vector (every rank
     holds it; it is tiny).  Returns (c_local, shard):
       free split  -> this rank's slab of C
@@ -95,6 +146,11 @@ def ttv_sharded(q: int, a_local, na: Sequence[int], pia: Sequence[int], b, *, ra
 
     # n_q split
     b_part = b[sh.begin: sh.begin + sh.count]
+    if exchange is not None and world > 1 and int(na[sh.mode - 1]) >= world:
+        # fused: the kernel's stores ARE the exchange; C comes back distributed (this rank's block of the flat C)
+        import dataclasses
+        c_block, first, count = exchange.exchange(1, sh.count, sh.c_count, a_local, b_part)
+        return c_block, dataclasses.replace(sh, kind="nq-scattered", c_offset=first, c_count=count)
     if sh.count:
         compute(q, a_local, list(sh.na_local), list(pia), b_part, c_local)
     else:
