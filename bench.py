@@ -224,7 +224,15 @@ def run_own_arm(args):
     exchange = None
     if world > 1 and not args.nccl_reduce:
         from ttv_b200.sharded import PeerExchange
-        exchange = PeerExchange(shards[ORDER].c_count, torch.float32, dev)
+        try:
+            exchange = PeerExchange(shards[ORDER].c_count, torch.float32, dev)
+        except Exception as exc:                      # no symmetric memory on this box: plain kernel + ncclReduce
+            print(f"bench.py: rank {rank}: peer-memory exchange unavailable ({exc}); using ncclReduce", file=sys.stderr)
+        ok = torch.tensor([1 if exchange is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            exchange = None
+            args.nccl_reduce = True
     live = {}          # what the last step produced: q -> (C of this rank, its shard)
 
     def step():
