@@ -15,6 +15,10 @@
 #include <string>
 #include <utility>
 #include <vector>
+#include <atomic>
+#include <condition_variable>
+#include <memory>
+#include <thread>
 #include <algorithm>
 
 using namespace ttvb;
@@ -61,6 +65,73 @@ struct DeviceState {
   cudaStream_t copy_stream = nullptr;
   Buffer ring[3];
   cudaEvent_t ready[3] = {nullptr, nullptr, nullptr}, freed[3] = {nullptr, nullptr, nullptr};
+  // pageable host memory: pinned bounce buffers, one per ring slot, filled by the copy threads
+  void*  bounce[3] = {nullptr, nullptr, nullptr};
+  size_t bounce_bytes = 0;
+};
+
+// Host threads that copy a chunk of pageable memory into a pinned bounce buffer in parallel.  cudaMemcpy from pageable
+// memory runs at ~11 GB/s on these hosts (the driver stages it through one thread); a handful of threads saturate PCIe.
+class CopyPool {
+ public:
+  explicit CopyPool(int n) { for (int i = 0; i < n; ++i) workers_.emplace_back([this] { run(); }); }
+  ~CopyPool()
+  {
+    { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  void copy(void* dst, const void* src, size_t bytes)
+  {
+    auto job = std::make_shared<Job>();
+    job->dst = static_cast<char*>(dst); job->src = static_cast<const char*>(src); job->bytes = bytes;
+    job->parts = (bytes + kPart - 1) / kPart;
+    job->remaining.store(job->parts);
+    if (job->parts == 0) return;
+    { std::lock_guard<std::mutex> lk(m_); cur_ = job; ++generation_; }
+    cv_.notify_all();
+    work(*job);                                              // the calling thread helps
+    std::unique_lock<std::mutex> lk(m_);
+    done_.wait(lk, [&] { return job->remaining.load() == 0; });
+  }
+
+ private:
+  static constexpr size_t kPart = 2u << 20;
+  struct Job {
+    char* dst = nullptr; const char* src = nullptr; size_t bytes = 0, parts = 0;
+    std::atomic<size_t> next{0}, remaining{0};
+  };
+  void work(Job& j)
+  {
+    for (;;) {
+      const size_t i = j.next.fetch_add(1);
+      if (i >= j.parts) return;
+      const size_t off = i * kPart;
+      std::memcpy(j.dst + off, j.src + off, std::min(kPart, j.bytes - off));
+      if (j.remaining.fetch_sub(1) == 1) { std::lock_guard<std::mutex> lk(m_); done_.notify_all(); }
+    }
+  }
+  void run()
+  {
+    uint64_t seen = 0;
+    for (;;) {
+      std::shared_ptr<Job> job;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
+        if (stop_) return;
+        seen = generation_;
+        job = cur_;
+      }
+      work(*job);
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  std::shared_ptr<Job> cur_;
+  uint64_t generation_ = 0;
+  bool stop_ = false;
 };
 
 std::mutex g_mutex;
@@ -98,6 +169,26 @@ int classify(const void* p, Where* where, int* device)
   if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) { *where = Where::Device; *device = attr.device; }
   else { *where = Where::Host; *device = -1; }
   return TTV_B200_OK;
+}
+
+bool is_pinned_host(const void* p)
+{
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return attr.type == cudaMemoryTypeHost;
+}
+
+CopyPool& copy_pool()
+{
+  static std::unique_ptr<CopyPool> pool;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    int n = 0;
+    if (const char* e = std::getenv("TTV_B200_COPY_THREADS")) n = std::atoi(e);
+    if (n <= 0) n = (int)std::min<unsigned>(12, std::max<unsigned>(2, std::thread::hardware_concurrency() * 3 / 4));
+    pool.reset(new CopyPool(n - 1));                          // the caller is the n-th copier
+  });
+  return *pool;
 }
 
 uint64_t alignment_of(const void* p)
@@ -172,7 +263,11 @@ int run_host_pipelined(int dtype, uint64_t count, const View* views, const void*
   const View& v0 = views[0];
   const uint64_t total = v0.outer * v0.nq * v0.inner;
   const uint64_t slow = v0.slow_extent ? v0.slow_extent : (v0.outer > 1 ? v0.outer : v0.nq);
-  const size_t chunk_target = (size_t)env_mb("TTV_B200_H2D_CHUNK_MB", 128) << 20;
+  // pageable A: smaller chunks, bounced through pinned buffers by the copy threads (memcpy of chunk i+1 overlaps the DMA
+  // of chunk i); pinned A: DMA straight from the caller's buffer
+  const bool bounce = !is_pinned_host(a) && env_mb("TTV_B200_BOUNCE", 1) != 0;
+  const size_t chunk_target = bounce ? std::min<size_t>((size_t)env_mb("TTV_B200_H2D_CHUNK_MB", 128), (size_t)env_mb("TTV_B200_BOUNCE_CHUNK_MB", 32)) << 20
+                                     : (size_t)env_mb("TTV_B200_H2D_CHUNK_MB", 128) << 20;
   const bool debug = env_mb("TTV_B200_DEBUG", 0) != 0;
   if (debug) fprintf(stderr, "[ttv_b200] host path: total=%llu slow=%llu chunk_target=%zu count=%llu\n", (unsigned long long)total,
                      (unsigned long long)slow, chunk_target, (unsigned long long)count);
@@ -212,12 +307,21 @@ int run_host_pipelined(int dtype, uint64_t count, const View* views, const void*
       }
     }
     for (int r = 0; r < 3; ++r) if (int rc = ensure(st->ring[r], chunk_bytes)) return rc;
+    if (bounce && st->bounce_bytes < chunk_bytes) {
+      for (int r = 0; r < 3; ++r) {
+        if (st->bounce[r]) { cudaFreeHost(st->bounce[r]); st->bounce[r] = nullptr; }
+        CUDA_TRY(cudaHostAlloc(&st->bounce[r], chunk_bytes, cudaHostAllocDefault), "cudaHostAlloc");
+      }
+      st->bounce_bytes = chunk_bytes;
+    }
     if (int rc = ensure(st->stage_b, max_b * count)) return rc;
     if (int rc = ensure(st->stage_c, sum_c)) return rc;
     db_ = static_cast<char*>(st->stage_b.ptr); dc_ = static_cast<char*>(st->stage_c.ptr);
   }
   // the vectors (and C when it is accumulated into) go first, on the compute stream
   std::vector<char*> dci(count);
+  std::vector<char> c_pinned(count);
+  for (uint64_t i = 0; i < count; ++i) c_pinned[i] = is_pinned_host(c[i]) ? 1 : 0;
   size_t coff = 0;
   for (uint64_t i = 0; i < count; ++i) {
     const size_t bytes_c = (size_t)(views[i].outer * views[i].inner) * s;
@@ -235,8 +339,15 @@ int run_host_pipelined(int dtype, uint64_t count, const View* views, const void*
     const int r = (int)(ch % 3);
     const uint64_t s0 = ch * per, s1 = std::min(slow, s0 + per), ns = s1 - s0;
     if (ch >= 3) CUDA_TRY(cudaStreamWaitEvent(st->copy_stream, st->freed[r], 0), "cudaStreamWaitEvent");
-    CUDA_TRY(cudaMemcpyAsync(st->ring[r].ptr, ah + (size_t)(s0 * slab) * s, (size_t)(ns * slab) * s, cudaMemcpyHostToDevice,
-                             st->copy_stream), "cudaMemcpyAsync H2D A chunk");
+    const char* src = ah + (size_t)(s0 * slab) * s;
+    if (bounce) {
+      // bounce[r] was last read by the DMA of chunk ch-3, whose completion is ready[r]
+      if (ch >= 3) CUDA_TRY(cudaEventSynchronize(st->ready[r]), "cudaEventSynchronize");
+      copy_pool().copy(st->bounce[r], src, (size_t)(ns * slab) * s);
+      src = static_cast<const char*>(st->bounce[r]);
+    }
+    CUDA_TRY(cudaMemcpyAsync(st->ring[r].ptr, src, (size_t)(ns * slab) * s, cudaMemcpyHostToDevice, st->copy_stream),
+             "cudaMemcpyAsync H2D A chunk");
     CUDA_TRY(cudaEventRecord(st->ready[r], st->copy_stream), "cudaEventRecord");
     CUDA_TRY(cudaStreamWaitEvent(stream, st->ready[r], 0), "cudaStreamWaitEvent");
     for (uint64_t i = 0; i < count; ++i) {
@@ -257,7 +368,7 @@ int run_host_pipelined(int dtype, uint64_t count, const View* views, const void*
       local.flags &= ~(uint32_t)TTV_B200_FLAG_ASYNC;
       local.stream = stream;
       if (int rc = run_view_device(dtype, v, st->ring[r].ptr, bsrc, cdst, &local, device, false)) return rc;
-      if (!nq_split) {
+      if (!nq_split && c_pinned[i]) {      // (a copy into pageable memory would block the host and with it the next chunk)
         const size_t bytes = (size_t)(v.outer * v.inner) * s;
         CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(c[i]) + (cdst - dci[i]), cdst, bytes, cudaMemcpyDeviceToHost, stream),
                  "cudaMemcpyAsync D2H C chunk");
@@ -266,8 +377,9 @@ int run_host_pipelined(int dtype, uint64_t count, const View* views, const void*
     CUDA_TRY(cudaEventRecord(st->freed[r], stream), "cudaEventRecord");
   }
   for (uint64_t i = 0; i < count; ++i)
-    if (views[i].outer == 1)
-      CUDA_TRY(cudaMemcpyAsync(c[i], dci[i], (size_t)views[i].inner * s, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync D2H C");
+    if (views[i].outer == 1 || !c_pinned[i])
+      CUDA_TRY(cudaMemcpyAsync(c[i], dci[i], (size_t)(views[i].outer * views[i].inner) * s, cudaMemcpyDeviceToHost, stream),
+               "cudaMemcpyAsync D2H C");
   CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
   return TTV_B200_OK;
 }
@@ -620,6 +732,8 @@ void ttv_b200_release(void)
     kv.second.workspace.clear();
     for (Buffer* b : {&kv.second.stage_a, &kv.second.stage_b, &kv.second.stage_c, &kv.second.ring[0], &kv.second.ring[1], &kv.second.ring[2]})
       if (b->ptr) { cudaFree(b->ptr); b->ptr = nullptr; b->bytes = 0; }
+    for (int r = 0; r < 3; ++r) if (kv.second.bounce[r]) { cudaFreeHost(kv.second.bounce[r]); kv.second.bounce[r] = nullptr; }
+    kv.second.bounce_bytes = 0;
     cudaSetDevice(prev);
   }
 }
