@@ -318,19 +318,23 @@ def test_stream_kernel_small_slabs(dtype, oracle):
         assert np.array_equal(run_lowlevel(q, a, na, pia, b, c0=c0, kernel="stream", flags=1), want + 3)
 
 
-@pytest.mark.parametrize("form", ["cta", "warp", "auto"])
+@pytest.mark.parametrize("form", ["cta", "warp", "realign", "realign8", "auto"])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.int32, np.int64])
 def test_colx_kernel_unaligned_rows(dtype, form, oracle, monkeypatch):
-    """kernel="colx", both forms (phase lanes across a CTA / all phases inside a warp): rows that start at every phase
-    of a 16-byte line (odd inner), several tiles per row, ragged last tile, a tensor whose last bytes are not a whole
-    vector, n_q shorter than the phase lanes, split n_q, accumulate; and the shapes the chooser routes there by itself"""
+    """kernel="colx", all forms (phase lanes across a CTA / all phases inside a warp / rows realigned at load time with
+    shuffles, two batch depths): rows that start at every phase of a 16-byte line (inner % 4 = 1, 2, 3 and 0), several
+    tiles per row, ragged last tile, a tensor whose last bytes are not a whole vector, n_q shorter than the phase lanes
+    and not a multiple of the batch, split n_q, accumulate; and the shapes the chooser routes there by itself"""
     if form != "auto":
-        monkeypatch.setenv("TTV_B200_COLX_WARP", "1" if form == "warp" else "0")
+        monkeypatch.setenv("TTV_B200_COLX_WARP", {"cta": "0", "warp": "1", "realign": "2", "realign8": "2"}[form])
+    if form == "realign8":
+        monkeypatch.setenv("TTV_B200_KU", "8")
     rng = np.random.default_rng(12)
     name = {np.float32: "f32", np.float64: "f64", np.complex64: "c64", np.int32: "i32", np.int64: "i64"}[dtype]
     cases = [((37, 5, 3), (1, 2, 3), 2), ((1021, 9, 2), (1, 2, 3), 2), ((1021, 3), (1, 2), 2), ((333, 7, 5), (1, 2, 3), 3),
              ((3, 1033, 6), (2, 1, 3), 3), ((2055, 70, 3), (1, 2, 3), 2), ((5, 413, 1, 9), (1, 2, 3, 4), 4), ((64, 10, 3), (1, 2, 3), 2),
-             ((2, 9, 3), (1, 2, 3), 2), ((4099, 33), (1, 2), 2)]
+             ((2, 9, 3), (1, 2, 3), 2), ((4099, 33), (1, 2), 2), ((1022, 9, 3), (1, 2, 3), 2), ((6, 343, 5, 2), (1, 2, 3, 4), 3),
+             ((250, 23, 7), (1, 2, 3), 2), ((127, 23, 9), (1, 2, 3), 2), ((23, 23, 23, 5), (1, 2, 3, 4), 4)]
     for na, pia, q in cases:
         a, b = random_case(rng, na, q, dtype)
         want = oracle.ttv(q, a, na, pia, b)

@@ -23,6 +23,7 @@ TORCH_DT = {"f32": torch.float32, "f64": torch.float64, "c64": torch.complex64, 
             "i32": torch.int32, "i64": torch.int64}
 SIZE = {"f32": 4, "f64": 8, "c64": 8, "c128": 16, "i32": 4, "i64": 8}
 L2 = 126 * 2 ** 20
+B2B = 0          # --b2b N: also time N launches back to back inside one event pair
 
 
 def configs(which):
@@ -31,6 +32,11 @@ def configs(which):
     last = lambda p: list(range(p, 0, -1))
     if which in ("quick", "cfg1", "all"):
         out += [("cfg1", "f32", [512, 512, 512], first(3), q) for q in (1, 2, 3)]
+    if which == "scal":      # size series of the cfg1 shape: fixed cost per launch against streaming rate
+        out += [("scal%d" % m, "f32", [512, 512, m], first(3), q) for m in (128, 256, 512, 1024, 2048, 4096) for q in (1, 2, 3)]
+    if which == "dotk":      # fibers of 1 .. 16 KB at 4 GiB and at 512 MiB: lanes per fiber / CTA size of the DOT kernel
+        out += [("dotk%d" % m, "f32", [m, (1 << 30) // m], first(2), 1) for m in (256, 512, 1024, 2048, 4096)]
+        out += [("dots%d" % m, "f32", [m, (1 << 27) // m], first(2), 1) for m in (256, 512, 1024, 2048, 4096)]
     if which in ("quick", "sym", "all"):
         out += [("sym4", "f32", [256] * 4, first(4), q) for q in (1, 2, 3, 4)]
     if which in ("sym", "all"):
@@ -81,8 +87,19 @@ def bench_one(dt, na, pia, q, reps=10, **opts):
     torch.cuda.synchronize()
     ts = sorted(e0.elapsed_time(e1) for e0, e1 in evs)
     byt = s * (n + na[q - 1] + n // na[q - 1])
+    out = {"ms_med": ts[len(ts) // 2], "ms_min": ts[0], "gbs_med": byt / ts[len(ts) // 2] / 1e6, "gbs_best": byt / ts[0] / 1e6, "bytes": byt}
+    if B2B:
+        # the same launches back to back inside ONE event pair: per-launch time without the event / launch gaps
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(B2B):
+            run(As[i % copies])
+        e1.record()
+        torch.cuda.synchronize()
+        out["ms_b2b"] = e0.elapsed_time(e1) / B2B
+        out["gbs_b2b"] = byt / out["ms_b2b"] / 1e6
     del As
-    return {"ms_med": ts[len(ts) // 2], "ms_min": ts[0], "gbs_med": byt / ts[len(ts) // 2] / 1e6, "gbs_best": byt / ts[0] / 1e6, "bytes": byt}
+    return out
 
 
 def main():
@@ -95,7 +112,10 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--ksplits", default="", help="comma-separated forced n_q splits to try on each config, e.g. '2,4,8'")
     ap.add_argument("--qs", default="", help="comma-separated modes to keep")
+    ap.add_argument("--b2b", type=int, default=0, help="also time N launches back to back inside one event pair")
     args = ap.parse_args()
+    global B2B
+    B2B = args.b2b
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     peak = 6553.9
     try:
@@ -133,7 +153,8 @@ def main():
                 if "gbs_med" in r:
                     rec["frac_measured"] = round(r["gbs_med"] / peak, 3)
                     print(f"{name:8s} {dt:5s} q={q} view={rec['view']} k={rec['kernel']} v={rec['vec']} tx={rec['tx']} ty={rec['ty']} "
-                          f"ks={rec['ksplit']} {rec['variant']}  {r['ms_med']:.3f} ms  {r['gbs_med']:.0f} GB/s ({rec['frac_measured']:.2f})", flush=True)
+                          f"ks={rec['ksplit']} nu={pl.get('nu')} ku={pl.get('ku')} ctas={rec['ctas']} {rec['variant']}  {r['ms_med']:.4f} ms  {r['gbs_med']:.0f} GB/s ({rec['frac_measured']:.2f})"
+                          + (f"  b2b {r['gbs_b2b']:.0f}" if "gbs_b2b" in r else ""), flush=True)
                 else:
                     print(f"{name:8s} {dt:5s} q={q} ERROR {r['error']}", flush=True)
                 f.write(json.dumps(rec) + "\n"); f.flush()

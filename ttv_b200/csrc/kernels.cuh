@@ -37,6 +37,9 @@ template<int NU, int KU> constexpr int min_ctas() { return TTVB_MIN_CTAS; }
 template<int NU, int KU> constexpr int min_ctas() { return 3; }
 #endif
 
+// the column kernel also exists with 256 bytes in flight per thread (16 vector loads): 2 CTAs per SM, 128 registers
+template<class T, int V, int NU, int KU> constexpr int col_min_ctas() { return NU * KU * V * (int)sizeof(T) > 128 ? 2 : min_ctas<NU, KU>(); }
+
 struct TileParams {
   const void* a;
   const void* b;
@@ -130,7 +133,7 @@ __device__ __forceinline__ void col_batch_bg(T (&acc)[NU][V], const T* ap, uint6
 }
 
 template<class T, int V, int NU, int KU, bool BG = false>
-__global__ void __launch_bounds__(256, min_ctas<NU, KU>())
+__global__ void __launch_bounds__(256, col_min_ctas<T, V, NU, KU>())
 ttv_col_kernel(const TileParams P)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -377,7 +380,7 @@ __device__ __forceinline__ void dot_batch_bg(T (&acc)[NU], const T* ap, uint64_t
 }
 
 template<class T, int V, int NU, int KU, bool BG = false>
-__global__ void __launch_bounds__(256, min_ctas<NU, KU>())
+__global__ void __launch_bounds__(256, col_min_ctas<T, V, NU, KU>())
 ttv_dot_kernel(const TileParams P)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -7,6 +7,7 @@
 #include "kernels.cuh"
 #include "stream_kernel.cuh"
 #include "colx_kernel.cuh"
+#include "colr_kernel.cuh"
 #include "dotf_kernel.cuh"
 #include "strided_kernel.cuh"
 #include "scatter_kernel.cuh"
@@ -197,6 +198,30 @@ static cudaError_t dispatch_batch(const TileParams& P, const Launch& l, cudaStre
     }
     return cudaErrorInvalidValue;
   }
+  if (l.kernel == TTV_B200_KERNEL_COLX && l.warp == 2) {      // COLR: inner % V is a template parameter
+    if constexpr (V > 1 && wide) {
+      const int im = (int)(P.inner % (uint64_t)V);
+#define TTVB_COLR_CASE(IM, NU, KU) case (IM) * 10000 + (NU) * 100 + (KU): return launch_tile(ttv_colr_kernel<T, V, IM, NU, KU>, P, l, stream);
+      switch (im * 10000 + key) {
+        TTVB_COLR_CASE(0, 1, 8) TTVB_COLR_CASE(0, 2, 4) TTVB_COLR_CASE(1, 1, 8) TTVB_COLR_CASE(1, 2, 4)
+        default: break;
+      }
+      if constexpr (V == 2) {
+        switch (im * 10000 + key) {
+          TTVB_COLR_CASE(0, 4, 2) TTVB_COLR_CASE(1, 4, 2)
+          default: break;
+        }
+      }
+      if constexpr (V == 4) {
+        switch (im * 10000 + key) {
+          TTVB_COLR_CASE(2, 1, 8) TTVB_COLR_CASE(2, 2, 4) TTVB_COLR_CASE(3, 1, 8) TTVB_COLR_CASE(3, 2, 4)
+          default: break;
+        }
+      }
+#undef TTVB_COLR_CASE
+    }
+    return cudaErrorInvalidValue;
+  }
   if (l.kernel == TTV_B200_KERNEL_COLX && l.warp) {
     if constexpr (V == 2 && sizeof(T) == 4) {      // 4-byte elements as 8-byte vectors: 2 phases, 4 accumulators per unit
       switch (key) {
@@ -241,6 +266,7 @@ static cudaError_t dispatch_batch(const TileParams& P, const Launch& l, cudaStre
     if constexpr (wide) {
       switch (key) {
         TTVB_BATCH_CASE(ttv_dot_kernel, 1, 8) TTVB_BATCH_CASE(ttv_dot_kernel, 2, 4) TTVB_BATCH_CASE(ttv_dot_kernel, 4, 2)
+        TTVB_BATCH_CASE(ttv_dot_kernel, 2, 8) TTVB_BATCH_CASE(ttv_dot_kernel, 4, 4) TTVB_BATCH_CASE(ttv_dot_kernel, 8, 2)
         default: return cudaErrorInvalidValue;
       }
     } else {
@@ -254,6 +280,7 @@ static cudaError_t dispatch_batch(const TileParams& P, const Launch& l, cudaStre
   if constexpr (wide) {
     switch (key) {
       TTVB_BATCH_CASE(ttv_col_kernel, 1, 8) TTVB_BATCH_CASE(ttv_col_kernel, 2, 4) TTVB_BATCH_CASE(ttv_col_kernel, 4, 2)
+      TTVB_BATCH_CASE(ttv_col_kernel, 1, 16) TTVB_BATCH_CASE(ttv_col_kernel, 2, 8)
       default: return cudaErrorInvalidValue;
     }
   } else {

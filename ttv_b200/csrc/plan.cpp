@@ -287,15 +287,25 @@ static int choose_colx(uint64_t s, const View& v, const ttv_b200_opts* opts, uin
   // Short contractions (fewer than 16 rows per phase lane): the per-tile prologue / shared-memory epilogue of the CTA
   // form dominates (measured 23^7 q=4: 4.0 TB/s against 6.4 TB/s), so the warp-autonomous form runs them; long
   // contractions are faster in the CTA form (1625^3 q=2: 7.3 against 6.8 TB/s), which keeps 3 CTAs per SM.
-  const int warp_mode = env_int("TTV_B200_COLX_WARP", -1);
-  if (warp_mode == 1 || (warp_mode == -1 && ceil_div(v.nq, TY) < 16)) {
+  const int warp_mode = env_int("TTV_B200_COLX_WARP", -1);      // -1 auto, 0 CTA form, 1 COLW (phase classes), 2 COLR (realigned)
+  if (warp_mode == 1 || warp_mode == 2 || (warp_mode == -1 && ceil_div(v.nq, TY) < 16)) {
     // a warp owns 31*V columns per unit and all rows of its n_q partition
-    l.warp = 1; l.tx = 32; l.ty = 1;
-    // Measured (23^7 q=4,7 fp32; 21^7 q=7 fp64): two rows in flight for many units beat deeper batches (6.5 against 6.3
-    // TB/s), and 4-byte elements do best as 8-byte vectors (2 phases: 4 accumulators per unit instead of 16).
+    // Measured (23^7 q=4,7 fp32; 21^7 q=7 fp64): the realigned form (80 registers, 3 CTAs per SM, whole-sector stores)
+    // is no faster than the phase-class form (115 registers, 2 CTAs): 6.48-6.53 against 6.46-6.55 TB/s in fp32, 6.33
+    // against 6.57 in fp64 -- neither residency nor the partial-sector stores bound these shapes -- so COLW stays the
+    // default and COLR is kept selectable (profiles/r01_colr_probe.txt).
+    l.warp = warp_mode == 2 ? 2 : 1; l.tx = 32; l.ty = 1;
     uint64_t Vw = V, loads = 8;
-    if (s == 4 && env_int("TTV_B200_COLW_V", 2) == 2) { Vw = 2; loads = 16; l.vec = 2; }
-    uint64_t ku = Vw == 2 ? 2 : 4;
+    uint64_t ku = V;
+    if (l.warp == 1) {
+      // COLW, measured (23^7 q=4,7 fp32; 21^7 q=7 fp64): two rows in flight for many units beat deeper batches (6.5
+      // against 6.3 TB/s), and 4-byte elements do best as 8-byte vectors (2 phases: 4 accumulators per unit, not 16).
+      if (s == 4 && env_int("TTV_B200_COLW_V", 2) == 2) { Vw = 2; loads = 16; l.vec = 2; }
+      ku = Vw == 2 ? 2 : 4;
+    } else {
+      // COLR: full 16-byte vectors, one phase period of rows per batch
+      ku = V;
+    }
     const int ku_env = env_int("TTV_B200_KU", 0);
     if ((ku_env == 2 || ku_env == 4 || ku_env == 8) && (uint64_t)ku_env % Vw == 0) ku = (uint64_t)ku_env;
     uint64_t nu = loads / ku;
@@ -313,7 +323,8 @@ static int choose_colx(uint64_t s, const View& v, const ttv_b200_opts* opts, uin
     l.ksplit = (uint32_t)ksplit; l.kchunk = kchunk;
     l.tiles = tiles1 * ksplit;
     l.ctas = std::min<uint64_t>(ceil_div(l.tiles, NT / 32), sms * 32);
-    l.kb = 0; l.smem_bytes = 0;
+    l.kb = 0;
+    l.smem_bytes = l.warp == 2 ? (NT / 32) * nu * l.wcols * s : 0;      // COLR: one output strip per warp
     l.workspace_bytes = ksplit > 1 ? ksplit * v.outer * v.inner * s : 0;
     *out = l;
     return TTV_B200_OK;
@@ -487,8 +498,11 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
     }
     const uint64_t kv = v.nq / V;                          // vector steps per fiber
     l.tx = 1;
-    // lanes per fiber: about eight vectors per lane, at most one warp (a fiber then reduces with shuffles only)
-    uint64_t ty = std::min<uint64_t>(32, pow2_ceil(ceil_div(kv, 8)));
+    // lanes per fiber: about four vectors per lane (eight when peeling), at most one warp (a fiber then reduces with
+    // shuffles only).  Measured on fibers of 256 / 512 floats (tools/sweep.py --set dotk): four per lane equals eight at
+    // 4 GiB (7.13 / 7.17 against 7.13 / 7.09 TB/s) and is ahead at 512 MiB (6.54 / 6.53 against 6.38 / 6.37): a tile is
+    // two batches instead of four, so the last wave of CTAs is shorter.
+    uint64_t ty = std::min<uint64_t>(32, pow2_ceil(ceil_div(kv, l.peel ? 8 : 4)));
     if (l.peel) ty = std::max<uint64_t>(ty, V == 4 ? 4 : 1);     // two rounds of ty lanes cover the 2V-2 head/tail elements
     // few fibers: put more lanes on each one, as long as every lane keeps at least four vectors
     while (!l.peel && ty < NT && kv / (ty * 2) >= 4 && ceil_div(v.outer, std::max<uint64_t>(1, NT / ty)) < sms * 2) ty *= 2;
@@ -522,6 +536,21 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
       // few slabs: use the idle threads of the CTA along n_q
       while (ty * 2 <= rem / to && v.nq / (ty * 2) >= 8 && ceil_div(v.outer, to) < sms * 2) ty *= 2;
       l.ty = (uint32_t)ty; l.to = (uint32_t)to; l.udir = 1;
+    }
+    {
+      // experiments: force the thread tile of the column kernel (tx lanes along inner, ty along n_q, to slabs per CTA)
+      const int tx_env = env_int("TTV_B200_COL_TX", 0), ty_env = env_int("TTV_B200_COL_TY", 0), to_env = env_int("TTV_B200_COL_TO", 0);
+      if (tx_env > 0 || ty_env > 0 || to_env > 0) {
+        uint64_t tx = tx_env > 0 ? std::min<uint64_t>((uint64_t)tx_env, std::min(cv, NT)) : l.tx;
+        uint64_t ty = ty_env > 0 ? std::min<uint64_t>((uint64_t)ty_env, std::max<uint64_t>(1, NT / tx)) : 1;
+        ty = std::max<uint64_t>(1, std::min(ty, v.nq));
+        uint64_t to = to_env > 0 ? (uint64_t)to_env : std::max<uint64_t>(1, NT / (tx * ty));
+        to = std::max<uint64_t>(1, std::min(std::min(to, NT / (tx * ty)), v.outer));
+        l.tx = (uint32_t)tx; l.ty = (uint32_t)ty; l.to = (uint32_t)to;
+        l.udir = cv > tx ? 0u : 1u;
+        row_units = 0;
+        if (l.udir == 0) { const uint64_t U = ceil_div(cv, tx); row_units = U <= 8 ? U : 0; }
+      }
     }
     // measured: 4/8-byte elements are faster through L1 unless lanes are strung along n_q; 16-byte elements bypass it
     l.stream = (s >= 16 || l.ty > 1) ? 1u : 0u;
@@ -564,7 +593,18 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
 
   // batch shape: ku k-steps for each of nu units; nu*ku loads in flight per thread (128 bytes with 16-byte vectors,
   // 16 loads with narrower ones)
-  const uint64_t loads = (V * s >= 16 || l.peel) ? 8 : 16;
+  uint64_t loads = (V * s >= 16 || l.peel) ? 8 : 16;
+  // Few CTAs (under ~10 per SM) cannot keep HBM busy with 128 bytes in flight per thread: the column kernel then runs
+  // with 16 vector loads per batch (256 bytes, 2 CTAs of 128 registers per SM).  Measured on [1, n_q, 262144] fp32,
+  // 256 CTAs: 6.38 -> 6.54 TB/s at 512 MB, 7.06 -> 7.31 at 4 GB; [1024, 512, 512], 512 CTAs: 5.96 -> 6.99; with 2048
+  // CTAs and more the three-CTA form is ahead again, and so it is when n_q is split across CTAs (65536^2 q=2, 19
+  // partitions: 7.34 against 7.05) (profiles/r01_small_launch_probe.txt).
+  {
+    const uint64_t units0 = dot ? ceil_div(v.outer, l.to) : (l.udir == 0 ? ceil_div(v.inner / V, l.tx) * ceil_div(v.outer, l.to) : ceil_div(v.outer, l.to));
+    const int deep_env = env_int("TTV_B200_LOADS", 0);
+    const bool few = !dot && ksplit == 1 && units0 < sms * 10;       // (with n_q split across CTAs the 3-CTA form stays ahead)
+    if (!l.peel && V * s >= 16 && (deep_env == 16 || (deep_env == 0 && few && !l.bdirect))) loads = 16;
+  }
   const uint64_t per = ceil_div(std::min(kchunk, v.nq), kstep);       // k-steps one thread makes per unit
   // Batch depth (all rules measured on B200, tools/sweep.py).  Predicated-off slots of the last batch are wasted
   // issue slots, so short contractions take the depth that wastes least and fill the batch with more units; long ones
@@ -613,17 +653,18 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
     l.c_ustride = l.to;
   } else if (l.udir == 0) {
     l.itiles = ceil_div(v.inner / V, (uint64_t)l.tx * l.nu);
-    l.otiles = v.outer;
+    l.otiles = ceil_div(v.outer, (uint64_t)l.to);
     l.a_ustride = (uint64_t)l.tx * V;
     l.c_ustride = (uint64_t)l.tx * V;
   } else {
-    l.itiles = 1;
+    l.itiles = ceil_div(v.inner / V, (uint64_t)l.tx);
     l.otiles = ceil_div(v.outer, (uint64_t)l.to * l.nu);
     l.a_ustride = (uint64_t)l.to * v.nq * v.inner;
     l.c_ustride = (uint64_t)l.to * v.inner;
   }
   l.tiles = l.itiles * l.otiles * ksplit;
-  l.ctas  = std::min<uint64_t>(l.tiles, sms * 64);
+  l.ctas  = std::min<uint64_t>(l.tiles, sms * (uint64_t)std::max(1, env_int("TTV_B200_GRID_MULT", 64)));
+  if (env_int("TTV_B200_GRID", 0) > 0) l.ctas = std::min<uint64_t>(l.tiles, (uint64_t)env_int("TTV_B200_GRID", 0));
 
   // shared memory: a chunk of b (16 KB at most; the peeled DOT keeps V shifted copies of all of b) + reduction scratch
   uint64_t kb = std::min<uint64_t>(kchunk, 16384 / s);
