@@ -594,6 +594,7 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
   // batch shape: ku k-steps for each of nu units; nu*ku loads in flight per thread (128 bytes with 16-byte vectors,
   // 16 loads with narrower ones)
   uint64_t loads = (V * s >= 16 || l.peel) ? 8 : 16;
+  const uint64_t per = ceil_div(std::min(kchunk, v.nq), kstep);       // k-steps one thread makes per unit
   // Few CTAs (under ~10 per SM) cannot keep HBM busy with 128 bytes in flight per thread: the column kernel then runs
   // with 16 vector loads per batch (256 bytes, 2 CTAs of 128 registers per SM).  Measured on [1, n_q, 262144] fp32,
   // 256 CTAs: 6.38 -> 6.54 TB/s at 512 MB, 7.06 -> 7.31 at 4 GB; [1024, 512, 512], 512 CTAs: 5.96 -> 6.99; with 2048
@@ -602,10 +603,9 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
   {
     const uint64_t units0 = dot ? ceil_div(v.outer, l.to) : (l.udir == 0 ? ceil_div(v.inner / V, l.tx) * ceil_div(v.outer, l.to) : ceil_div(v.outer, l.to));
     const int deep_env = env_int("TTV_B200_LOADS", 0);
-    const bool few = !dot && ksplit == 1 && units0 < sms * 10;       // (with n_q split across CTAs the 3-CTA form stays ahead)
+    const bool few = !dot && ksplit == 1 && units0 < sms * 10 && per >= 16;       // (with n_q split across CTAs the 3-CTA form stays ahead)
     if (!l.peel && V * s >= 16 && (deep_env == 16 || (deep_env == 0 && few && !l.bdirect))) loads = 16;
   }
-  const uint64_t per = ceil_div(std::min(kchunk, v.nq), kstep);       // k-steps one thread makes per unit
   // Batch depth (all rules measured on B200, tools/sweep.py).  Predicated-off slots of the last batch are wasted
   // issue slots, so short contractions take the depth that wastes least and fill the batch with more units; long ones
   // take the full depth with one unit.
