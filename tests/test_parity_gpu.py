@@ -94,6 +94,42 @@ def test_non_power_of_two_and_unit_extents(dtype, oracle):
                 assert np.array_equal(c, oracle.naive(q, a, na, pia, b)), (na, pia, q, dtype)
 
 
+@pytest.mark.parametrize("dtype", ALL_DTYPES)
+def test_random_orders_shapes_layouts(dtype, oracle):
+    """seeded fuzz over what the reference's grid never varies together: order 2..9, extents that are odd / prime / 1 /
+    one or two large ones (so that every kernel family and its ragged edges are reached through the chooser), random
+    non-hierarchical layouts, every q; device and host pointers alternate.  Bit-exact against the oracle's loop nest."""
+    import torch
+    rng = np.random.default_rng(20261017 + ALL_DTYPES.index(dtype))
+    small = [1, 2, 3, 4, 5, 7, 8, 9, 16, 21, 23]
+    large = [31, 40, 64, 84, 127, 215, 256, 333, 512, 1025, 1625, 4099]
+    seen = set()
+    for case in range(60):
+        p = int(rng.integers(2, 10))
+        na = [int(rng.choice(small)) for _ in range(p)]
+        for _ in range(int(rng.integers(0, 3))):                      # up to two large modes
+            na[int(rng.integers(0, p))] = int(rng.choice(large))
+        while int(np.prod(na, dtype=object)) > 3_000_000:              # keep the oracle fast: shrink the largest mode
+            na[int(np.argmax(na))] = max(1, max(na) // 2)
+        pia = [int(x) + 1 for x in rng.permutation(p)]
+        for q in range(1, p + 1):
+            a, b = random_case(rng, na, q, dtype)
+            want = oracle.ttv(q, a, na, pia, b)
+            if (case + q) % 2:
+                got = run_lowlevel(q, a, na, pia, b)
+            else:
+                ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+                tc = torch.full((want.size,), 7, dtype=ta.dtype, device="cuda")          # C is overwritten
+                nc = ttv_b200.generate_output_shape(na, q); pic = ttv_b200.generate_output_layout(pia, q)
+                ttv_b200.ttv_lowlevel(q, p, ta, na, ttv_b200.generate_strides(na, pia), pia, tb, [len(b)], tc, nc,
+                                      ttv_b200.generate_strides(nc, pic), pic)
+                torch.cuda.synchronize()
+                got = tc.cpu().numpy()
+            assert np.array_equal(got, want), (na, pia, q)
+            seen.add(ttv_b200.plan(q, na, pia, dtype=ttv_b200.api.dtype_code(a))["kernel"])
+    assert {1, 2}.issubset(seen), seen                                 # at least the two main families were exercised
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.complex128])
 def test_rounding_within_stated_tolerance(dtype, oracle):
     rng = np.random.default_rng(9)
@@ -480,6 +516,42 @@ def test_arrays_that_are_not_contiguous_are_read_in_place(dtype):
                     if np.shares_memory(x, base) else torch.from_numpy(np.ascontiguousarray(x)).cuda()
                 tg = ttv_b200.ttv(q, tx, torch.from_numpy(b).cuda())
                 assert np.array_equal(tg.cpu().numpy(), want), (x.shape, x.strides, q, "device")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.complex128, np.int32])
+def test_padded_rows_when_q_is_the_contiguous_mode(dtype):
+    """slices whose CONTIGUOUS axis is the contracted one (rows with a padded leading dimension): lane groups of
+    ttv_strided_dot_kernel along the fibers -- vector widths 4 / 2 / 1 by the alignment of extent, strides and base
+    address, group sizes 2..32, fibers longer than one pass of the group, fewer fibers than a warp holds, accumulate"""
+    import torch
+    rng = np.random.default_rng(43)
+    bases = [rng.integers(-8, 9, shape).astype(dtype) for shape in [(50, 9, 300), (3, 2100), (7, 5, 3, 64), (1000, 36)]]
+    if np.dtype(dtype).kind == "c":
+        bases = [x + 1j * rng.integers(-8, 9, x.shape).astype(dtype) for x in bases]
+    views = [bases[0][:, :, :250], bases[0][:, :, :248], bases[0][1:, 2:7, 3:36], bases[0][:, :, 1:10], bases[1][:, :2048],
+             bases[1][:, 5:1030], bases[2][:, 1:4, :, :40], bases[3][:, :32], bases[3][::3, 4:36]]
+    for x in views:
+        q = x.ndim                                        # C-contiguous base: the last axis has stride 1
+        b = rng.integers(-8, 9, x.shape[q - 1]).astype(dtype)
+        want = np.tensordot(x, b, axes=([q - 1], [0]))
+        got = ttv_b200.ttv(q, x, b)
+        assert got.shape == want.shape and np.array_equal(got, want), (x.shape, x.strides)
+        base = next(y for y in bases if np.shares_memory(x, y))
+        off = (x.__array_interface__["data"][0] - base.__array_interface__["data"][0]) // x.itemsize
+        tx = torch.from_numpy(base).cuda().as_strided(x.shape, [st // x.itemsize for st in x.strides], off)
+        tg = ttv_b200.ttv(q, tx, torch.from_numpy(b).cuda())
+        assert np.array_equal(tg.cpu().numpy(), want), (x.shape, x.strides, "device")
+        # the C-like interface with the strides taken at their word (TTV_B200_FLAG_HONOR_STRIDES = 8), accumulate (1)
+        p = x.ndim
+        na = list(x.shape); wa = [st // x.itemsize for st in x.strides]
+        pia = [int(m) + 1 for m in np.argsort(wa, kind="stable")]
+        nc = ttv_b200.generate_output_shape(na, q); pic = ttv_b200.generate_output_layout(pia, q)
+        wc = ttv_b200.generate_strides(nc, pic)
+        flat = base.reshape(-1)[off:]
+        c = np.full(want.size, 3, dtype)
+        ttv_b200.ttv_lowlevel(q, p, flat, na, wa, pia, b, [len(b)], c, nc, wc, pic, flags=8 | 1)
+        got = np.lib.stride_tricks.as_strided(c, shape=nc, strides=[w * c.itemsize for w in wc])
+        assert np.array_equal(got, want + 3), (x.shape, x.strides, "lowlevel")
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.complex64])

@@ -21,7 +21,7 @@ def main():
     ap.add_argument("--kernel", default="auto")
     ap.add_argument("--launches", type=int, default=4)
     args = ap.parse_args()
-    for name, dt, na, pia, q in sweep.configs("all"):
+    for name, dt, na, pia, q, *rest in sweep.configs("all"):
         if name == args.cfg and q == args.q and (not args.dtype or dt == args.dtype):
             opts = {}
             if args.ksplit:

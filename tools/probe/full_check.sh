@@ -1,4 +1,2 @@
-set -x
-python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-python tools/sweep.py --set all --reps 10 --out gpurun_out/sweep_s3.jsonl > gpurun_out/sweep_s3.txt 2>&1
-python tools/sweep.py --set all --only cplx5,cplx6 --qs 5,2 --reps 10 --envs "TTV_B200_USE_STREAM=1;TTV_B200_USE_DOTF=0" --out gpurun_out/stream_c128.jsonl > gpurun_out/stream_c128.txt 2>&1
+python tools/sweep.py --set pad --reps 7 --out gpurun_out/pad.jsonl > gpurun_out/pad.txt 2>&1
+python tools/sweep.py --set quick --reps 7 --out gpurun_out/quick.jsonl > gpurun_out/quick.txt 2>&1

@@ -37,6 +37,11 @@ def configs(which):
     if which == "dotk":      # fibers of 1 .. 16 KB at 4 GiB and at 512 MiB: lanes per fiber / CTA size of the DOT kernel
         out += [("dotk%d" % m, "f32", [m, (1 << 30) // m], first(2), 1) for m in (256, 512, 1024, 2048, 4096)]
         out += [("dots%d" % m, "f32", [m, (1 << 27) // m], first(2), 1) for m in (256, 512, 1024, 2048, 4096)]
+    if which == "pad":       # slices of a packed 256^4 tensor, read in place through wa (TTV_B200_FLAG_HONOR_STRIDES)
+        w4 = [1, 256, 256 ** 2, 256 ** 3]
+        out += [("pad3", "f32", [256, 256, 250, 256], first(4), q, w4) for q in (1, 2, 3, 4)]      # A[:, :, :250, :]
+        out += [("pad1", "f32", [250, 256, 256, 256], first(4), q, w4) for q in (1, 2, 3, 4)]      # A[:250]: padded rows
+        out += [("pad12", "f64", [120, 250, 128, 128], first(4), q, [1, 128, 128 * 256, 128 * 256 * 128]) for q in (1, 2, 3, 4)]
     if which in ("quick", "sym", "all"):
         out += [("sym4", "f32", [256] * 4, first(4), q) for q in (1, 2, 3, 4)]
     if which in ("sym", "all"):
@@ -63,21 +68,24 @@ def configs(which):
     return out
 
 
-def bench_one(dt, na, pia, q, reps=10, **opts):
+def bench_one(dt, na, pia, q, reps=10, wa=None, **opts):
     n = int(np.prod(na, dtype=object))
     s = SIZE[dt]
     copies = max(1, min(4, -(-4 * L2 // (n * s))))         # rotate when A is not much larger than L2
     As = []
+    span = n if wa is None else 1 + sum((e - 1) * w for e, w in zip(na, wa))
     for i in range(copies):
-        a = torch.empty(n, dtype=TORCH_DT[dt], device="cuda")
+        a = torch.empty(span, dtype=TORCH_DT[dt], device="cuda")
         ttv_b200.fill(a, 0x77170001 + i)
         As.append(a)
     b = torch.empty(na[q - 1], dtype=TORCH_DT[dt], device="cuda")
     ttv_b200.fill(b, 0x77170002)
     nc = ttv_b200.generate_output_shape(na, q); pic = ttv_b200.generate_output_layout(pia, q)
-    wa = ttv_b200.generate_strides(na, pia); wc = ttv_b200.generate_strides(nc, pic)
+    flags = 2 if wa is None else 2 | 8
+    wa = ttv_b200.generate_strides(na, pia) if wa is None else list(wa)
+    wc = ttv_b200.generate_strides(nc, pic)
     c = torch.empty(n // na[q - 1], dtype=TORCH_DT[dt], device="cuda")
-    run = lambda a: ttv_b200.ttv_lowlevel(q, len(na), a, na, wa, pia, b, [na[q - 1]], c, nc, wc, pic, flags=2, **opts)
+    run = lambda a: ttv_b200.ttv_lowlevel(q, len(na), a, na, wa, pia, b, [na[q - 1]], c, nc, wc, pic, flags=flags, **opts)
     for i in range(3):
         run(As[i % copies])
     torch.cuda.synchronize()
@@ -123,7 +131,8 @@ def main():
     except Exception:
         pass
     with open(args.out, "a") as f:
-        for name, dt, na, pia, q in configs(args.set):
+        for name, dt, na, pia, q, *rest in configs(args.set):
+            wa = rest[0] if rest else None
             if args.only and name not in args.only.split(","):
                 continue
             variants = [dict()]
@@ -141,8 +150,8 @@ def main():
                     os.environ[k] = v
                 opts = {k: v for k, v in var.items() if k != "env"}
                 try:
-                    pl = ttv_b200.plan(q, na, pia, dtype=dt, **opts)
-                    r = bench_one(dt, na, pia, q, reps=args.reps, **opts)
+                    pl = ttv_b200.plan(q, na, pia, dtype=dt, wa=wa, **({**opts, "flags": 8} if wa else opts))
+                    r = bench_one(dt, na, pia, q, reps=args.reps, wa=wa, **opts)
                 except Exception as exc:
                     r, pl = {"error": str(exc)}, {}
                 for k in env:

@@ -13,6 +13,7 @@ torch is only used for device memory and streams -- all arithmetic happens in li
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from typing import Sequence
 
 import numpy as np
@@ -69,13 +70,22 @@ def _ptr(x):
     return C.c_void_p(x.ctypes.data)
 
 
-def _tuple(v):
-    if v is None:
-        return None, None
-    arr = np.ascontiguousarray(np.asarray(list(v), dtype=np.uint64))
+@functools.lru_cache(maxsize=8192)
+def _tuple_cached(key: tuple):
+    arr = np.ascontiguousarray(np.asarray(key, dtype=np.uint64))
     if arr.size == 0:
         arr = np.zeros(1, np.uint64)        # keep the pointer non-null; the length travels separately (p)
-    return arr, arr.ctypes.data_as(_lib.u64p)
+    arr.setflags(write=False)
+    return arr, C.cast(arr.ctypes.data, _lib.u64p)
+
+
+def _tuple(v):
+    """(uint64 array, pointer) of a shape / stride / layout tuple.  The C side only reads them, so the conversions are
+    cached per value: a call of the low-level interface converts seven tuples, which otherwise costs more host time than
+    the launch itself."""
+    if v is None:
+        return None, None
+    return _tuple_cached(tuple(int(x) for x in v))
 
 
 def make_opts(*, execution="par_loop", slicing="subtensor", fusion="all", kernel="auto", ksplit=0, flags=0, device=-1,

@@ -341,8 +341,32 @@ cudaError_t TTVB_CAT(scatter_dtype_, TTVB_DTYPE)(const ScatterParams& S, int vec
   return cudaErrorInvalidValue;
 }
 
+template<int V>
+static cudaError_t launch_strided_dot(const StridedParams& S, int sm_count, cudaStream_t stream)
+{
+  // lanes per fiber: one batch of loads each if a warp suffices, at most a warp
+  const uint64_t kv = S.nq / (uint64_t)V;
+  uint32_t G = 1;
+  while (G < 32 && (uint64_t)G * strided_dot_ku<elem_t, V>() < kv) G *= 2;
+  const uint64_t fibers_per_cta = 256 / G;
+  const uint64_t blocks = std::max<uint64_t>(1, std::min<uint64_t>((S.total + fibers_per_cta - 1) / fibers_per_cta, (uint64_t)sm_count * 32));
+  ttv_strided_dot_kernel<elem_t, V><<<(unsigned)blocks, 256, 0, stream>>>(S, G);
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t TTVB_CAT(strided_dtype_, TTVB_DTYPE)(const StridedParams& S, int sm_count, cudaStream_t stream)
 {
+  if (S.wq == 1 && S.nq >= 8) {
+    // q is the contiguous mode: lane groups along the fibers, with the widest vector the strides and addresses allow
+    uint64_t align = (uint64_t)(reinterpret_cast<uintptr_t>(S.a) | reinterpret_cast<uintptr_t>(S.b)) / sizeof(elem_t);
+    if ((reinterpret_cast<uintptr_t>(S.a) | reinterpret_cast<uintptr_t>(S.b)) % sizeof(elem_t)) align = 1;
+    align |= S.nq;
+    for (uint32_t d = 0; d < S.nfree; ++d) align |= S.wa[d];
+    if constexpr (kVmax >= 4) if (align % 4 == 0) return launch_strided_dot<4>(S, sm_count, stream);
+    if constexpr (kVmax >= 2) if (align % 2 == 0) return launch_strided_dot<2>(S, sm_count, stream);
+    return launch_strided_dot<1>(S, sm_count, stream);
+  }
   const uint64_t blocks = std::max<uint64_t>(1, std::min<uint64_t>((S.total + 255) / 256, (uint64_t)sm_count * 32));
   ttv_strided_kernel<elem_t><<<(unsigned)blocks, 256, 0, stream>>>(S);
   count_launch();

@@ -498,11 +498,12 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
     }
     const uint64_t kv = v.nq / V;                          // vector steps per fiber
     l.tx = 1;
-    // lanes per fiber: about four vectors per lane (eight when peeling), at most one warp (a fiber then reduces with
-    // shuffles only).  Measured on fibers of 256 / 512 floats (tools/sweep.py --set dotk): four per lane equals eight at
-    // 4 GiB (7.13 / 7.17 against 7.13 / 7.09 TB/s) and is ahead at 512 MiB (6.54 / 6.53 against 6.38 / 6.37): a tile is
-    // two batches instead of four, so the last wave of CTAs is shorter.
-    uint64_t ty = std::min<uint64_t>(32, pow2_ceil(ceil_div(kv, l.peel ? 8 : 4)));
+    // lanes per fiber: about eight vectors per lane, at most one warp (a fiber then reduces with shuffles only); four
+    // per lane on tensors under 2 GiB, where a tile of two batches instead of four shortens the last wave of CTAs.
+    // Measured on fibers of 256 / 512 floats (tools/sweep.py --set dotk, profiles/r01_dot_lanes_probe.txt): at
+    // 512 MiB 6.54 / 6.53 against 6.38 / 6.37 TB/s, at 4 GiB 7.13 / 7.17 against 7.13 / 7.09, at 16 GiB 7.14 against 7.18.
+    const bool small_tensor = v.outer * v.nq * s < (2ull << 30);
+    uint64_t ty = std::min<uint64_t>(32, pow2_ceil(ceil_div(kv, (l.peel || !small_tensor) ? 8 : 4)));
     if (l.peel) ty = std::max<uint64_t>(ty, V == 4 ? 4 : 1);     // two rounds of ty lanes cover the 2V-2 head/tail elements
     // few fibers: put more lanes on each one, as long as every lane keeps at least four vectors
     while (!l.peel && ty < NT && kv / (ty * 2) >= 4 && ceil_div(v.outer, std::max<uint64_t>(1, NT / ty)) < sms * 2) ty *= 2;
