@@ -9,8 +9,8 @@ wrapped_ttv.cpp:205-206; strides ignored, :44-45) every element type of the C-AB
 C-contiguous (transposes, slices, Fortran order) are read in place through their strides.  Errors the reference raises as
 std::invalid_argument surface as ValueError with the same text.
 
-ttvs keeps the intermediates in HBM: A and the vectors are uploaded once, the p-1 kernels run back to back on the
-device, and only the final vector is copied back.
+ttvs keeps the intermediates in HBM: A crosses PCIe once (streamed in chunks under the first product when it comes from
+host memory), the remaining kernels run back to back on the device, and only the final vector is copied back.
 """
 from __future__ import annotations
 
@@ -100,14 +100,23 @@ def ttvs(q: int, A, bs, order: str = "optimal"):
         return A
 
     import torch
+    steps = chain_plan(q, shape, order)
     if on_device:
         cur = A.contiguous()
         vecs = [bj.contiguous() for bj in bs]
     else:
         if not torch.cuda.is_available():
             raise api.TTVError(40, "Error in ttv_b200: CUDA failure (no CPU fallback exists). [no CUDA device]")
-        cur = torch.from_numpy(A).cuda()
+        # The first product reads all of A: it goes through the host-pointer path of the C-ABI, which streams A across
+        # PCIe in chunks with the kernels overlapping the copies (a plain upload of pageable memory first measured
+        # 11.5 GB/s on a 17 GB tensor).  Its result is n_q times smaller and continues on the device.
+        mode, j = steps[0]
+        first = api.ttv(mode, A, np.ascontiguousarray(np.asarray(bs[j]), dtype=A.dtype))
+        steps = steps[1:]
+        if not steps:
+            return np.ascontiguousarray(first)
+        cur = torch.from_numpy(np.ascontiguousarray(first)).cuda()
         vecs = [torch.from_numpy(np.ascontiguousarray(np.asarray(bj), dtype=A.dtype)).cuda() for bj in bs]
-    for mode, j in chain_plan(q, shape, order):
+    for mode, j in steps:
         cur = api.ttv(mode, cur, vecs[j]).contiguous()      # output of a last-order tensor is last-order: no copy
     return cur if on_device else cur.cpu().numpy()
