@@ -60,6 +60,8 @@ def configs(which):
             out += [("asym5", dt, [4, 1 << 18, 2, 2, 256], first(5), q) for q in (1, 2, 3, 4, 5)]
             out += [("asym4", dt, [16, 1024, 4, 1 << 14], first(4), q) for q in (1, 2, 3, 4)]
             out += [("asym6", dt, [2, 3, 1 << 20, 2, 4, 16], first(6), q) for q in (1, 2, 3, 4, 6)]
+            out += [("asym8", dt, [4, 1 << 16, 2, 2, 3, 2, 2, 64], first(8), q) for q in (1, 2, 5, 8)]
+            out += [("asym10", dt, [2, 2, 4, 2, 1 << 15, 2, 3, 2, 2, 128], first(10), q) for q in (1, 3, 5, 7, 10)]
     if which in ("complex", "all"):
         out += [("cplx4", "c64", [128] * 4, last(4), q) for q in (1, 2, 4)]
         out += [("cplx4r", "c64", [128] * 4, [3, 1, 4, 2], q) for q in (1, 2, 3, 4)]
