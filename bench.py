@@ -205,7 +205,14 @@ def run_own_arm(args):
         raise SystemExit("bench.py: no CUDA device; this framework has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_bound = False
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        if not args.no_numa_bind:
+            # one process per GPU: keep this rank (and the pinned staging buffers it allocates) on the socket of its GPU
+            from ttv_b200.sharded import bind_host_to_gpu
+            numa_bound = bind_host_to_gpu(local)
         dist.init_process_group("nccl", device_id=dev)
 
     na_global = [EXT, EXT, EXT, EXT * world]
@@ -338,6 +345,8 @@ def run_own_arm(args):
 
     if e2e:
         e2e.pop("_a_host", None)
+        if world > 1:
+            e2e["host_bound_to_gpu_socket"] = bool(numa_bound)
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
@@ -486,6 +495,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not pin the rank to the CPUs next to its GPU")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--nccl-reduce", action="store_true", help="N > 1: plain kernel + ncclReduce for the n_q-split product instead of the fused exchange")
     args = ap.parse_args()

@@ -554,6 +554,66 @@ def test_padded_rows_when_q_is_the_contiguous_mode(dtype):
         assert np.array_equal(got, want + 3), (x.shape, x.strides, "lowlevel")
 
 
+def test_async_device_calls_are_capturable_in_a_cuda_graph(oracle):
+    """TTV_B200_FLAG_ASYNC calls on device pointers only enqueue work on the caller's stream (no allocation, no
+    synchronisation once the workspace has its size), so a launch-bound sequence of products -- every mode of a small
+    tensor, a split-n_q product with its reduce pass, a ttvs-like chain -- can be captured ONCE into a CUDA graph and
+    replayed on new data with a single launch"""
+    import torch
+    rng = np.random.default_rng(77)
+    na, pia = (24, 18, 20, 6), (2, 1, 4, 3)
+    p = len(na)
+    n = int(np.prod(na))
+    a0, _ = random_case(rng, na, 1, np.float32)
+    ta = torch.from_numpy(a0).cuda()
+    tbs, tcs, meta = [], [], []
+    for q in range(1, p + 1):
+        tbs.append(torch.from_numpy(rng.integers(-8, 9, na[q - 1]).astype(np.float32)).cuda())
+        nc = ttv_b200.generate_output_shape(na, q); pic = ttv_b200.generate_output_layout(pia, q)
+        tcs.append(torch.zeros(n // na[q - 1], dtype=torch.float32, device="cuda"))
+        meta.append((nc, ttv_b200.generate_strides(nc, pic), pic))
+    wa = ttv_b200.generate_strides(na, pia)
+    # a second stage on the result of q = 1 (a chain like ttvs), and a forced n_q split (workspace + reduce launch)
+    nc1, wc1, pic1 = meta[0]
+    tb2 = torch.from_numpy(rng.integers(-8, 9, nc1[0]).astype(np.float32)).cuda()
+    nc2 = ttv_b200.generate_output_shape(nc1, 1); pic2 = ttv_b200.generate_output_layout(pic1, 1)
+    tc2 = torch.zeros(int(np.prod(nc2)), dtype=torch.float32, device="cuda")
+    tc_split = torch.zeros_like(tcs[2])
+    stream = torch.cuda.Stream()
+
+    def enqueue():
+        for q in range(1, p + 1):
+            nc, wc, pic = meta[q - 1]
+            ttv_b200.ttv_lowlevel(q, p, ta, na, wa, pia, tbs[q - 1], [na[q - 1]], tcs[q - 1], nc, wc, pic, flags=2, stream=stream)
+        ttv_b200.ttv_lowlevel(1, p - 1, tcs[0], nc1, wc1, pic1, tb2, [nc1[0]], tc2, nc2, ttv_b200.generate_strides(nc2, pic2), pic2,
+                              flags=2, stream=stream)
+        nc, wc, pic = meta[2]
+        ttv_b200.ttv_lowlevel(3, p, ta, na, wa, pia, tbs[2], [na[2]], tc_split, nc, wc, pic, flags=2, ksplit=4, stream=stream)
+
+    with torch.cuda.stream(stream):
+        enqueue()                                    # warm-up outside the capture: sizes the workspace
+    stream.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    before = ttv_b200.launch_count()
+    with torch.cuda.graph(graph, stream=stream):
+        enqueue()
+    assert ttv_b200.launch_count() - before >= p + 3          # p products + chain stage + split product and its reduce pass
+    for trial in range(2):                           # replay on NEW contents of the same buffers
+        a1, _ = random_case(rng, na, 1, np.float32)
+        ta.copy_(torch.from_numpy(a1))
+        for c in tcs + [tc2, tc_split]:
+            c.fill_(-1)
+        torch.cuda.synchronize()
+        graph.replay()
+        torch.cuda.synchronize()
+        for q in range(1, p + 1):
+            want = oracle.ttv(q, a1, na, pia, tbs[q - 1].cpu().numpy())
+            assert np.array_equal(tcs[q - 1].cpu().numpy(), want), (trial, q)
+        want1 = oracle.ttv(1, a1, na, pia, tbs[0].cpu().numpy())
+        assert np.array_equal(tc2.cpu().numpy(), oracle.ttv(1, want1, nc1, pic1, tb2.cpu().numpy())), trial
+        assert np.array_equal(tc_split.cpu().numpy(), oracle.ttv(3, a1, na, pia, tbs[2].cpu().numpy())), trial
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.complex64])
 def test_host_tensors_are_streamed_in_chunks(dtype, oracle, monkeypatch):
     """host-pointer calls on large tensors stream A across PCIe in chunks of slabs of the slowest mode, kernels of one

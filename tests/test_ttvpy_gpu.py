@@ -74,3 +74,28 @@ def test_other_dtypes_and_device_chain():
     assert got.is_cuda and np.array_equal(got.cpu().numpy(), want)
     Ai = A.astype(np.int32)
     assert np.array_equal(tp.ttv(3, Ai, bs[1].astype(np.int32)), np.einsum("ijkl,k->ijl", Ai, bs[1].astype(np.int32)))
+
+
+def test_captured_chain_replays_on_new_data():
+    """ttvpy.CapturedTtvs: the chain recorded into a CUDA graph gives what ttvs gives, also after A and the vectors were
+    refilled in place (every q, every order, two element types)"""
+    import torch
+    from ttv_b200 import ttvpy
+    rng = np.random.default_rng(5)
+    for dtype in (np.float64, np.float32):
+        shape = (6, 9, 4, 7)
+        A = torch.from_numpy(rng.integers(-4, 5, shape).astype(dtype)).cuda()
+        for q in range(1, 5):
+            bs = [torch.from_numpy(rng.integers(-4, 5, shape[r]).astype(dtype)).cuda() for r in range(4) if r != q - 1]
+            for order in ("optimal", "backward", "forward"):
+                plan = ttvpy.CapturedTtvs(q, A, bs, order)
+                for _ in range(2):
+                    A.copy_(torch.from_numpy(rng.integers(-4, 5, shape).astype(dtype)))
+                    for bj in bs:
+                        bj.copy_(torch.from_numpy(rng.integers(-4, 5, bj.shape[0]).astype(dtype)))
+                    got = plan.replay()
+                    torch.cuda.synchronize()
+                    letters = "abcd"
+                    want = np.einsum(letters + "," + ",".join(letters[r] for r in range(4) if r != q - 1) + "->" + letters[q - 1],
+                                     A.cpu().numpy(), *[bj.cpu().numpy() for bj in bs])
+                    assert np.array_equal(got.cpu().numpy(), want), (dtype, q, order)

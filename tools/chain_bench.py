@@ -87,6 +87,19 @@ def main():
                 t0 = time.perf_counter(); got = ttvpy.ttvs(q, A_host, vec_host, order); ms_host = (time.perf_counter() - t0) * 1e3
                 rec = {"shape": shape, "q": q, "order": order, "chain_bytes": byt, "ms_device": ms_dev, "gbs_device": byt / ms_dev / 1e6,
                        "ms_host": ms_host, "gbs_host": byt / ms_host / 1e6}
+                # the same chain captured into a CUDA graph (ttvpy.CapturedTtvs): one launch per replay
+                plan = ttvpy.CapturedTtvs(q, A_dev, vec_dev, order)
+                plan.replay(); torch.cuda.synchronize()
+                ts = []
+                for _ in range(max(args.reps, 10)):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); plan.replay(); e1.record()
+                    torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                ms_graph = sorted(ts)[len(ts) // 2]
+                rec.update(ms_graph=ms_graph, gbs_graph=byt / ms_graph / 1e6,
+                           graph_matches=bool(torch.equal(plan.result, ttvpy.ttvs(q, A_dev, vec_dev, order))))
+                del plan
                 if ref is not None:
                     ref.ttvs(q, A_host, vec_host, order)                         # warm-up (thread pool, page faults)
                     t0 = time.perf_counter(); want = ref.ttvs(q, A_host, vec_host, order); ms_ref = (time.perf_counter() - t0) * 1e3

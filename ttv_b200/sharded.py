@@ -26,6 +26,43 @@ from dataclasses import dataclass
 from typing import Callable, Sequence
 
 
+def gpu_numa_cpus(device_index: int):
+    """CPUs of the NUMA node the GPU's PCIe root port hangs off (sysfs local_cpulist of the device), or None when the
+    platform does not say (single node, virtualised PCI topology)."""
+    import torch
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            text = f.read().strip()
+    except (OSError, AttributeError):
+        return None
+    cpus = set()
+    for part in text.split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus or None
+
+
+def bind_host_to_gpu(device_index: int) -> bool:
+    """Pins the calling process to the CPUs next to its GPU, so that the pinned staging buffers it allocates afterwards
+    (first touch) live in the memory of that socket and the H2D / D2H copies of its slab do not cross the socket
+    interconnect.  With one process per GPU on a two-socket 8-GPU box every rank otherwise allocates wherever the
+    scheduler happened to start it.  Returns False when nothing was changed."""
+    import os
+    cpus = gpu_numa_cpus(device_index)
+    if not cpus or not hasattr(os, "sched_setaffinity"):
+        return False
+    allowed = os.sched_getaffinity(0)
+    want = cpus & allowed
+    if not want or want == allowed:
+        return False
+    os.sched_setaffinity(0, want)
+    return True
+
+
 @dataclass(frozen=True)
 class Shard:
     """what one rank owns of the global problem"""

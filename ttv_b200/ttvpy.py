@@ -18,7 +18,7 @@ import numpy as np
 
 from . import api
 
-__all__ = ["ttv", "ttvs", "chain_plan"]
+__all__ = ["ttv", "ttvs", "chain_plan", "CapturedTtvs"]
 
 
 def _as_c_array(x):
@@ -120,3 +120,60 @@ def ttvs(q: int, A, bs, order: str = "optimal"):
     for mode, j in steps:
         cur = api.ttv(mode, cur, vecs[j]).contiguous()      # output of a last-order tensor is last-order: no copy
     return cur if on_device else cur.cpu().numpy()
+
+
+class CapturedTtvs:
+    """The p-1 launches of ttvs(q, A, bs, order) on DEVICE tensors, captured once into a CUDA graph.
+
+    On small tensors the chain is launch-bound: every product costs tens of microseconds of host time for a kernel
+    that runs a few microseconds.  The asynchronous device-pointer path of the C-ABI only enqueues work on the caller's
+    stream, so the whole chain can be recorded once and replayed with ONE launch.  The graph is bound to the storage of
+    A and of the vectors: refill them in place, call replay(), read `result` (a device tensor owned by this object).
+
+        plan = ttvpy.CapturedTtvs(q, A, bs)        # A: contiguous torch CUDA tensor, bs: p-1 CUDA vectors
+        A.copy_(new_values); plan.replay(); y = plan.result
+    """
+
+    def __init__(self, q: int, A, bs, order: str = "optimal"):
+        import torch
+        if order not in ("optimal", "backward", "forward"):
+            raise ValueError("Error calling ttvpy::ttvs: multiplication order should be either 'optimal', 'backward' or 'forward'.")
+        if not (api._is_torch(A) and A.is_cuda and A.is_contiguous()):
+            raise ValueError("CapturedTtvs needs a contiguous torch CUDA tensor (the graph is bound to its storage).")
+        p = A.dim()
+        if p < 2:
+            raise ValueError("Error calling ttvpy::ttvs: input tensor order should be greater than one for a captured chain.")
+        if q == 0 or q > p:
+            raise ValueError("Error calling ttvpy::ttvs: contraction mode should be greater than zero or less than or equal to p.")
+        if len(bs) != p - 1:
+            raise ValueError("Error calling ttvpy::ttvs: number of input vectors is not equal to the tensor order - 1.")
+        shape = [int(x) for x in A.shape]
+        want = [shape[r - 1] for r in range(1, p + 1) if r != q]
+        if [int(bj.shape[0]) for bj in bs] != want or any(bj.dim() != 1 for bj in bs):
+            raise ValueError("Error calling ttvpy::ttvs: vector dimension is not compatible with the dimension of a tensor mode.")
+        self.A, self.bs = A, [bj.contiguous() for bj in bs]
+        self._steps = []                                   # (mode, input view, vector, flat output)
+        cur, cur_shape = A, shape
+        for mode, j in chain_plan(q, shape, order):
+            out_shape = cur_shape[: mode - 1] + cur_shape[mode:]
+            flat = torch.empty(int(np.prod(out_shape, dtype=object)), dtype=A.dtype, device=A.device)
+            self._steps.append((mode, cur, self.bs[j], flat))
+            cur, cur_shape = flat.view(*out_shape), out_shape   # a last-order tensor stays last-order: no copy
+        self.result = cur
+        self._stream = torch.cuda.Stream(A.device)
+        self._stream.wait_stream(torch.cuda.current_stream(A.device))
+        with torch.cuda.stream(self._stream):
+            self._enqueue()                                # warm-up outside the capture: sizes workspaces
+        self._stream.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph, stream=self._stream):
+            self._enqueue()
+
+    def _enqueue(self):
+        for mode, src, vec, flat in self._steps:
+            api.ttv(mode, src, vec, out=flat, flags=api.FLAG_ASYNC, stream=self._stream)
+
+    def replay(self):
+        """recomputes `result` from the current contents of A and the vectors; ordered on the current stream"""
+        self._graph.replay()
+        return self.result
