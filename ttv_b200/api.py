@@ -130,35 +130,57 @@ def is_valid_strides(pi, w) -> bool:
     return bool(r)
 
 
-def generate_strides(n, pi) -> list[int]:
+# The tuple helpers are pure functions of small integer tuples and sit on the path of every call of the tensor-level
+# interface, so their results are cached (a failing call raises every time: lru_cache does not cache exceptions).
+@functools.lru_cache(maxsize=8192)
+def _strides_cached(n: tuple, pi: tuple) -> tuple:
     a1, p1 = _tuple(n); a2, p2 = _tuple(pi)
     w = np.zeros(max(len(n), 1), np.uint64)
     if len(n) != len(pi) or _lib.load().ttv_b200_compute_strides(p1, p2, len(n), w.ctypes.data_as(_lib.u64p)):
         raise TTVError(14, "Error in tlib::detail::compute_strides(): input shape or layout is not valid.")
-    return [int(x) for x in w[: len(n)]]
+    return tuple(int(x) for x in w[: len(n)])
 
 
-def generate_output_shape(na, q) -> list[int]:
+def generate_strides(n, pi) -> list[int]:
+    return list(_strides_cached(tuple(int(x) for x in n), tuple(int(x) for x in pi)))
+
+
+@functools.lru_cache(maxsize=8192)
+def _output_shape_cached(na: tuple, q: int) -> tuple:
     a1, p1 = _tuple(na)
     nc = np.zeros(max(len(na), 1), np.uint64)
     if _lib.load().ttv_b200_output_shape(p1, len(na), q, nc.ctypes.data_as(_lib.u64p)):
         raise TTVError(14, "Error in tlib::detail::generate_output_shape(): input shape or contraction mode is not valid.")
-    return [int(x) for x in nc[: len(na) - 1]]
+    return tuple(int(x) for x in nc[: len(na) - 1])
 
 
-def generate_output_layout(pia, q) -> list[int]:
+def generate_output_shape(na, q) -> list[int]:
+    return list(_output_shape_cached(tuple(int(x) for x in na), int(q)))
+
+
+@functools.lru_cache(maxsize=8192)
+def _output_layout_cached(pia: tuple, q: int) -> tuple:
     a1, p1 = _tuple(pia)
     pic = np.zeros(max(len(pia), 1), np.uint64)
     if _lib.load().ttv_b200_output_layout(p1, len(pia), q, pic.ctypes.data_as(_lib.u64p)):
         raise TTVError(16, "Error in tlib::detail::generate_output_layout(): input layout or contraction mode is not valid.")
-    return [int(x) for x in pic[: len(pia) - 1]]
+    return tuple(int(x) for x in pic[: len(pia) - 1])
 
 
-def generate_k_order_layout(p, k) -> list[int]:
+def generate_output_layout(pia, q) -> list[int]:
+    return list(_output_layout_cached(tuple(int(x) for x in pia), int(q)))
+
+
+@functools.lru_cache(maxsize=1024)
+def _k_order_cached(p: int, k: int) -> tuple:
     pi = np.zeros(max(p, 1), np.uint64)
     if _lib.load().ttv_b200_k_order_layout(p, k, pi.ctypes.data_as(_lib.u64p)):
         raise TTVError(16, "Error in tlib::detail::compute_k_order: range provided by begin and end not correct!")
-    return [int(x) for x in pi[:p]]
+    return tuple(int(x) for x in pi[:p])
+
+
+def generate_k_order_layout(p, k) -> list[int]:
+    return list(_k_order_cached(int(p), int(k)))
 
 
 # ---- the low-level interface -----------------------------------------------------------------------------------------
@@ -303,20 +325,28 @@ def _layout_of(x, layout):
     wrapped_ttv.cpp:44-45), an F-contiguous one a first-order tensor; any other array with positive strides that do not
     overlap is a tensor whose layout is the order of its strides, possibly padded (slices, transposes): it is read IN
     PLACE through wa with TTV_B200_FLAG_HONOR_STRIDES.  Returns None when the array has to be copied first."""
-    p = x.ndim
-    shape = [int(v) for v in x.shape]
+    shape = tuple(int(v) for v in x.shape)
     if layout is not None:
-        layout = [int(v) for v in layout]
-        if len(layout) != p:
+        layout = tuple(int(v) for v in layout)
+        if len(layout) != len(shape):
             raise TTVError(16, "Error in tlib::tensor: shape vector and layout vector must have the same length.")
-        return layout, generate_strides(shape, layout), False
+        return list(layout), generate_strides(shape, layout), False
     c_contig = x.is_contiguous() if _is_torch(x) else x.flags.c_contiguous
+    st = None if c_contig else _element_strides(x)
+    if not c_contig and st is None:
+        return None
+    desc = _layout_core(shape, bool(c_contig), None if st is None else tuple(st))
+    return None if desc is None else (list(desc[0]), list(desc[1]), desc[2])
+
+
+@functools.lru_cache(maxsize=8192)
+def _layout_core(shape: tuple, c_contig: bool, st):
+    p = len(shape)
+    shape = list(shape)
     if c_contig:
         pia = generate_k_order_layout(p, 0)
-        return pia, generate_strides(shape, pia), False
-    st = _element_strides(x)
-    if st is None:
-        return None
+        return tuple(pia), tuple(generate_strides(shape, pia)), False
+    st = list(st)
     # layout = modes by ascending stride (extent-1 modes last: their stride is meaningless)
     order = sorted(range(p), key=lambda m: (shape[m] == 1, st[m], m))
     need = 1
@@ -333,7 +363,7 @@ def _layout_of(x, layout):
             wa[m] = top
         top = max(top, wa[m] * shape[m])
     packed = wa == generate_strides(shape, pia) or all(shape[m] == 1 or wa[m] == w for m, w in enumerate(generate_strides(shape, pia)))
-    return pia, wa, not packed
+    return tuple(pia), tuple(wa), not packed
 
 
 def ttv(q: int, A, b, *, layout: Sequence[int] | None = None, out=None, **opt_kwargs):
