@@ -253,7 +253,7 @@ def run_own_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- smoke check of one product against the oracle on sampled fibers (the checker, not the thing measured) ----
+    # ---- self-check of every product on sampled fibers against a host long-double dot (not the thing measured) ----
     step()
     torch.cuda.synchronize()
     verify_sample(torch, {q: live[q][0] for q in live}, {q: live[q][1] for q in live}, na_global, bs, rank, world)
@@ -372,10 +372,20 @@ def local_product(ttv_b200, q, a, shard, pia, b, c):
                           ttv_b200.generate_strides(nc, pic), pic, flags=2)
 
 
+def synth_f32(seed: int, idx):
+    """the synthetic generator of the fill kernel (csrc/numeric.cuh: splitmix64 of seed ^ j, top 53 bits mapped to
+    [-1, 1)), restated in numpy for the sampled self-check below -- no code under oracle/ runs on this arm outside the
+    cpu_baseline leg"""
+    with np.errstate(over="ignore"):
+        z = (np.asarray(idx, dtype=np.uint64) ^ np.uint64(seed)) + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return ((z >> np.uint64(11)).astype(np.float64) * (2.0 / 9007199254740992.0) - 1.0).astype(np.float32)
+
+
 def verify_sample(torch, cs, shards, na_global, bs, rank, world):
-    """64 sampled outputs per product against a host long-double dot on regenerated data (oracle generator)"""
-    from oracle.oracle import Oracle
-    oracle = Oracle()
+    """64 sampled outputs per product against a host long-double dot on regenerated data"""
     rng = np.random.default_rng(1234 + rank)
     for q in range(1, ORDER + 1):
         sh = shards[q]
@@ -389,7 +399,7 @@ def verify_sample(torch, cs, shards, na_global, bs, rank, world):
             jg = int(j) + sh.c_offset                       # index into the global C
             o, i = divmod(jg, inner)
             idx = (o * nq + np.arange(nq)) * inner + i      # global element indices of the fiber
-            fiber = np.array([oracle.fill(DTYPE, 1, SEED_A, first=int(e))[0] for e in idx], dtype=np.longdouble)
+            fiber = synth_f32(SEED_A, idx).astype(np.longdouble)
             want = float(np.dot(fiber, bh))
             tol = 2 * nq * (np.finfo(np.float32).eps / 2) * float(np.dot(np.abs(fiber), np.abs(bh))) + 1e-30
             got = float(c[int(j)].item())

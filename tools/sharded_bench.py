@@ -28,6 +28,18 @@ from ttv_b200.sharded import make_shard, ttv_sharded  # noqa: E402
 SEED_A, SEED_B = 0x77170001, 0x77170002
 
 
+
+def synth_f64(seed: int, idx):
+    """the synthetic generator of the fill kernel (csrc/numeric.cuh: splitmix64 of seed ^ j, top 53 bits mapped to
+    [-1, 1)) restated in numpy for the sampled self-checks"""
+    with np.errstate(over="ignore"):
+        z = (np.asarray(idx, dtype=np.uint64) ^ np.uint64(seed)) + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) * (2.0 / 9007199254740992.0) - 1.0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--extent", type=int, default=2048)
@@ -74,8 +86,6 @@ def main():
             ms = float(t.item())
         # sampled check (rank 0 holds the reduced C for q = 3; every rank checks its own slab otherwise)
         if not (shq.kind == "nq" and rank != 0):
-            from oracle.oracle import Oracle
-            oracle = Oracle()
             rng = np.random.default_rng(7 + rank)
             inner = n ** (q - 1)
             bh = b.cpu().numpy().astype(np.longdouble)
@@ -83,7 +93,7 @@ def main():
                 jg = int(j) + shq.c_offset
                 o, i = divmod(jg, inner)
                 idx = (o * n + np.arange(n)) * inner + i
-                fiber = np.array([oracle.fill("f64", 1, SEED_A, first=int(e))[0] for e in idx], dtype=np.longdouble)
+                fiber = synth_f64(SEED_A, idx).astype(np.longdouble)
                 want = float(np.dot(fiber, bh))
                 tol = 2 * n * (np.finfo(np.float64).eps / 2) * float(np.dot(np.abs(fiber), np.abs(bh))) + 1e-300
                 got = float(c[int(j)].item())
@@ -118,8 +128,6 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         # every rank checks samples of ITS block of C
-        from oracle.oracle import Oracle
-        oracle = Oracle()
         rng = np.random.default_rng(17 + rank)
         c, shq = out["c"], out["sh"]
         inner = n * n
@@ -127,7 +135,7 @@ def main():
         for j in rng.integers(0, shq.c_count, 8):
             i = int(j) + shq.c_offset
             idx = np.arange(n) * inner + i
-            fiber = np.array([oracle.fill("f64", 1, SEED_A, first=int(e))[0] for e in idx], dtype=np.longdouble)
+            fiber = synth_f64(SEED_A, idx).astype(np.longdouble)
             want = float(np.dot(fiber, bh))
             tol = 2 * n * (np.finfo(np.float64).eps / 2) * float(np.dot(np.abs(fiber), np.abs(bh))) + 1e-300
             assert abs(float(c[int(j)].item()) - want) <= tol, ("fused", i)
