@@ -249,7 +249,8 @@ def test_chooser_only_picks_instantiated_kernels():
             wide = pl["vec"] * size[dt] >= 16
             key = (pl["nu"], pl["ku"])
             if pl["kernel"] == 3:       # STREAM: slabs through shared memory, one kernel shape
-                assert nq * inner * size[dt] <= 8192 and pl["smem_bytes"] <= 227 * 1024 and pl["ksplit"] == 1
+                assert nq * inner * size[dt] <= 75 * 1024 and nq * size[dt] <= 8192 and pl["smem_bytes"] <= 227 * 1024 and pl["ksplit"] == 1
+                assert pl["ctas"] <= 148 * (2 if pl["smem_bytes"] + 1024 <= 227 * 1024 // 2 else 1)      # what an SM can hold
                 continue
             if pl["kernel"] == 5:       # DOTF: short aligned fibers as one flat stream
                 vec = 16 // size[dt]
@@ -259,7 +260,7 @@ def test_chooser_only_picks_instantiated_kernels():
             if pl["kernel"] == 4:       # COLX: odd wide rows, 16-byte loads at any phase
                 assert (key in {(1, 8), (2, 4), (4, 2)} and wide or key == (8, 2) and size[dt] == 4) and size[dt] < 16, (dt, outer, nq, inner, pl)
                 assert inner * size[dt] >= 2048 and inner % (16 // size[dt]) != 0
-                if -(-nq // (16 // size[dt])) < 16:      # short contraction: warp-autonomous form, no shared memory
+                if -(-nq // (16 // size[dt])) < 48:      # short contraction: warp-autonomous form, no shared memory
                     assert (pl["tx"], pl["ty"], pl["smem_bytes"]) == (32, 1, 0) and pl["ku"] % pl["vec"] == 0 and pl["vec"] == 2
                 else:
                     assert pl["ty"] == 16 // size[dt] and pl["tx"] * pl["ty"] <= 256 and pl["smem_bytes"] <= 100 * 1024

@@ -337,6 +337,9 @@ def test_stream_kernel_small_slabs(dtype, oracle):
              ((1, 7, 13), (1, 2, 3), 2), ((40, 5, 6000), (1, 2, 3), 1),
              # fibers of even length are walked skewed (bank conflicts otherwise)
              ((84, 3001), (1, 2), 1), ((4, 70001), (1, 2), 1), ((24, 5003), (1, 2), 1), ((128, 1001), (1, 2), 1), ((2, 3, 4099), (1, 2, 3), 1)]
+    # slabs that get a stage of their own (36 .. 75 KB): odd rows, ragged last chunk, a slab that ends the tensor unaligned
+    cases += [((529, 23, 9), (1, 2, 3), 2), ((73, 73, 11), (1, 2, 3), 2), ((441, 21, 5), (1, 2, 3), 2), ((2, 4500, 7), (1, 2, 3), 1),
+              ((1201, 9, 3), (1, 2, 3), 2)]
     for na, pia, q in cases:
         a, b = random_case(rng, na, q, dtype)
         want = oracle.ttv(q, a, na, pia, b)
@@ -344,8 +347,10 @@ def test_stream_kernel_small_slabs(dtype, oracle):
                 np.dtype(np.complex128): "c128", np.dtype(np.int32): "i32", np.dtype(np.int64): "i64"}[np.dtype(dtype)]
         try:
             pl = ttv_b200.plan(q, na, pia, dtype=name, kernel="stream")
-        except ttv_b200.TTVError as exc:          # slab larger than a stage for this element size: not eligible
-            assert exc.status == 32 and int(np.prod(na)) // na[-1] * np.dtype(dtype).itemsize > 8192
+        except ttv_b200.TTVError as exc:          # slab larger than three stages of shared memory hold, or b too long
+            k = list(pia).index(q)
+            slab = int(np.prod([na[m - 1] for m in pia[: k + 1]])) * np.dtype(dtype).itemsize
+            assert exc.status == 32 and (slab > 74 * 1024 or na[q - 1] * np.dtype(dtype).itemsize > 8192), (na, pia, q, slab)
             continue
         assert pl["kernel"] == 3
         c = run_lowlevel(q, a, na, pia, b, kernel="stream")

@@ -47,14 +47,17 @@ def configs(which):
     if which in ("sym", "all"):
         out += [("sym2", "f32", [65536, 65536], first(2), q) for q in (1, 2)]
         out += [("sym3", "f32", [1625] * 3, first(3), q) for q in (1, 2, 3)]
-        out += [("sym5", "f32", [84] * 5, first(5), q) for q in (1, 2, 3, 5)]
-        out += [("sym6", "f32", [40] * 6, first(6), q) for q in (1, 2, 4, 6)]
-        out += [("sym7", "f32", [23] * 7, first(7), q) for q in (1, 2, 4, 7)]
+        out += [("sym5", "f32", [84] * 5, first(5), q) for q in range(1, 6)]
+        out += [("sym6", "f32", [40] * 6, first(6), q) for q in range(1, 7)]
+        out += [("sym7", "f32", [23] * 7, first(7), q) for q in range(1, 8)]
     if which in ("fp64", "all"):
         out += [("cfg5/8", "f64", [2048, 2048, 256], first(3), q) for q in (1, 2, 3)]
+        out += [("sym2d", "f64", [46340] * 2, first(2), q) for q in (1, 2)]
         out += [("sym3d", "f64", [1290] * 3, first(3), q) for q in (1, 2, 3)]
-        out += [("sym4d", "f64", [215] * 4, first(4), q) for q in (1, 2, 4)]
-        out += [("sym7d", "f64", [21] * 7, first(7), q) for q in (1, 2, 7)]
+        out += [("sym4d", "f64", [215] * 4, first(4), q) for q in range(1, 5)]
+        out += [("sym5d", "f64", [73] * 5, first(5), q) for q in range(1, 6)]
+        out += [("sym6d", "f64", [36] * 6, first(6), q) for q in range(1, 7)]
+        out += [("sym7d", "f64", [21] * 7, first(7), q) for q in range(1, 8)]
     if which in ("asym", "all"):
         for dt in ("f32", "i32"):
             out += [("asym5", dt, [4, 1 << 18, 2, 2, 256], first(5), q) for q in (1, 2, 3, 4, 5)]

@@ -313,7 +313,16 @@ cudaError_t TTVB_CAT(reduce_dtype_, TTVB_DTYPE)(const void* ws, void* c, uint64_
 cudaError_t TTVB_CAT(stream_dtype_, TTVB_DTYPE)(const StreamParams& S, const Launch& l, cudaStream_t stream)
 {
   // fibers (inner == 1) of even length are walked skewed: bank conflicts otherwise (stream_fibers_skewed)
-  auto kern = (S.inner == 1 && (S.nq & 1) == 0) ? ttv_stream_kernel<elem_t, 3, 4, true> : ttv_stream_kernel<elem_t, 3, 4, false>;
+  const bool skew = S.inner == 1 && (S.nq & 1) == 0;
+  auto kern = skew ? ttv_stream_kernel<elem_t, 3, 4, true> : ttv_stream_kernel<elem_t, 3, 4, false>;
+  if (l.threads > 256) {                     // a big slab alone in its stage: one CTA of up to 1024 threads per SM
+    if (skew || l.threads > 1024) return cudaErrorInvalidValue;
+    kern = l.stages == 3 ? ttv_stream_kernel<elem_t, 3, 1, false, 1024> : l.stages == 4 ? ttv_stream_kernel<elem_t, 4, 1, false, 1024>
+         : ttv_stream_kernel<elem_t, 5, 1, false, 1024>;
+    if (l.stages < 3 || l.stages > 5) return cudaErrorInvalidValue;
+  } else if (l.stages == 4) kern = skew ? ttv_stream_kernel<elem_t, 4, 4, true> : ttv_stream_kernel<elem_t, 4, 4, false>;
+  else if (l.stages == 5) kern = skew ? ttv_stream_kernel<elem_t, 5, 4, true> : ttv_stream_kernel<elem_t, 5, 4, false>;
+  else if (l.stages != 3) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes);
   if (e != cudaSuccess) return e;
   kern<<<(unsigned)l.ctas, l.threads, l.smem_bytes, stream>>>(S);

@@ -284,11 +284,12 @@ static int choose_colx(uint64_t s, const View& v, const ttv_b200_opts* opts, uin
   l.vec = (int)V; l.ty = (uint32_t)TY; l.to = 1; l.udir = 0;
   l.stream = (uint32_t)env_int("TTV_B200_STREAM", 1);
 
-  // Short contractions (fewer than 16 rows per phase lane): the per-tile prologue / shared-memory epilogue of the CTA
-  // form dominates (measured 23^7 q=4: 4.0 TB/s against 6.4 TB/s), so the warp-autonomous form runs them; long
-  // contractions are faster in the CTA form (1625^3 q=2: 7.3 against 6.8 TB/s), which keeps 3 CTAs per SM.
+  // Short contractions (fewer than 48 rows per phase lane): the per-tile prologue / shared-memory epilogue of the CTA
+  // form dominates (measured 23^7 q=4: 4.0 TB/s against 6.4 TB/s; 73^5 fp64 q=3,5, 37 rows per lane: 6.0 against 6.7), so
+  // the warp-autonomous form runs them; long contractions are faster in the CTA form (1625^3 q=2: 7.3 against 6.8 TB/s;
+  // 215^4 fp64, 108 rows per lane: 6.9), which keeps 3 CTAs per SM.
   const int warp_mode = env_int("TTV_B200_COLX_WARP", -1);      // -1 auto, 0 CTA form, 1 COLW (phase classes), 2 COLR (realigned)
-  if (warp_mode == 1 || warp_mode == 2 || (warp_mode == -1 && ceil_div(v.nq, TY) < 16)) {
+  if (warp_mode == 1 || warp_mode == 2 || (warp_mode == -1 && ceil_div(v.nq, TY) < (uint64_t)env_int("TTV_B200_COLX_WARP_ROWS", 48))) {
     // a warp owns 31*V columns per unit and all rows of its n_q partition
     // Measured (23^7 q=4,7 fp32; 21^7 q=7 fp64): the realigned form (80 registers, 3 CTAs per SM, whole-sector stores)
     // is no faster than the phase-class form (115 registers, 2 CTAs): 6.48-6.53 against 6.46-6.55 TB/s in fp32, 6.33
@@ -386,17 +387,30 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
   // b are small, A is 16-byte aligned and n_q is not split.
   {
     const uint64_t slab_bytes = v.nq * v.inner * s;
-    const bool eligible = slab_bytes <= 8192 && v.nq * s <= 8192 && (align_a % 16) == 0 && (!opts || opts->ksplit <= 1) &&
-                          v.outer * v.nq * v.inner * s >= 16;
-    const uint64_t max_payload = (uint64_t)env_int("TTV_B200_STAGE_KB", 36) * 1024 - 128;
-    const bool fills_cta = (max_payload / std::max<uint64_t>(1, slab_bytes)) * v.inner >= 128;   // outputs per stage vs 256 threads
+    // Small slabs share a stage of up to 36 KB (2 CTAs x 3 stages per SM).  A slab of up to 75 KB gets a stage of its own
+    // (1 CTA of up to 1024 threads x 3 stages per SM, ~100-150 KB in flight): 23 x 529 floats (48.7 KB) run at 6.7-6.8
+    // TB/s this way, 4.9 with the warp form of COLX, whose units of 62 columns tile a row of 529 badly; 21 x 441 doubles
+    // (74 KB) 6.5 against 5.9.
+    const uint64_t small_payload = (uint64_t)env_int("TTV_B200_STAGE_KB", 36) * 1024 - 128;
+    const uint64_t big_slab_max = (uint64_t)env_int("TTV_B200_STREAM_SLAB_KB", 75) * 1024;
+    const bool big_slab = slab_bytes > small_payload;
+    const uint64_t big_stage = (slab_bytes + 32 + 127) / 128 * 128, b_bytes16 = (v.nq * s + 15) / 16 * 16;
+    const uint64_t big_smem = 3 * big_stage + b_bytes16 + 3 * 8;                        // at least three stages of one slab
+    const bool eligible = slab_bytes <= std::max<uint64_t>(8192, big_slab_max) && (!big_slab || big_smem <= 227 * 1024) &&
+                          v.nq * s <= 8192 && (align_a % 16) == 0 && (!opts || opts->ksplit <= 1) && v.outer * v.nq * v.inner * s >= 16;
+    const uint64_t max_payload = big_slab ? slab_bytes : small_payload;
+    // outputs per stage against the 256 threads of the CTA (measured: fibers of 73 doubles, 62 per stage: 6.4 TB/s
+    // against 5.5 with the peeled DOT kernel)
+    const bool fills_cta = (max_payload / std::max<uint64_t>(1, slab_bytes)) * v.inner >= (uint64_t)env_int("TTV_B200_STREAM_MIN_OUT", 48);
     const bool misaligned = (v.inner == 1 ? v.nq : v.inner) % vmax_of(s) != 0;      // the other kernels would fall back to narrow loads
     const int mode = env_int("TTV_B200_USE_STREAM", -1);                               // -1 auto, 0 never, 1 whenever eligible
     const bool pick = forced == TTV_B200_KERNEL_STREAM ? eligible
                     : forced != 0 ? false
                     : mode == 1 ? eligible
                     : mode == 0 ? false
-                    : (eligible && misaligned && fills_cta && v.outer >= sms * 64 && !(flags & TTV_B200_FLAG_NO_VEC) &&
+                    // (a big slab needs enough outputs for the thread-per-output mapping: 73 x 73 doubles, 73 outputs,
+                    // ran 5.7 TB/s against 6.6 with the column kernel)
+                    : (eligible && misaligned && fills_cta && (!big_slab || v.inner >= 256) && v.outer >= sms * 64 && !(flags & TTV_B200_FLAG_NO_VEC) &&
                        stream_conflict_degree(v.nq * v.inner, v.inner, s) <= 2);
     if (forced == TTV_B200_KERNEL_STREAM && !eligible) return TTV_B200_ERR_OPTS;
     if (pick) {
@@ -405,6 +419,9 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
       const uint64_t payload = max_payload;
       l.kernel = TTV_B200_KERNEL_STREAM;
       l.threads = (uint32_t)env_int("TTV_B200_STREAM_THREADS", 256);
+      // a big slab alone in its stage: as many threads as it has outputs (one round), up to 1024, fibers excepted
+      if (big_slab && v.inner > 256 && env_int("TTV_B200_STREAM_THREADS", 0) == 0)
+        l.threads = (uint32_t)std::min<uint64_t>(1024, ceil_div(v.inner, 128) * 128);
       l.vec = 1; l.tx = 1; l.ty = 1; l.to = 1; l.nu = 4; l.ku = 1; l.ksplit = 1; l.stream = 1;
       uint64_t S = std::max<uint64_t>(1, std::min<uint64_t>(payload / slab_bytes, v.outer));
       const uint64_t rounds = S * v.inner / l.threads;
@@ -413,9 +430,15 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
       l.chunks = ceil_div(v.outer, l.slabs_per_chunk);
       l.stage_bytes = (uint32_t)((l.slabs_per_chunk * slab_bytes + 32 + 127) / 128 * 128);
       l.tiles = l.chunks;
-      l.ctas = std::min<uint64_t>(l.chunks, sms * (uint64_t)env_int("TTV_B200_STREAM_CTAS", 2));
+      // a big slab is alone in its stage and the CTA alone on its SM; more than three stages (TTV_B200_STREAM_STAGES, up
+      // to 5 when they fit) measured no better: 23 x 529 floats 6.80 TB/s with 3 stages, 6.66 with 4
+      l.stages = 3;
+      if (big_slab) l.stages = (uint32_t)std::max<uint64_t>(3, std::min<uint64_t>((uint64_t)env_int("TTV_B200_STREAM_STAGES", 3), (227 * 1024 - b_bytes16 - 64) / l.stage_bytes));
+      l.smem_bytes = (uint64_t)l.stages * l.stage_bytes + b_bytes16 + (uint64_t)l.stages * 8;
+      if (l.smem_bytes > 227 * 1024) return TTV_B200_ERR_OPTS;                          // (excluded by `eligible`)
+      const uint64_t per_sm = l.smem_bytes + 1024 <= (227 * 1024) / 2 ? 2 : 1;        // CTAs of this size an SM can hold
+      l.ctas = std::min<uint64_t>(l.chunks, sms * std::min<uint64_t>(per_sm, (uint64_t)env_int("TTV_B200_STREAM_CTAS", 2)));
       l.kchunk = v.nq; l.kb = (uint32_t)v.nq;
-      l.smem_bytes = 3ull * l.stage_bytes + ((v.nq * s + 15) / 16 * 16) + 3 * 8;
       l.workspace_bytes = 0;
       *out = l;
       return TTV_B200_OK;

@@ -60,6 +60,7 @@ struct Launch {
   // STREAM kernel only: slabs per shared-memory stage, bytes of one stage, number of chunks
   uint64_t slabs_per_chunk = 0, chunks = 0;
   uint32_t stage_bytes = 0;
+  uint32_t stages = 3;      // STREAM: shared-memory stages in the ring (3 small ones x 2 CTAs per SM, or 3..5 of one big slab each)
   // COLX kernel only: output columns owned by one tile
   uint64_t wcols = 0;
   uint32_t bdirect = 0;     // b read straight from global memory / L2 (lanes along n_q, b too long to stay resident)

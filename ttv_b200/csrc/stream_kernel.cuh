@@ -60,12 +60,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 } // namespace tma
 
-// UO outputs (u, u + step, ...) of one thread: acc_j = sum_k slab[s_j][k][i_j] * b[k], b[k] read once per k for all of them
-template<class T, int UO>
+// UO outputs (u, u + step, ...) of one thread: acc_j = sum_k slab[s_j][k][i_j] * b[k], b[k] read once per k for all of them.
+// KR partial sums per output (k, k+1, .. go round robin): with UO = 1 -- the stragglers of a chunk, or every output of
+// a slab that is alone in its stage and has few more outputs than the CTA has threads -- a single accumulator is one
+// dependent FMA chain of n_q shared-memory loads, which 8 warps per SM cannot hide (23 x 529 floats: 4.5 TB/s).
+template<class T, int UO, int KR = 1>
 __device__ __forceinline__ void stream_outputs(const T* slab0, const T* sb, T* cbase, uint32_t u0, uint32_t step, uint32_t nq,
                                                uint32_t inner, uint32_t M, uint32_t accumulate)
 {
-  T acc[UO];
+  static_assert(KR == 1 || KR == 2 || KR == 4, "partial sums per output");
+  T acc[UO][KR];
   const T* base[UO];
 #pragma unroll
   for (int j = 0; j < UO; ++j) {
@@ -73,7 +77,8 @@ __device__ __forceinline__ void stream_outputs(const T* slab0, const T* sb, T* c
     const uint32_t s = inner == 1 ? u : u / inner;
     const uint32_t i = inner == 1 ? 0 : u - s * inner;
     base[j] = slab0 + (size_t)s * M + i;
-    acc[j] = Num<T>::zero();
+#pragma unroll
+    for (int r = 0; r < KR; ++r) acc[j][r] = Num<T>::zero();
   }
   uint32_t k = 0;
   for (; k + 4 <= nq; k += 4) {                                    // four k per step: b comes in as one vector when it can
@@ -83,17 +88,20 @@ __device__ __forceinline__ void stream_outputs(const T* slab0, const T* sb, T* c
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int j = 0; j < UO; ++j) acc[j] = Num<T>::madd(base[j][(size_t)(k + r) * inner], bk[r], acc[j]);
+      for (int j = 0; j < UO; ++j) acc[j][r % KR] = Num<T>::madd(base[j][(size_t)(k + r) * inner], bk[r], acc[j][r % KR]);
   }
   for (; k < nq; ++k) {
     const T bk = sb[k];
 #pragma unroll
-    for (int j = 0; j < UO; ++j) acc[j] = Num<T>::madd(base[j][(size_t)k * inner], bk, acc[j]);
+    for (int j = 0; j < UO; ++j) acc[j][0] = Num<T>::madd(base[j][(size_t)k * inner], bk, acc[j][0]);
   }
 #pragma unroll
   for (int j = 0; j < UO; ++j) {
+    T sum = acc[j][0];
+#pragma unroll
+    for (int r = 1; r < KR; ++r) sum = Num<T>::add(sum, acc[j][r]);
     T* out = cbase + u0 + j * step;
-    *out = accumulate ? Num<T>::add(*out, acc[j]) : acc[j];
+    *out = accumulate ? Num<T>::add(*out, sum) : sum;
   }
 }
 
@@ -129,8 +137,11 @@ __device__ __forceinline__ void stream_fibers_skewed(const T* slab0, const T* sb
   }
 }
 
-template<class T, int NS, int UO, bool SKEW = false>
-__global__ void __launch_bounds__(256, 2)
+// MAXT: 256 threads, 2 CTAs per SM for the shared stages of small slabs; up to 1024 threads, 1 CTA per SM when a big
+// slab is alone in its stage (the 8 warps of a 256-thread CTA cannot hide the shared-memory latency of 500+ outputs:
+// 23 x 529 floats ran at 4.5 TB/s with 30 % of the issue slots busy and 6.5 cycles between two instructions of a warp)
+template<class T, int NS, int UO, bool SKEW = false, int MAXT = 256>
+__global__ void __launch_bounds__(MAXT, MAXT == 256 ? 2 : 1)
 ttv_stream_kernel(const StreamParams P)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];   // the runtime places dynamic shared memory at a 1024-byte aligned offset when it is the only shared allocation
@@ -210,9 +221,9 @@ ttv_stream_kernel(const StreamParams P)
     } else {
       for (uint32_t u0 = tid; u0 < outs; u0 += UO * blockDim.x) {
         // outputs u0, u0 + NT, ... of this thread; a full set of UO shares every b[k], stragglers go one by one
-        if (u0 + (UO - 1) * blockDim.x < outs) stream_outputs<T, UO>(slab0, sb, C + o0 * inner, u0, blockDim.x, nq, inner, M, P.accumulate);
+        if (u0 + (UO - 1) * blockDim.x < outs) stream_outputs<T, UO, (UO == 1 ? 4 : 1)>(slab0, sb, C + o0 * inner, u0, blockDim.x, nq, inner, M, P.accumulate);
         else
-          for (uint32_t u = u0; u < outs; u += blockDim.x) stream_outputs<T, 1>(slab0, sb, C + o0 * inner, u, blockDim.x, nq, inner, M, P.accumulate);
+          for (uint32_t u = u0; u < outs; u += blockDim.x) stream_outputs<T, 1, (MAXT > 256 ? 4 : 1)>(slab0, sb, C + o0 * inner, u, blockDim.x, nq, inner, M, P.accumulate);
       }
     }
 
