@@ -37,6 +37,15 @@ def configs(which):
     if which == "dotk":      # fibers of 1 .. 16 KB at 4 GiB and at 512 MiB: lanes per fiber / CTA size of the DOT kernel
         out += [("dotk%d" % m, "f32", [m, (1 << 30) // m], first(2), 1) for m in (256, 512, 1024, 2048, 4096)]
         out += [("dots%d" % m, "f32", [m, (1 << 27) // m], first(2), 1) for m in (256, 512, 1024, 2048, 4096)]
+    if which == "cplxall":   # BASELINE configs[3] in full: order 4..6, complex<float> / complex<double>, last-order + 2 seeded random layouts, every q
+        for pp, ext in ((4, 128), (5, 48), (6, 25)):
+            lays = [("L", last(pp))]
+            for seed in (1, 2):
+                perm = [int(x) + 1 for x in np.random.default_rng(seed).permutation(pp)]
+                lays.append(("R%d" % seed, perm))
+            for dt in ("c64", "c128"):
+                for tag, pia in lays:
+                    out += [("cx%d%s" % (pp, tag), dt, [ext] * pp, pia, q) for q in range(1, pp + 1)]
     if which == "pad":       # slices of a packed 256^4 tensor, read in place through wa (TTV_B200_FLAG_HONOR_STRIDES)
         w4 = [1, 256, 256 ** 2, 256 ** 3]
         out += [("pad3", "f32", [256, 256, 250, 256], first(4), q, w4) for q in (1, 2, 3, 4)]      # A[:, :, :250, :]

@@ -460,7 +460,8 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
                     : forced != 0 ? false
                     : mode == 1 ? eligible
                     : mode == 0 ? false
-                    : (eligible && nvf <= (uint64_t)env_int("TTV_B200_DOTF_NV", 48) && v.outer >= sms * 64);
+                    // (16-byte elements: up to 128 per fiber -- 128 complex<double> run 6.95 TB/s here, 6.18 with lane groups)
+                    : (eligible && nvf <= (uint64_t)env_int("TTV_B200_DOTF_NV", s >= 16 ? 128 : 48) && v.outer >= sms * 64);
     if (pick) {
       l.kernel = TTV_B200_KERNEL_DOTF;
       l.threads = 256;
@@ -495,6 +496,15 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
 
   l.threads = (uint32_t)env_int("TTV_B200_THREADS", 256);
   if (l.threads < 32 || l.threads > 256 || (l.threads % 32)) return TTV_B200_ERR_OPTS;
+  // A row of one to three CTA-widths whose last width would be mostly empty (625 vector columns: 256 + 256 + 113) fits
+  // CTAs of 128 threads better (4 x 128 + 113): complex<double> [15625, 25, 625] 6.19 -> 6.54 TB/s.
+  if (env_int("TTV_B200_THREADS", 0) == 0 && v.inner > 1 && forced != TTV_B200_KERNEL_DOT) {
+    const uint64_t v0 = (flags & TTV_B200_FLAG_NO_VEC) ? 1 : vmax_of(s);
+    if (v.inner % v0 == 0) {
+      const uint64_t cv0 = v.inner / v0, u256 = ceil_div(cv0, 256), u128 = ceil_div(cv0, 128);
+      if (cv0 >= 256 && u256 <= 3 && cv0 * 100 < u256 * 256 * 85 && cv0 * 100 >= u128 * 128 * 95) l.threads = 128;
+    }
+  }
   const uint64_t NT = l.threads;
   const uint64_t vmax = (flags & TTV_B200_FLAG_NO_VEC) ? 1 : std::max<uint64_t>(1, 16 / s);
 
@@ -546,6 +556,8 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
       // a row is only a few CTA-widths long: the units of a thread must not outnumber the units of a row, or most of
       // its loads are predicated off (480 columns, 4 units of 256: measured [13200, 25, 480] c128 5.8 -> 6.7 TB/s with 2).
       // Spreading the row evenly over the units (2 x 240 instead of 256 + 224) measured no better, so tx stays the CTA.
+      // (Measured again on 625 columns of complex<double>, 3 x 209 instead of 256 + 256 + 113: 6.06 against 6.19 TB/s;
+      // CTAs of 128 threads do help there, see the top of this function.)
       const uint64_t U = ceil_div(cv, NT);
       l.tx = (uint32_t)(U <= 8 && env_int("TTV_B200_EVEN_UNITS", 0) ? ceil_div(cv, U) : NT);
       row_units = U <= 8 ? U : 0;
@@ -647,7 +659,9 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
   else if (dot && per >= 16)        ku = 4;
   else if (!dot && per >= 16) {                                                 // deepest batch that wastes <= 10 %
     ku = (loads > 8 && per < 64) ? 4 : loads;                                   // narrow loads: shallow, more units
-    while (ku > 2 && waste(ku) > 0.10) ku /= 2;
+    // (never below four: depth matters more than the predicated-off slots of the last batch -- 25 rows of
+    // complex<double>: ku = 2 / 4 / 8 waste 4 / 11 / 22 % and run 5.3 / 6.7 / 6.4 TB/s)
+    while (ku > 4 && waste(ku) > 0.10) ku /= 2;
   } else                            ku = least_waste(std::min<uint64_t>(loads, 8), false);
   const int ku_env = env_int("TTV_B200_KU", 0);
   if (ku_env > 0 && (uint64_t)ku_env <= loads && pow2_ceil((uint64_t)ku_env) == (uint64_t)ku_env && (ku_env > 1 || (dot && !l.peel))) ku = (uint64_t)ku_env;
