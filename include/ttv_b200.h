@@ -21,6 +21,11 @@
  *     the reference's non-BLAS column kernel (matrix_times_vector.h:124).
  *   - Argument checks, their order and their messages follow ttv.h:64-89 and tensor_times_vector.h:147-168.
  *   - The call is synchronous unless TTV_B200_FLAG_ASYNC is set together with device pointers.
+ *   - Threads: every entry point may be called from several host threads.  Device-pointer calls only share a small
+ *     table (looked up under a short lock, never held across a launch or a wait) and one split-n_q workspace per
+ *     (device, stream) -- as with any CUDA stream, one stream is fed by one thread at a time.  Host-pointer calls
+ *     share the staging buffers of their device and therefore run one at a time per device (they are PCIe-bound).
+ *     The reference is re-entrant apart from its process-global BLAS/OpenMP settings (tensor_times_vector.h:90-143).
  *   - There is no CPU fallback: without a usable CUDA device every compute entry returns TTV_B200_ERR_CUDA.
  *     ttv_b200_plan() is pure host code and needs no device.
  */
@@ -232,7 +237,7 @@ int         ttv_b200_version(void);
 int         ttv_b200_device_count(void);       /* 0 when no usable CUDA device */
 uint64_t    ttv_b200_launch_count(void);       /* kernels launched by this library in this process */
 int         ttv_b200_dtype_size(int dtype);
-void        ttv_b200_release(void);            /* frees cached workspaces / staging buffers */
+void        ttv_b200_release(void);            /* waits for queued work, frees workspaces / staging buffers / copy stream */
 
 #ifdef __cplusplus
 }

@@ -682,3 +682,57 @@ def test_fused_scatter_exchange_emulated_on_one_gpu(dtype, oracle):
         torch.cuda.synchronize()
         assert ttv_b200.launch_count() - before >= world + 1
         assert np.array_equal(got.cpu().numpy(), want), ((outer, nq, inner), world, dtype)
+
+
+def test_calls_from_several_host_threads(oracle, monkeypatch):
+    """the C-ABI is callable from several host threads at once (ctypes drops the GIL): host-pointer calls share the staging
+    buffers of their device and are serialised inside the library, device-pointer calls on their own streams share only
+    the per-(device, stream) split-n_q workspace table.  Every result must still be the oracle's."""
+    import threading
+    import torch
+    monkeypatch.setenv("TTV_B200_H2D_CHUNK_MB", "1")          # the larger cases take the chunk ring
+    rng = np.random.default_rng(71)
+    cases = []
+    for na, pia, dtype in [((64, 50, 203), (1, 2, 3), np.float32), ((33, 47, 21), (3, 1, 2), np.float64), ((3000, 211), (1, 2), np.int32),
+                           ((17, 9, 40, 23), (2, 1, 4, 3), np.complex64), ((211, 3000), (2, 1), np.int64), ((48, 40, 36), (1, 2, 3), np.float64)]:
+        for q in range(1, len(na) + 1):
+            a, b = random_case(rng, na, q, dtype)
+            cases.append((q, a, na, pia, b, oracle.ttv(q, a, na, pia, b)))
+    errors = []
+
+    def host_worker(tid):
+        try:
+            for rep in range(3):
+                for i in range(tid, len(cases), 2):
+                    q, a, na, pia, b, want = cases[i]
+                    if not np.array_equal(run_lowlevel(q, a, na, pia, b), want):
+                        errors.append(("host", tid, na, pia, q))
+        except Exception as e:                                # noqa: BLE001 - reported below
+            errors.append(("host", tid, repr(e)))
+
+    def device_worker(tid):
+        try:
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                for rep in range(3):
+                    for i in range(tid, len(cases), 2):
+                        q, a, na, pia, b, want = cases[i]
+                        ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+                        tc = torch.empty(want.size, dtype=ta.dtype, device="cuda")
+                        nc = ttv_b200.generate_output_shape(na, q); pic = ttv_b200.generate_output_layout(pia, q)
+                        ttv_b200.ttv_lowlevel(q, len(na), ta, na, ttv_b200.generate_strides(na, pia), pia, tb, [len(b)], tc, nc,
+                                              ttv_b200.generate_strides(nc, pic), pic, ksplit=2 + (rep + tid) % 3,
+                                              stream=stream.cuda_stream)
+                        stream.synchronize()
+                        if not np.array_equal(tc.cpu().numpy(), want):
+                            errors.append(("device", tid, na, pia, q))
+        except Exception as e:                                # noqa: BLE001
+            errors.append(("device", tid, repr(e)))
+
+    threads = [threading.Thread(target=host_worker, args=(t,)) for t in range(2)] + \
+              [threading.Thread(target=device_worker, args=(t,)) for t in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:5]

@@ -59,6 +59,9 @@ struct Buffer {
 
 struct DeviceState {
   int sm_count = 0;
+  // Host-pointer calls share the staging buffers, the chunk ring and the copy stream of their device: one such call at a
+  // time per device (they are synchronous and PCIe-bound, so nothing is lost).  Always taken BEFORE g_mutex.
+  std::mutex host_mutex;
   std::map<cudaStream_t, Buffer> workspace;   // split-n_q partials, one per stream so that streams do not share it
   Buffer stage_a, stage_b, stage_c;           // staging for host-pointer calls
   // chunked host path: a copy stream and a ring of chunk buffers with their events
@@ -134,19 +137,28 @@ class CopyPool {
   bool stop_ = false;
 };
 
-std::mutex g_mutex;
-std::map<int, DeviceState> g_devices;
+std::mutex g_mutex;                                        // guards g_devices and the buffer tables inside a DeviceState
+std::map<int, std::unique_ptr<DeviceState>> g_devices;     // entries are never erased: a DeviceState* stays valid
 
+// caller holds g_mutex
 int device_state(int device, DeviceState** out)
 {
   auto it = g_devices.find(device);
   if (it == g_devices.end()) {
-    DeviceState st;
-    CUDA_TRY(cudaDeviceGetAttribute(&st.sm_count, cudaDevAttrMultiProcessorCount, device), "cudaDeviceGetAttribute");
-    it = g_devices.emplace(device, st).first;
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device), "cudaDeviceGetAttribute");
+    std::unique_ptr<DeviceState> st(new DeviceState);
+    st->sm_count = sms;
+    it = g_devices.emplace(device, std::move(st)).first;
   }
-  *out = &it->second;
+  *out = it->second.get();
   return TTV_B200_OK;
+}
+
+int device_state_locked(int device, DeviceState** out)
+{
+  std::lock_guard<std::mutex> lock(g_mutex);
+  return device_state(device, out);
 }
 
 int ensure(Buffer& buf, size_t bytes)
@@ -216,9 +228,8 @@ int run_view_device(int dtype, const View& v, const void* a, const void* b, void
   cudaStream_t stream = opts ? static_cast<cudaStream_t>(opts->stream) : nullptr;
   const bool accumulate = opts && (opts->flags & TTV_B200_FLAG_ACCUMULATE);
 
-  std::lock_guard<std::mutex> lock(g_mutex);
   DeviceState* st = nullptr;
-  if (int rc = device_state(device, &st)) return rc;
+  if (int rc = device_state_locked(device, &st)) return rc;
 
   if (v.strided) {
     CUDA_TRY(launch_strided(dtype, v, a, b, c, accumulate, st->sm_count, stream), "kernel launch");
@@ -231,10 +242,16 @@ int run_view_device(int dtype, const View& v, const void* a, const void* b, void
 
   void* ws = nullptr;
   if (l.workspace_bytes) {
+    // one workspace per (device, stream); calls on ONE stream must come from one thread at a time, as for any CUDA stream
+    std::unique_lock<std::mutex> lock(g_mutex);
     Buffer& buf = st->workspace[stream];
     if (buf.bytes < l.workspace_bytes) {
       // the old block may still be in use by work queued on this stream
-      if (buf.ptr) CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+      if (buf.ptr) {
+        lock.unlock();
+        CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+        lock.lock();
+      }
       if (int r2 = ensure(buf, (size_t)l.workspace_bytes)) return r2;
     }
     ws = buf.ptr;
@@ -391,6 +408,9 @@ int run_view_host(int dtype, const View& v, const void* a, const void* b, void* 
   if (device < 0) CUDA_TRY(cudaGetDevice(&device), "cudaGetDevice (is a CUDA device visible?)");
   DeviceGuard guard;
   CUDA_TRY(guard.set(device), "cudaSetDevice");
+  DeviceState* hst = nullptr;
+  if (int rc = device_state_locked(device, &hst)) return rc;
+  std::lock_guard<std::mutex> host_lock(hst->host_mutex);      // staging buffers are per device: one host call at a time
 
   {
     const void* bs[1] = {b};
@@ -513,6 +533,9 @@ int ttv_b200_multi(int dtype, uint64_t p,
   if (device < 0) CUDA_TRY(cudaGetDevice(&device), "cudaGetDevice (is a CUDA device visible?)");
   DeviceGuard guard;
   CUDA_TRY(guard.set(device), "cudaSetDevice");
+  DeviceState* hst = nullptr;
+  if (int rc = device_state_locked(device, &hst)) return rc;
+  std::lock_guard<std::mutex> host_lock(hst->host_mutex);      // staging buffers are per device: one host call at a time
   {
     const int rc = run_host_pipelined(dtype, count, views.data(), a, b, c, opts, device);
     if (rc >= 0) return rc;
@@ -723,18 +746,31 @@ int ttv_b200_device_count(void)
 
 void ttv_b200_release(void)
 {
-  std::lock_guard<std::mutex> lock(g_mutex);
-  for (auto& kv : g_devices) {
-    int prev = -1;
-    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); continue; }
-    cudaSetDevice(kv.first);
-    for (auto& w : kv.second.workspace) if (w.second.ptr) cudaFree(w.second.ptr);
-    kv.second.workspace.clear();
-    for (Buffer* b : {&kv.second.stage_a, &kv.second.stage_b, &kv.second.stage_c, &kv.second.ring[0], &kv.second.ring[1], &kv.second.ring[2]})
+  // collect the states first: host_mutex is always taken before g_mutex
+  std::vector<std::pair<int, DeviceState*>> states;
+  {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    for (auto& kv : g_devices) states.emplace_back(kv.first, kv.second.get());
+  }
+  for (auto& ds : states) {
+    DeviceState& st = *ds.second;
+    std::lock_guard<std::mutex> host_lock(st.host_mutex);       // no host-pointer call is using the buffers
+    std::lock_guard<std::mutex> lock(g_mutex);
+    DeviceGuard guard;
+    if (guard.set(ds.first) != cudaSuccess) { cudaGetLastError(); continue; }
+    cudaDeviceSynchronize();                                    // queued kernels may still read a workspace
+    for (auto& w : st.workspace) if (w.second.ptr) cudaFree(w.second.ptr);
+    st.workspace.clear();
+    for (Buffer* b : {&st.stage_a, &st.stage_b, &st.stage_c, &st.ring[0], &st.ring[1], &st.ring[2]})
       if (b->ptr) { cudaFree(b->ptr); b->ptr = nullptr; b->bytes = 0; }
-    for (int r = 0; r < 3; ++r) if (kv.second.bounce[r]) { cudaFreeHost(kv.second.bounce[r]); kv.second.bounce[r] = nullptr; }
-    kv.second.bounce_bytes = 0;
-    cudaSetDevice(prev);
+    for (int r = 0; r < 3; ++r) {
+      if (st.bounce[r]) { cudaFreeHost(st.bounce[r]); st.bounce[r] = nullptr; }
+      if (st.ready[r]) { cudaEventDestroy(st.ready[r]); st.ready[r] = nullptr; }
+      if (st.freed[r]) { cudaEventDestroy(st.freed[r]); st.freed[r] = nullptr; }
+    }
+    st.bounce_bytes = 0;
+    if (st.copy_stream) { cudaStreamDestroy(st.copy_stream); st.copy_stream = nullptr; }
+    cudaGetLastError();
   }
 }
 
