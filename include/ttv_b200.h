@@ -187,6 +187,24 @@ int ttv_b200_multi(int dtype, uint64_t p,
                    uint64_t count, const uint64_t* q, const void* const* b, void* const* c,
                    const ttv_b200_opts* opts);
 
+/* The chain of p-1 products that leaves mode q:  c = A x_1 b_1 ... x_{q-1} b_{q-1} x_{q+1} b_{q+1} ... x_p b_p, a vector of
+ * na[q-1] elements.  Replaces ttvpy::ttvs (reference ttvpy/src/wrapped_ttv.cpp:83-198), which calls ttv p-1 times and
+ * creates a fresh numpy array for every intermediate.  Here the intermediates live in HBM (stream-ordered pool of the
+ * library): with HOST pointers A crosses PCIe once, streamed in chunks under the kernels of the first product, the
+ * other p-2 kernels run back to back on the device and only c comes back; with DEVICE pointers nothing leaves HBM and
+ * TTV_B200_FLAG_ASYNC returns after enqueueing on opts->stream.
+ *   a        packed tensor of shape na and layout pia (ttvpy: C-contiguous numpy array = last-order layout p..1)
+ *   b[j]     j < p-1, the vector of mode j+1 (j+1 < q) or j+2: na[mode-1] elements, unit stride (wrapped_ttv.cpp:126-129)
+ *   order    which mode goes first (wrapped_ttv.cpp:135-192): longest vector first / mode p downwards / mode 1 upwards;
+ *            every order gives the same result up to the rounding of a different summation order
+ *   a, b[j], c: all host or all device.  opts: device, stream, hints and TTV_B200_FLAG_{ASYNC,NO_VEC}; other fields ignored. */
+enum ttv_b200_chain_order { TTV_B200_CHAIN_OPTIMAL = 0, TTV_B200_CHAIN_BACKWARD = 1, TTV_B200_CHAIN_FORWARD = 2 };
+int ttv_b200_ttvs(int dtype, uint64_t q, uint64_t p, const void* a, const uint64_t* na, const uint64_t* pia,
+                  const void* const* b, int order, void* c, const ttv_b200_opts* opts);
+/* The schedule ttv_b200_ttvs follows, p-1 entries: step i contracts mode modes[i] (1-based, numbered in the tensor left
+ * after the steps before it) with vector b[vectors[i]].  Pure host code. */
+int ttv_b200_chain_plan(uint64_t q, uint64_t p, const uint64_t* na, int order, uint64_t* modes, uint64_t* vectors);
+
 /* Validation + layout folding + kernel choice without touching a device (pure host code).  Pointers a, b, c are
  * only checked for null-ness; pass any non-null value.  Returns the same status codes as ttv_b200_run. */
 int ttv_b200_plan(int dtype, uint64_t q, uint64_t p,

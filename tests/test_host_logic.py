@@ -234,6 +234,43 @@ def test_chain_plan_orders():
     assert chain_plan(4, (3, 9, 4, 5), "optimal") == [(2, 1), (2, 2), (1, 0)]
 
 
+def test_native_chain_plan_matches_the_restated_schedule():
+    """ttv_b200_chain_plan (the schedule ttv_b200_ttvs follows) against the Python restatement of wrapped_ttv.cpp:135-192
+    on random shapes, every q and order; and against the reference's own loops for backward / forward"""
+    import random
+    from ttv_b200 import api
+    from ttv_b200.ttvpy import chain_plan
+    rng = random.Random(7)
+    for _ in range(300):
+        p = rng.randint(2, 9)
+        shape = [rng.choice([1, 2, 3, 5, 5, 8, 13]) for _ in range(p)]
+        for q in range(1, p + 1):
+            for order in ("optimal", "backward", "forward"):
+                got = api.chain_plan(q, shape, order)
+                assert got == chain_plan(q, shape, order), (shape, q, order)
+                assert sorted(j for _, j in got) == list(range(p - 1))
+            # wrapped_ttv.cpp:135-146 (backward) and :147-156 (forward), written out the way the reference loops
+            back = [(p - 1 if q == p else p, p - 2)]
+            r0 = back[0][0]
+            back += [(r1, r1 - 2) for r1 in range(r0 - 1, q, -1)]
+            back += [(r2, r2 - 1) for r2 in range((r0 - 1) if q == p else (q - 1), 0, -1)]
+            assert api.chain_plan(q, shape, "backward") == back, (shape, q)
+            fwd = [(2 if q == 1 else 1, 0)] + [(1, r1 - 1) for r1 in range(2, q)] + [(2, r2 - 1) for r2 in range(2 if q == 1 else q, p)]
+            assert api.chain_plan(q, shape, "forward") == fwd, (shape, q)
+    with pytest.raises(ttv_b200.TTVError) as e:
+        api.chain_plan(0, (2, 3), "optimal")
+    assert e.value.status == 2
+
+
+def test_native_chain_needs_a_device():
+    if ttv_b200.device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    from ttv_b200 import ttvpy
+    with pytest.raises(ttv_b200.TTVError) as e:
+        ttvpy.ttvs(1, np.ones((3, 4, 2)), [np.ones(4), np.ones(2)])
+    assert e.value.status == 40 and "no CPU fallback" in str(e.value)
+
+
 def test_chooser_only_picks_instantiated_kernels():
     """fuzz of the canonical view: the (nu, ku) batch shape must be one the dispatcher instantiates (launch.cu), the
     thread tile must fit the CTA, vectors must divide the extent they run along"""

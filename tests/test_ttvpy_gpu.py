@@ -99,3 +99,86 @@ def test_captured_chain_replays_on_new_data():
                     want = np.einsum(letters + "," + ",".join(letters[r] for r in range(4) if r != q - 1) + "->" + letters[q - 1],
                                      A.cpu().numpy(), *[bj.cpu().numpy() for bj in bs])
                     assert np.array_equal(got.cpu().numpy(), want), (dtype, q, order)
+
+
+def _chain_reference(A, bs, q):
+    """the chain by einsum, contracting one mode after the other (exact on small-integer data)"""
+    p = A.ndim
+    letters = "abcdefgh"[:p]
+    return np.einsum(letters + "," + ",".join(letters[r] for r in range(p) if r != q - 1) + "->" + letters[q - 1], A, *bs)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.complex64, np.complex128, np.int32, np.int64])
+def test_native_chain_host_and_device(dtype, monkeypatch):
+    """ttv_b200_ttvs (one native call, intermediates in the library's stream-ordered pool) against einsum and against the
+    stepwise Python chain: orders 2..6, every q and order, extent-1 modes, host tensors (plain and chunked upload of A
+    with the first result staying on the device) and device tensors; through a non-default layout as well"""
+    import torch
+    from ttv_b200 import api
+    import ttv_b200
+    rng = np.random.default_rng(11)
+    shapes = [(7, 5), (1, 9), (6, 1, 4), (3, 2, 4, 5), (5, 1, 3, 1, 4), (4, 3, 2, 3, 2, 5), (64, 50, 83)]
+    for shape in shapes:
+        p = len(shape)
+        A = rng.integers(-3, 4, shape).astype(dtype)
+        if np.dtype(dtype).kind == "c":
+            A = (A + 1j * rng.integers(-3, 4, shape)).astype(dtype)
+        for q in range(1, p + 1):
+            bs = [rng.integers(-2, 3, shape[r]).astype(dtype) for r in range(p) if r != q - 1]
+            want = _chain_reference(A, bs, q)
+            for order in ("optimal", "backward", "forward"):
+                before = ttv_b200.launch_count()
+                got = tp.ttvs(q, A, bs, order)
+                assert got.shape == want.shape and np.array_equal(got, want), (shape, q, order, "host")
+                assert ttv_b200.launch_count() - before >= p - 1
+            monkeypatch.setenv("TTV_B200_PY_CHAIN", "1")
+            assert np.array_equal(tp.ttvs(q, A, bs, "optimal"), want), (shape, q, "stepwise")
+            monkeypatch.delenv("TTV_B200_PY_CHAIN")
+            tA, tbs = torch.from_numpy(A).cuda(), [torch.from_numpy(b).cuda() for b in bs]
+            for order in ("optimal", "forward"):
+                got = tp.ttvs(q, tA, tbs, order)
+                assert got.is_cuda and np.array_equal(got.cpu().numpy(), want), (shape, q, order, "device")
+            # the same tensor stored first-order (Fortran order): the native entry takes any layout tuple
+            flat = np.ascontiguousarray(A.reshape(-1, order="F"))
+            got = api.ttvs(q, flat, list(shape), list(range(1, p + 1)), bs, "backward")
+            assert np.array_equal(got, want), (shape, q, "first-order")
+    # chunked upload: A of a few MB with 1 MiB chunks, the first product's result stays in HBM
+    monkeypatch.setenv("TTV_B200_H2D_CHUNK_MB", "1")
+    shape = (40, 30, 100, 9)
+    A = rng.integers(-3, 4, shape).astype(dtype)
+    for q in range(1, 5):
+        bs = [rng.integers(-2, 3, shape[r]).astype(dtype) for r in range(4) if r != q - 1]
+        want = _chain_reference(A, bs, q)
+        for order in ("optimal", "backward", "forward"):
+            assert np.array_equal(tp.ttvs(q, A, bs, order), want), (q, order, "chunked")
+
+
+def test_native_chain_async_on_a_stream_and_errors():
+    import torch
+    from ttv_b200 import api
+    import ttv_b200
+    rng = np.random.default_rng(12)
+    shape = (12, 7, 9, 5)
+    A = rng.integers(-3, 4, shape).astype(np.float64)
+    bs = [rng.integers(-2, 3, shape[r]).astype(np.float64) for r in (0, 1, 3)]
+    want = _chain_reference(A, bs, 3)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        tA, tbs = torch.from_numpy(A).cuda(), [torch.from_numpy(b).cuda() for b in bs]
+        out = torch.full((9,), -1.0, dtype=torch.float64, device="cuda")
+        for _ in range(3):                                   # the pool hands the same blocks out again
+            api.ttvs(3, tA, list(shape), [4, 3, 2, 1], tbs, "optimal", out=out, flags=api.FLAG_ASYNC, stream=stream)
+    stream.synchronize()
+    assert np.array_equal(out.cpu().numpy(), want)
+    # argument errors keep the low-level interface's codes; host and device pointers must not be mixed
+    with pytest.raises(ttv_b200.TTVError) as e:
+        api.ttvs(5, A, list(shape), [4, 3, 2, 1], bs)
+    assert e.value.status == 2
+    with pytest.raises(ttv_b200.TTVError) as e:
+        api.ttvs(3, A, list(shape), [4, 3, 3, 1], bs)
+    assert e.value.status == 16
+    with pytest.raises(ttv_b200.TTVError) as e:
+        api.ttvs(3, A, list(shape), [4, 3, 2, 1], [bs[0], tbs[1], bs[2]])
+    assert e.value.status == 41
+    ttv_b200._lib.load().ttv_b200_release()                # waits, frees staging / workspaces, trims the pool
+    assert np.array_equal(tp.ttvs(3, A, bs), want)         # and everything comes back on demand

@@ -47,6 +47,9 @@ SYMBOLS = {
     "ttv_b200_i64": (C.c_int, _RUN_ARGS),
     "ttv_b200_multi": (C.c_int, [C.c_int, C.c_uint64, C.c_void_p, u64p, u64p, u64p, C.c_uint64, u64p,
                                  C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(Opts)]),
+    "ttv_b200_ttvs": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, u64p, u64p, C.POINTER(C.c_void_p), C.c_int,
+                                C.c_void_p, C.POINTER(Opts)]),
+    "ttv_b200_chain_plan": (C.c_int, [C.c_uint64, C.c_uint64, u64p, C.c_int, u64p, u64p]),
     "ttv_b200_plan": (C.c_int, [C.c_int] + _RUN_ARGS + [C.POINTER(Plan)]),
     "ttv_b200_view": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.POINTER(Opts)]),

@@ -237,6 +237,46 @@ def ttv_multi(qs: Sequence[int], a, na, pia, bs, cs=None, *, wa=None, opts: Opts
     return cs
 
 
+CHAIN_ORDERS = {"optimal": 0, "backward": 1, "forward": 2}
+
+
+def chain_plan(q: int, na, order: str = "optimal"):
+    """[(mode to contract, index into bs), ...] of the p-1 products ttv_b200_ttvs runs (ttv_b200_chain_plan; pure host
+    code).  Modes are numbered in the tensor that is left when the step runs (wrapped_ttv.cpp:135-192)."""
+    lib = _lib.load()
+    p = len(na)
+    modes = (C.c_uint64 * max(p - 1, 1))()
+    vecs = (C.c_uint64 * max(p - 1, 1))()
+    _check(lib.ttv_b200_chain_plan(q, p, _tuple(na)[1], CHAIN_ORDERS[order], modes, vecs))
+    return [(int(modes[i]), int(vecs[i])) for i in range(p - 1)]
+
+
+def ttvs(q: int, a, na, pia, bs, order: str = "optimal", out=None, *, opts: Opts | None = None, **opt_kwargs):
+    """c = A contracted with bs[j] along every mode except q (ttv_b200_ttvs, the native form of ttvpy::ttvs,
+    wrapped_ttv.cpp:83-198).  a: flat packed buffer of shape na / layout pia -- numpy (host: A crosses PCIe once, the
+    intermediates stay in HBM) or torch CUDA (device).  bs: the p-1 vectors in mode order, same kind as a.  Returns the
+    vector of na[q-1] elements (`out` if given)."""
+    lib = _lib.load()
+    p = len(na)
+    torch_in = _is_torch(a)
+    if out is None:
+        n_out = int(na[q - 1]) if 1 <= q <= p else 1        # (an invalid q is reported by the library, with its text)
+        if torch_in:
+            import torch
+            out = torch.empty(n_out, dtype=a.dtype, device=a.device)
+        else:
+            out = np.empty(n_out, dtype=np.asarray(a).dtype)
+    if opts is None:
+        if "stream" not in opt_kwargs and torch_in and a.is_cuda:
+            opt_kwargs["stream"] = _current_torch_stream(a)
+        opts = make_opts(**opt_kwargs)
+    n = len(bs)
+    barr = (C.c_void_p * max(n, 1))(*[_ptr(b).value for b in bs])
+    _check(lib.ttv_b200_ttvs(dtype_code(a), q, p, _ptr(a), _tuple(na)[1], _tuple(pia)[1], barr, CHAIN_ORDERS[order], _ptr(out),
+                             C.byref(opts)))
+    return out
+
+
 def plan(q: int, na, pia, *, dtype="f32", wa=None, wc=None, pic=None, **opt_kwargs) -> dict:
     """What the layout folder and the kernel chooser decide for (na, pia, q): pure host code, needs no GPU."""
     lib = _lib.load()

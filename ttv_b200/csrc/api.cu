@@ -71,6 +71,8 @@ struct DeviceState {
   // pageable host memory: pinned bounce buffers, one per ring slot, filled by the copy threads
   void*  bounce[3] = {nullptr, nullptr, nullptr};
   size_t bounce_bytes = 0;
+  // stream-ordered pool for the intermediates of a chain of products (ttv_b200_ttvs)
+  cudaMemPool_t pool = nullptr;
 };
 
 // Host threads that copy a chunk of pageable memory into a pinned bounce buffer in parallel.  cudaMemcpy from pageable
@@ -274,8 +276,9 @@ int env_mb(const char* name, int fallback)
 // buffers of A live on the device, so the tensor may be larger than what is free in HBM.
 // Returns -1 when the call is not eligible (small, strided, one indivisible slab): the caller takes the plain path.
 int run_host_pipelined(int dtype, uint64_t count, const View* views, const void* a, const void* const* b, void* const* c,
-                       const ttv_b200_opts* opts, int device)
+                       const ttv_b200_opts* opts, int device, bool bc_dev = false)
 {
+  // bc_dev: the vectors and the results are DEVICE buffers (the first product of a chain): nothing of them is staged
   const size_t s = (size_t)dtype_size(dtype);
   const View& v0 = views[0];
   const uint64_t total = v0.outer * v0.nq * v0.inner;
@@ -331,18 +334,23 @@ int run_host_pipelined(int dtype, uint64_t count, const View* views, const void*
       }
       st->bounce_bytes = chunk_bytes;
     }
-    if (int rc = ensure(st->stage_b, max_b * count)) return rc;
-    if (int rc = ensure(st->stage_c, sum_c)) return rc;
-    db_ = static_cast<char*>(st->stage_b.ptr); dc_ = static_cast<char*>(st->stage_c.ptr);
+    if (!bc_dev) {
+      if (int rc = ensure(st->stage_b, max_b * count)) return rc;
+      if (int rc = ensure(st->stage_c, sum_c)) return rc;
+      db_ = static_cast<char*>(st->stage_b.ptr); dc_ = static_cast<char*>(st->stage_c.ptr);
+    }
   }
   // the vectors (and C when it is accumulated into) go first, on the compute stream
   std::vector<char*> dci(count);
+  std::vector<const char*> dbi(count);
   std::vector<char> c_pinned(count);
-  for (uint64_t i = 0; i < count; ++i) c_pinned[i] = is_pinned_host(c[i]) ? 1 : 0;
+  for (uint64_t i = 0; i < count; ++i) c_pinned[i] = (!bc_dev && is_pinned_host(c[i])) ? 1 : 0;
   size_t coff = 0;
   for (uint64_t i = 0; i < count; ++i) {
+    if (bc_dev) { dci[i] = static_cast<char*>(c[i]); dbi[i] = static_cast<const char*>(b[i]); continue; }
     const size_t bytes_c = (size_t)(views[i].outer * views[i].inner) * s;
     dci[i] = dc_ + coff;
+    dbi[i] = db_ + i * max_b;
     coff += (bytes_c + 255) / 256 * 256;
     CUDA_TRY(cudaMemcpyAsync(db_ + i * max_b, b[i], (size_t)views[i].nq * s, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync H2D b");
     if (accumulate) CUDA_TRY(cudaMemcpyAsync(dci[i], c[i], bytes_c, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync H2D C");
@@ -371,7 +379,7 @@ int run_host_pipelined(int dtype, uint64_t count, const View* views, const void*
       View v = views[i];
       const bool nq_split = v.outer == 1;
       char* cdst = dci[i];
-      const char* bsrc = db_ + i * max_b;
+      const char* bsrc = dbi[i];
       if (nq_split) {
         v.nq = ns;
         bsrc += (size_t)s0 * s;
@@ -393,7 +401,7 @@ int run_host_pipelined(int dtype, uint64_t count, const View* views, const void*
     }
     CUDA_TRY(cudaEventRecord(st->freed[r], stream), "cudaEventRecord");
   }
-  for (uint64_t i = 0; i < count; ++i)
+  for (uint64_t i = 0; i < count && !bc_dev; ++i)
     if (views[i].outer == 1 || !c_pinned[i])
       CUDA_TRY(cudaMemcpyAsync(c[i], dci[i], (size_t)(views[i].outer * views[i].inner) * s, cudaMemcpyDeviceToHost, stream),
                "cudaMemcpyAsync D2H C");
@@ -402,7 +410,7 @@ int run_host_pipelined(int dtype, uint64_t count, const View* views, const void*
 }
 
 // host pointers: H2D(A, b) -> kernel -> D2H(C), all on one stream, then wait
-int run_view_host(int dtype, const View& v, const void* a, const void* b, void* c, const ttv_b200_opts* opts)
+int run_view_host(int dtype, const View& v, const void* a, const void* b, void* c, const ttv_b200_opts* opts, bool bc_dev = false)
 {
   int device = opts ? opts->device : -1;
   if (device < 0) CUDA_TRY(cudaGetDevice(&device), "cudaGetDevice (is a CUDA device visible?)");
@@ -415,7 +423,7 @@ int run_view_host(int dtype, const View& v, const void* a, const void* b, void* 
   {
     const void* bs[1] = {b};
     void* cs[1] = {c};
-    const int rc = run_host_pipelined(dtype, 1, &v, a, bs, cs, opts, device);
+    const int rc = run_host_pipelined(dtype, 1, &v, a, bs, cs, opts, device, bc_dev);
     if (rc >= 0) return rc;
   }
   const size_t s = (size_t)dtype_size(dtype);
@@ -432,16 +440,22 @@ int run_view_host(int dtype, const View& v, const void* a, const void* b, void* 
     DeviceState* st = nullptr;
     if (int rc = device_state(device, &st)) return rc;
     if (int rc = ensure(st->stage_a, bytes_a)) return rc;
-    if (int rc = ensure(st->stage_b, bytes_b)) return rc;
-    if (int rc = ensure(st->stage_c, bytes_c)) return rc;
-    da = st->stage_a.ptr; db = st->stage_b.ptr; dc = st->stage_c.ptr;
+    da = st->stage_a.ptr;
+    if (bc_dev) { db = const_cast<void*>(b); dc = c; }
+    else {
+      if (int rc = ensure(st->stage_b, bytes_b)) return rc;
+      if (int rc = ensure(st->stage_c, bytes_c)) return rc;
+      db = st->stage_b.ptr; dc = st->stage_c.ptr;
+    }
   }
   CUDA_TRY(cudaMemcpyAsync(da, a, bytes_a, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync H2D A");
-  CUDA_TRY(cudaMemcpyAsync(db, b, bytes_b, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync H2D b");
-  if (c_goes_up) CUDA_TRY(cudaMemcpyAsync(dc, c, bytes_c, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync H2D C");
+  if (!bc_dev) {
+    CUDA_TRY(cudaMemcpyAsync(db, b, bytes_b, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync H2D b");
+    if (c_goes_up) CUDA_TRY(cudaMemcpyAsync(dc, c, bytes_c, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync H2D C");
+  }
   if (int rc = run_view_device(dtype, v, da, db, dc, opts, device, false)) return rc;
-  CUDA_TRY(cudaMemcpyAsync(c, dc, bytes_c, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync D2H C");
-  CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+  if (!bc_dev) CUDA_TRY(cudaMemcpyAsync(c, dc, bytes_c, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync D2H C");
+  CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");   // the staging of A is free again when this returns
   return TTV_B200_OK;
 }
 
@@ -460,6 +474,73 @@ int run_any(int dtype, const View& v, const void* a, const void* b, void* c, con
   const bool async = opts && (opts->flags & TTV_B200_FLAG_ASYNC);
   return run_view_device(dtype, v, a, b, c, opts, da, !async);
 }
+
+// ---- the chain of p-1 products (reference ttvpy/src/wrapped_ttv.cpp:83-198) ----------------------------------------
+// Which mode each step contracts and with which vector: vector j belongs to mode r = j+1 (j+1 < q) or j+2.
+//   backward: r = p, p-1, ... (skipping q)      wrapped_ttv.cpp:135-146
+//   forward : r = 1, 2, ...   (skipping q)      wrapped_ttv.cpp:147-156
+//   optimal : longest vector first, so that the tensor shrinks as fast as possible (:157-192; ties: smaller mode first)
+// modes[i] is numbered in the tensor that is left when step i runs (contracted modes drop out, later ones move down).
+int chain_plan(uint64_t q, uint64_t p, const uint64_t* na, int order, uint64_t* modes, uint64_t* vectors)
+{
+  std::vector<uint64_t> seq;                                     // original modes in the order they are contracted
+  for (uint64_t r = 1; r <= p; ++r) if (r != q) seq.push_back(r);
+  if (order == TTV_B200_CHAIN_BACKWARD) std::reverse(seq.begin(), seq.end());
+  else if (order == TTV_B200_CHAIN_OPTIMAL)
+    std::stable_sort(seq.begin(), seq.end(), [na](uint64_t x, uint64_t y) { return na[x - 1] > na[y - 1]; });
+  std::vector<uint64_t> alive;
+  for (uint64_t r = 1; r <= p; ++r) alive.push_back(r);
+  for (size_t i = 0; i < seq.size(); ++i) {
+    const uint64_t r = seq[i];
+    const auto it = std::find(alive.begin(), alive.end(), r);
+    modes[i] = (uint64_t)(it - alive.begin()) + 1;
+    vectors[i] = r < q ? r - 1 : r - 2;
+    alive.erase(it);
+  }
+  return TTV_B200_OK;
+}
+
+int chain_pool(int device, cudaMemPool_t* out)
+{
+  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceState* st = nullptr;
+  if (int rc = device_state(device, &st)) return rc;
+  if (!st->pool) {
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    CUDA_TRY(cudaMemPoolCreate(&st->pool, &props), "cudaMemPoolCreate");
+    // blocks of up to 1 GiB stay with the pool across synchronisations (a chain on the same shapes allocates nothing new);
+    // anything above goes back to the driver so that other allocators of the process can have it
+    uint64_t keep = 1ull << 30;
+    CUDA_TRY(cudaMemPoolSetAttribute(st->pool, cudaMemPoolAttrReleaseThreshold, &keep), "cudaMemPoolSetAttribute");
+  }
+  *out = st->pool;
+  return TTV_B200_OK;
+}
+
+// stream-ordered allocations of one chain; whatever is still held goes back to the pool when the chain leaves
+struct PoolAllocs {
+  cudaMemPool_t pool = nullptr;
+  cudaStream_t stream = nullptr;
+  std::vector<void*> held;
+  int get(void** out, size_t bytes)
+  {
+    CUDA_TRY(cudaMallocFromPoolAsync(out, std::max<size_t>(bytes, 256), pool, stream), "cudaMallocFromPoolAsync");
+    held.push_back(*out);
+    return TTV_B200_OK;
+  }
+  void put(void* ptr)
+  {
+    auto it = std::find(held.begin(), held.end(), ptr);
+    if (it == held.end()) return;
+    held.erase(it);
+    if (cudaFreeAsync(ptr, stream) != cudaSuccess) cudaGetLastError();
+  }
+  ~PoolAllocs() { while (!held.empty()) put(held.back()); }
+};
 
 } // namespace
 
@@ -572,6 +653,128 @@ int ttv_b200_multi(int dtype, uint64_t p,
     coff += (bytes_c + 255) / 256 * 256;
   }
   CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+  return TTV_B200_OK;
+}
+
+int ttv_b200_chain_plan(uint64_t q, uint64_t p, const uint64_t* na, int order, uint64_t* modes, uint64_t* vectors)
+{
+  if (p == 0) return fail(TTV_B200_ERR_ORDER_ZERO);
+  if (q == 0 || q > p) return fail(TTV_B200_ERR_MODE);
+  if (!na) return fail(TTV_B200_ERR_NA_NULL);
+  if (!modes || !vectors) return fail(TTV_B200_ERR_OPTS, "ttv_b200_chain_plan: modes and vectors must not be null");
+  if (order < TTV_B200_CHAIN_OPTIMAL || order > TTV_B200_CHAIN_FORWARD) return fail(TTV_B200_ERR_OPTS, "ttv_b200_chain_plan: unknown order %d", order);
+  return chain_plan(q, p, na, order, modes, vectors);
+}
+
+int ttv_b200_ttvs(int dtype, uint64_t q, uint64_t p, const void* a, const uint64_t* na, const uint64_t* pia,
+                  const void* const* b, int order, void* c, const ttv_b200_opts* opts)
+{
+  const size_t s = (size_t)dtype_size(dtype);
+  if (s == 0) return fail(TTV_B200_ERR_DTYPE);
+  if (p == 0) return fail(TTV_B200_ERR_ORDER_ZERO);
+  if (q == 0 || q > p) return fail(TTV_B200_ERR_MODE);
+  if (!a) return fail(TTV_B200_ERR_A_NULL);
+  if (!b) return fail(TTV_B200_ERR_B_NULL);
+  if (!c) return fail(TTV_B200_ERR_C_NULL);
+  if (!na) return fail(TTV_B200_ERR_NA_NULL);
+  if (!pia) return fail(TTV_B200_ERR_PIA_NULL);
+  if (p > (uint64_t)kMaxOrder) return fail(TTV_B200_ERR_OPTS, "order above %d", kMaxOrder);
+  if (!is_valid_shape(na, p)) return fail(TTV_B200_ERR_SHAPE_A);
+  if (!is_valid_layout(pia, p)) return fail(TTV_B200_ERR_LAYOUT_A);
+  if (p < 2) return fail(TTV_B200_ERR_SHAPE_C);                      // nothing to contract
+  if (order < TTV_B200_CHAIN_OPTIMAL || order > TTV_B200_CHAIN_FORWARD) return fail(TTV_B200_ERR_OPTS, "ttv_b200_ttvs: unknown order %d", order);
+  const uint64_t steps = p - 1;
+  for (uint64_t j = 0; j < steps; ++j) if (!b[j]) return fail(TTV_B200_ERR_B_NULL);
+
+  Where where, wx;
+  int dev_a = -1, dx = -1;
+  if (int rc = classify(a, &where, &dev_a)) return rc;
+  if (int rc = classify(c, &wx, &dx)) return rc;
+  if (wx != where || (where == Where::Device && dx != dev_a)) return fail(TTV_B200_ERR_MIXED_POINTERS);
+  for (uint64_t j = 0; j < steps; ++j) {
+    if (int rc = classify(b[j], &wx, &dx)) return rc;
+    if (wx != where || (where == Where::Device && dx != dev_a)) return fail(TTV_B200_ERR_MIXED_POINTERS);
+  }
+  const bool host = where == Where::Host;
+  int device = host ? (opts ? opts->device : -1) : dev_a;
+  if (device < 0) CUDA_TRY(cudaGetDevice(&device), "cudaGetDevice (is a CUDA device visible?)");
+  DeviceGuard guard;
+  CUDA_TRY(guard.set(device), "cudaSetDevice");
+
+  ttv_b200_opts local = opts ? *opts : ttv_b200_opts{-1, TTV_B200_EXEC_PAR_LOOP, TTV_B200_SUBTENSOR, TTV_B200_FUSE_ALL, 0, 0, 0, 0, nullptr};
+  const bool async = !host && (local.flags & TTV_B200_FLAG_ASYNC);
+  local.device = device;
+  local.kernel = 0; local.ksplit = 0;                                  // every step picks its own kernel
+  local.flags &= (uint32_t)TTV_B200_FLAG_NO_VEC;                       // no accumulate, no strides, steps never wait
+  cudaStream_t stream = static_cast<cudaStream_t>(local.stream);
+
+  uint64_t modes[kMaxOrder], vecs[kMaxOrder];
+  chain_plan(q, p, na, order, modes, vecs);
+
+  PoolAllocs mem;
+  mem.stream = stream;
+  if (int rc = chain_pool(device, &mem.pool)) return rc;
+
+  // host vectors go up once, packed into one block
+  std::vector<const void*> dvec(steps);
+  if (host) {
+    std::vector<size_t> off(steps);
+    size_t total = 0;
+    for (uint64_t j = 0; j < steps; ++j) {
+      const uint64_t r = j + 1 < q ? j + 1 : j + 2;
+      off[j] = total;
+      total += ((size_t)na[r - 1] * s + 255) / 256 * 256;
+    }
+    void* block = nullptr;
+    if (int rc = mem.get(&block, total)) return rc;
+    for (uint64_t j = 0; j < steps; ++j) {
+      const uint64_t r = j + 1 < q ? j + 1 : j + 2;
+      dvec[j] = static_cast<char*>(block) + off[j];
+      CUDA_TRY(cudaMemcpyAsync(const_cast<void*>(dvec[j]), b[j], (size_t)na[r - 1] * s, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync H2D b");
+    }
+  } else {
+    for (uint64_t j = 0; j < steps; ++j) dvec[j] = b[j];
+  }
+
+  uint64_t cn[kMaxOrder], cpi[kMaxOrder], cw[kMaxOrder], nn[kMaxOrder], npi[kMaxOrder], nw[kMaxOrder];
+  std::copy(na, na + p, cn);
+  std::copy(pia, pia + p, cpi);
+  uint64_t cp = p;
+  const void* cur = a;                 // host pointer at step 0 of a host chain, device pointer otherwise
+  void* cur_owned = nullptr;           // the pool block behind `cur`, if any
+  for (uint64_t i = 0; i < steps; ++i) {
+    const uint64_t m = modes[i];
+    output_shape(cn, cp, m, nn);
+    output_layout(cpi, cp, m, npi);
+    uint64_t stride = 1, elems = 1;                                     // packed strides of both tensors
+    for (uint64_t r = 0; r < cp; ++r) { cw[cpi[r] - 1] = stride; stride *= cn[cpi[r] - 1]; }
+    for (uint64_t r = 0; r + 1 < cp; ++r) { nw[npi[r] - 1] = elems; elems *= nn[npi[r] - 1]; }
+    const bool last = i + 1 == steps;
+    void* dst = nullptr;
+    void* dst_owned = nullptr;
+    if (last && !host) dst = c;
+    else { if (int rc = mem.get(&dst, (size_t)elems * s)) return rc; dst_owned = dst; }
+    const uint64_t nb = cn[m - 1];
+    View v;
+    if (int rc = validate_and_fold(m, cp, cur, cn, cw, cpi, dvec[vecs[i]], &nb, dst, nn, nw, npi, 0u, &v)) return fail(rc);
+    if (i == 0 && host) {
+      // the only step that reads all of A: streamed across PCIe in chunks under its own kernels; the result stays in HBM
+      if (int rc = run_view_host(dtype, v, cur, dvec[vecs[i]], dst, &local, /*bc_dev=*/true)) return rc;
+    } else {
+      if (int rc = run_view_device(dtype, v, cur, dvec[vecs[i]], dst, &local, device, false)) return rc;
+    }
+    if (cur_owned) mem.put(cur_owned);                                  // stream-ordered: free after the step that read it
+    cur = dst; cur_owned = dst_owned;
+    std::copy(nn, nn + cp - 1, cn);
+    std::copy(npi, npi + cp - 1, cpi);
+    --cp;
+  }
+  if (host) {
+    CUDA_TRY(cudaMemcpyAsync(c, cur, (size_t)na[q - 1] * s, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync D2H c");
+    CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+  } else if (!async) {
+    CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+  }
   return TTV_B200_OK;
 }
 
@@ -770,6 +973,7 @@ void ttv_b200_release(void)
     }
     st.bounce_bytes = 0;
     if (st.copy_stream) { cudaStreamDestroy(st.copy_stream); st.copy_stream = nullptr; }
+    if (st.pool) cudaMemPoolTrimTo(st.pool, 0);
     cudaGetLastError();
   }
 }

@@ -9,10 +9,13 @@ wrapped_ttv.cpp:205-206; strides ignored, :44-45) every element type of the C-AB
 C-contiguous (transposes, slices, Fortran order) are read in place through their strides.  Errors the reference raises as
 std::invalid_argument surface as ValueError with the same text.
 
-ttvs keeps the intermediates in HBM: A crosses PCIe once (streamed in chunks under the first product when it comes from
-host memory), the remaining kernels run back to back on the device, and only the final vector is copied back.
+ttvs keeps the intermediates in HBM (ttv_b200_ttvs, one native call): A crosses PCIe once (streamed in chunks under the
+first product when it comes from host memory), the remaining kernels run back to back on the device, and only the final
+vector is copied back.
 """
 from __future__ import annotations
+
+import os
 
 import numpy as np
 
@@ -99,6 +102,20 @@ def ttvs(q: int, A, bs, order: str = "optimal"):
     if p == 1:
         return A
 
+    if os.environ.get("TTV_B200_PY_CHAIN", "0") != "1":
+        # the native chain (ttv_b200_ttvs): one call, intermediates in a stream-ordered pool in HBM, only c comes back
+        last_order = list(range(p, 0, -1))                  # a C-contiguous array is a last-order tensor (wrapped_ttv.cpp:44-45)
+        if on_device:
+            vecs = [bj.to(dtype=A.dtype, device=A.device).contiguous() for bj in bs]
+            return api.ttvs(q, A.contiguous(), shape, last_order, vecs, order)
+        vecs = [np.ascontiguousarray(np.asarray(bj), dtype=A.dtype) for bj in bs]
+        return api.ttvs(q, A, shape, last_order, vecs, order)
+    return _ttvs_stepwise(q, A, bs, order, on_device, shape)
+
+
+def _ttvs_stepwise(q, A, bs, order, on_device, shape):
+    """the same chain as p-1 calls of the low-level interface from Python (TTV_B200_PY_CHAIN=1; also what CapturedTtvs
+    records); the first product of a host tensor returns to the host before the rest continues on the device"""
     import torch
     steps = chain_plan(q, shape, order)
     if on_device:
