@@ -499,6 +499,58 @@ def test_non_packed_strides(dtype, oracle):
         assert np.array_equal(np.lib.stride_tricks.as_strided(c, shape=nc, strides=[w * c.itemsize for w in wc]), want + 3)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.complex128, np.int32, np.int64])
+def test_padded_tensors_with_aligned_rows_take_vector_loads(dtype, monkeypatch):
+    """general strides whose fastest free mode is contiguous in A and C and whose other strides are multiples of a
+    16-byte vector (ttv_strided_vec_kernel: V consecutive outputs per thread): against the definition, with the
+    vector form forced (TTV_B200_STRIDED_SCALAR=2; by default it is taken from ~2.4 M vector outputs on) and the
+    thread-per-output form forced (=1) as a second opinion, odd n_q (partial last batch),
+    accumulate, padding of C untouched, and a device buffer whose start is NOT vector-aligned (falls back to scalar)"""
+    import torch
+    rng = np.random.default_rng(33)
+    cases = [
+        # na, pia, q, wa, wc
+        ((8, 5, 6), (1, 2, 3), 2, (1, 12, 64), (1, 12)),                    # rows padded 8 -> 12
+        ((16, 37, 9, 3), (1, 2, 3, 4), 3, (1, 16, 600, 5600), (1, 20, 800)),  # q in the middle, C padded too
+        ((64, 3, 21, 4), (1, 2, 3, 4), 3, (1, 64, 200, 4400), (1, 64, 192)),
+        ((12, 10, 7), (1, 3, 2), 3, (1, 100, 12), (1, 16)),                  # layout (1,3,2): q = 3 sits in the middle
+        ((4, 250, 8, 6), (1, 2, 3, 4), 2, (1, 4, 1024, 8192), (1, 4, 32)),   # a slice [:250] of a 256-extent mode
+        ((6, 9, 5), (1, 2, 3), 2, (1, 8, 72), (1, 8)),                       # extent 6: only 8-byte vectors for 4-byte types
+    ]
+    for na, pia, q, wa, wc in cases:
+        p = len(na)
+        nc = ttv_b200.generate_output_shape(na, q); pic = ttv_b200.generate_output_layout(pia, q)
+        x, a = _padded(rng, na, wa, dtype)
+        b = rng.integers(-8, 9, na[q - 1]).astype(dtype)
+        want = np.tensordot(x, b, axes=([q - 1], [0]))
+        span_c = 1 + sum((n - 1) * w for n, w in zip(nc, wc))
+        touched = np.zeros(span_c, bool)
+        np.lib.stride_tricks.as_strided(touched, shape=nc, strides=list(wc))[...] = True
+        results = []
+        for scalar in ("2", "1"):                             # 2 = vector form wherever the strides allow, 1 = never
+            monkeypatch.setenv("TTV_B200_STRIDED_SCALAR", scalar)
+            c = np.full(span_c, 55, dtype)
+            ttv_b200.ttv_lowlevel(q, p, a, na, wa, pia, b, [len(b)], c, nc, wc, pic)
+            got = np.lib.stride_tricks.as_strided(c, shape=nc, strides=[w * c.itemsize for w in wc])
+            assert np.array_equal(got, want), (na, pia, q, wa, wc, scalar)
+            assert np.all(c[~touched] == 55), "padding of C was written"
+            results.append(c)
+            c = np.full(span_c, 3, dtype)
+            ttv_b200.ttv_lowlevel(q, p, a, na, wa, pia, b, [len(b)], c, nc, wc, pic, flags=1)
+            assert np.array_equal(np.lib.stride_tricks.as_strided(c, shape=nc, strides=[w * c.itemsize for w in wc]), want + 3)
+        assert np.array_equal(results[0], results[1])
+        monkeypatch.setenv("TTV_B200_STRIDED_SCALAR", "2")
+        # device buffers one element past an aligned address: same strides, but no vector fits
+        ta = torch.zeros(a.size + 1, dtype=torch.from_numpy(a).dtype, device="cuda")
+        ta[1:] = torch.from_numpy(a).cuda()
+        tb = torch.from_numpy(b).cuda()
+        tc = torch.full((span_c + 1,), 55, dtype=ta.dtype, device="cuda")
+        ttv_b200.ttv_lowlevel(q, p, ta[1:], na, wa, pia, tb, [len(b)], tc[1:], nc, wc, pic)
+        c = tc[1:].cpu().numpy()
+        assert np.array_equal(np.lib.stride_tricks.as_strided(c, shape=nc, strides=[w * c.itemsize for w in wc]), want)
+        assert np.all(c[~touched] == 55)
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int64])
 def test_arrays_that_are_not_contiguous_are_read_in_place(dtype):
     """numpy / torch front end: transposes, slices and strided views for EVERY q -- also the cases

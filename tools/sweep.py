@@ -51,6 +51,12 @@ def configs(which):
         out += [("pad3", "f32", [256, 256, 250, 256], first(4), q, w4) for q in (1, 2, 3, 4)]      # A[:, :, :250, :]
         out += [("pad1", "f32", [250, 256, 256, 256], first(4), q, w4) for q in (1, 2, 3, 4)]      # A[:250]: padded rows
         out += [("pad12", "f64", [120, 250, 128, 128], first(4), q, [1, 128, 128 * 256, 128 * 256 * 128]) for q in (1, 2, 3, 4)]
+    if which == "padv":      # what decides between the vector and the thread-per-output form of the general-stride kernel
+        w4 = [1, 256, 256 ** 2, 256 ** 3]
+        out += [("pad1b", "f32", [248, 256, 256, 256], first(4), q, w4) for q in (2, 3, 4)]       # rows of 248 of 256 floats
+        out += [("pad12L", "f64", [120, 250, 256, 256], first(4), q, [1, 128, 128 * 256, 128 * 256 * 256]) for q in (2, 3, 4)]
+        out += [("pad3h", "f32", [256, 256, 250, 32], first(4), q, w4) for q in (2, 3, 4)]         # 2 GB: fewer waves
+        out += [("pad3c", "c64", [128, 256, 250, 128], first(4), q, [1, 128, 128 * 256, 128 * 256 * 256]) for q in (2, 3, 4)]
     if which in ("quick", "sym", "all"):
         out += [("sym4", "f32", [256] * 4, first(4), q) for q in (1, 2, 3, 4)]
     if which in ("sym", "all"):

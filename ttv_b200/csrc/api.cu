@@ -461,7 +461,7 @@ int run_view_host(int dtype, const View& v, const void* a, const void* b, void* 
 
 int run_any(int dtype, const View& v, const void* a, const void* b, void* c, const ttv_b200_opts* opts)
 {
-  Where wa, wb, wc;
+  Where wa = Where::Host, wb = Where::Host, wc = Where::Host;
   int da = -1, db = -1, dc = -1;
   if (int rc = classify(a, &wa, &da)) return rc;
   if (int rc = classify(b, &wb, &db)) return rc;
@@ -588,7 +588,7 @@ int ttv_b200_multi(int dtype, uint64_t p,
     if (int rc = validate_and_fold(q[i], p, a, na, wa, pia, b[i], &nb, c[i], nc, wc, pic, opts ? opts->flags : 0u, &views[i])) return fail(rc);
   }
 
-  Where wa_, wx;
+  Where wa_ = Where::Host, wx = Where::Host;
   int da = -1, dx = -1;
   if (int rc = classify(a, &wa_, &da)) return rc;
   for (uint64_t i = 0; i < count; ++i) {
@@ -686,7 +686,7 @@ int ttv_b200_ttvs(int dtype, uint64_t q, uint64_t p, const void* a, const uint64
   const uint64_t steps = p - 1;
   for (uint64_t j = 0; j < steps; ++j) if (!b[j]) return fail(TTV_B200_ERR_B_NULL);
 
-  Where where, wx;
+  Where where = Where::Host, wx = Where::Host;
   int dev_a = -1, dx = -1;
   if (int rc = classify(a, &where, &dev_a)) return rc;
   if (int rc = classify(c, &wx, &dx)) return rc;

@@ -13,6 +13,7 @@
 #include "scatter_kernel.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <atomic>
 
 namespace ttvb {
@@ -342,12 +343,45 @@ cudaError_t TTVB_CAT(dotf_dtype_, TTVB_DTYPE)(const DotfParams& D, const Launch&
   return cudaGetLastError();
 }
 
+template<int V>
+static cudaError_t launch_scatter_vec(const ScatterParams& S, uint64_t ctas, uint64_t smem, cudaStream_t stream)
+{
+  if constexpr (V <= kVmax) {
+    ttv_col_scatter_kernel<elem_t, V><<<(unsigned)ctas, 256, smem, stream>>>(S);
+    count_launch();
+    return cudaGetLastError();
+  } else {
+    return cudaErrorInvalidValue;
+  }
+}
+
 cudaError_t TTVB_CAT(scatter_dtype_, TTVB_DTYPE)(const ScatterParams& S, int vec, uint64_t ctas, uint64_t smem, cudaStream_t stream)
 {
-  if constexpr (kVmax >= 4) if (vec == 4) { ttv_col_scatter_kernel<elem_t, 4><<<(unsigned)ctas, 256, smem, stream>>>(S); count_launch(); return cudaGetLastError(); }
-  if constexpr (kVmax >= 2) if (vec == 2) { ttv_col_scatter_kernel<elem_t, 2><<<(unsigned)ctas, 256, smem, stream>>>(S); count_launch(); return cudaGetLastError(); }
-  if (vec == 1) { ttv_col_scatter_kernel<elem_t, 1><<<(unsigned)ctas, 256, smem, stream>>>(S); count_launch(); return cudaGetLastError(); }
+  if (vec == 4) return launch_scatter_vec<4>(S, ctas, smem, stream);
+  if (vec == 2) return launch_scatter_vec<2>(S, ctas, smem, stream);
+  if (vec == 1) return launch_scatter_vec<1>(S, ctas, smem, stream);
   return cudaErrorInvalidValue;
+}
+
+// TTV_B200_STRIDED_SCALAR: 1 = keep the thread-per-output form, 2 = take the vector form whenever the strides allow it
+// (A/B measurements, tests of both forms); unset / 0 = the measured rule in strided_dtype_*
+static int strided_form_forced()
+{
+  const char* e = std::getenv("TTV_B200_STRIDED_SCALAR");
+  return (e && *e) ? std::atoi(e) : 0;
+}
+
+template<int V>
+static cudaError_t launch_strided_vec(const StridedParams& S, int sm_count, cudaStream_t stream)
+{
+  if constexpr (V <= kVmax) {                           // (wider vectors than 16 bytes are never instantiated)
+    const uint64_t blocks = std::max<uint64_t>(1, std::min<uint64_t>((S.total / (uint64_t)V + 255) / 256, (uint64_t)sm_count * 32));
+    ttv_strided_vec_kernel<elem_t, V><<<(unsigned)blocks, 256, 0, stream>>>(S);
+    count_launch();
+    return cudaGetLastError();
+  } else {
+    return cudaErrorInvalidValue;
+  }
 }
 
 template<int V>
@@ -375,6 +409,21 @@ cudaError_t TTVB_CAT(strided_dtype_, TTVB_DTYPE)(const StridedParams& S, int sm_
     if constexpr (kVmax >= 4) if (align % 4 == 0) return launch_strided_dot<4>(S, sm_count, stream);
     if constexpr (kVmax >= 2) if (align % 2 == 0) return launch_strided_dot<2>(S, sm_count, stream);
     return launch_strided_dot<1>(S, sm_count, stream);
+  }
+  const int forced = strided_form_forced();
+  if (kVmax > 1 && S.nfree >= 1 && S.wa[0] == 1 && S.wc[0] == 1 && forced != 1) {
+    // the fastest free mode is contiguous in both tensors: V consecutive outputs per thread when everything else lines up
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(S.a) | reinterpret_cast<uintptr_t>(S.c);
+    uint64_t align = (addr % sizeof(elem_t)) ? 1 : (uint64_t)(addr / sizeof(elem_t));
+    align |= S.n[0] | S.wq;
+    for (uint32_t d = 1; d < S.nfree; ++d) align |= S.wa[d] | S.wc[d];
+    // Measured (profiles/r01_padded_strides.txt, session 4): 16-byte vectors of 4-byte elements gain 7-12 % when a warp's
+    // 32 vectors never straddle two rows (slices of a 256^4 fp32 tensor that leave the rows whole: 6.2-6.4 -> 6.8-6.9 TB/s);
+    // on rows that are cut short (248 of 256 floats, 120 of 128 doubles) the vector form LOSES 5-9 %, and 8-byte elements
+    // gain nothing either way -- their thread-per-output loop is not issue-bound.  So: 4-byte elements, whole warps per row.
+    const bool pays = kVmax == 4 && S.n[0] % 128 == 0 && S.total / 4 >= (uint64_t)sm_count * 2048;
+    if (align % kVmax == 0 && (pays || forced == 2)) return launch_strided_vec<kVmax>(S, sm_count, stream);
+    if (forced == 2 && kVmax >= 4 && align % 2 == 0) return launch_strided_vec<2>(S, sm_count, stream);
   }
   const uint64_t blocks = std::max<uint64_t>(1, std::min<uint64_t>((S.total + 255) / 256, (uint64_t)sm_count * 32));
   ttv_strided_kernel<elem_t><<<(unsigned)blocks, 256, 0, stream>>>(S);

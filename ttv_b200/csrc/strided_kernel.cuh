@@ -88,6 +88,75 @@ ttv_strided_kernel(const StridedParams P)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// STRIDED, vector form: the fastest free mode is contiguous in A AND in C and every other stride, the extent of that
+// mode and the addresses are multiples of V elements (a leading dimension padded to whole 16-byte lines, a slice that
+// cuts a slower mode).  A thread then owns V CONSECUTIVE outputs: one 16-byte load per k-step instead of V scalar ones,
+// eight of them (128 bytes) in flight, one 16-byte store; the index decode is shared by the V outputs.
+// ------------------------------------------------------------------------------------------------------------------
+template<class T, int V>
+__global__ void __launch_bounds__(256)
+ttv_strided_vec_kernel(const StridedParams P)
+{
+  const T* __restrict__ A = static_cast<const T*>(P.a);
+  const T* __restrict__ B = static_cast<const T*>(P.b);
+  T* __restrict__       C = static_cast<T*>(P.c);
+  constexpr int KU = 8;
+  const uint64_t n0v = P.n[0] / V;                     // vectors along the fastest free mode (stride 1 in A and C)
+  const uint64_t total_v = P.total / V;
+
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total_v; j += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t rem = j / n0v;
+    uint64_t offa = (j - rem * n0v) * V, offc = offa;
+    for (uint32_t d = 1; d < P.nfree; ++d) {
+      const uint64_t i = rem % P.n[d];
+      rem /= P.n[d];
+      offa += i * P.wa[d];
+      offc += i * P.wc[d];
+    }
+    const T* ap = A + offa;
+    T acc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = Num<T>::zero();
+    uint64_t k = 0;
+    for (; k + KU <= P.nq; k += KU) {
+      Vec<T, V> v[KU];
+#pragma unroll
+      for (int s = 0; s < KU; ++s) v[s] = load_stream<T, V>(ap + (k + s) * P.wq);
+#pragma unroll
+      for (int s = 0; s < KU; ++s) {
+        const T bb = B[k + s];
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] = Num<T>::madd(v[s].e[e], bb, acc[e]);
+      }
+    }
+    if (k < P.nq) {                                     // last, partial batch: still all loads first
+      Vec<T, V> v[KU];
+#pragma unroll
+      for (int s = 0; s < KU; ++s)
+        if (k + s < P.nq) v[s] = load_stream<T, V>(ap + (k + s) * P.wq);
+#pragma unroll
+      for (int s = 0; s < KU; ++s)
+        if (k + s < P.nq) {
+          const T bb = B[k + s];
+#pragma unroll
+          for (int e = 0; e < V; ++e) acc[e] = Num<T>::madd(v[s].e[e], bb, acc[e]);
+        }
+    }
+    Vec<T, V>* out = reinterpret_cast<Vec<T, V>*>(C + offc);
+    Vec<T, V> r;
+    if (P.accumulate) {
+      r = *out;
+#pragma unroll
+      for (int e = 0; e < V; ++e) r.e[e] = Num<T>::add(r.e[e], acc[e]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < V; ++e) r.e[e] = acc[e];
+    }
+    *out = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // STRIDED, q contiguous (wa[q-1] == 1): the fibers are contiguous runs of n_q elements whose starts are strided
 // (rows of a matrix with a padded leading dimension, the fastest mode of a sliced tensor).  One thread per output
 // would put the lanes of a warp on 32 different fibers (measured 256^3 x 250 slice, q = 1: 1.1 TB/s).  Here a GROUP of
