@@ -17,8 +17,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gib", type=float, default=4.0)
     args = ap.parse_args()
-    n4 = int(args.gib * (1 << 30) / 4 / (256 ** 3))
-    na, pia = [256, 256, 256, n4], [1, 2, 3, 4]
+    n4 = max(2, int(args.gib * (1 << 30) / 4 / (256 * 256 * 16)))          # slabs of 4 MiB along the slowest mode
+    na, pia = [256, 256, 16, n4], [1, 2, 3, 4]
     n = int(np.prod(na))
     q = 2
     nc = ttv_b200.generate_output_shape(na, q); pic = ttv_b200.generate_output_layout(pia, q)
@@ -31,11 +31,12 @@ def main():
         else:
             ta = torch.ones(n, dtype=torch.float32).pin_memory(); a = ta.numpy()
             tc = torch.empty(n // na[q - 1], dtype=torch.float32).pin_memory(); c = tc.numpy()
-        for mode in ("default", "TTV_B200_H2D_CHUNK_MB=0"):
+        for mode in ("default", "TTV_B200_BOUNCE_ADAPT=0", "TTV_B200_H2D_CHUNK_MB=0"):
+            for key in ("TTV_B200_H2D_CHUNK_MB", "TTV_B200_BOUNCE_ADAPT"):
+                os.environ.pop(key, None)
             if mode != "default":
-                os.environ["TTV_B200_H2D_CHUNK_MB"] = "0"
-            else:
-                os.environ.pop("TTV_B200_H2D_CHUNK_MB", None)
+                key, val = mode.split("=")
+                os.environ[key] = val
             ts = []
             for _ in range(3):
                 t0 = time.perf_counter()

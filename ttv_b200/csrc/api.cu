@@ -286,8 +286,12 @@ int run_host_pipelined(int dtype, uint64_t count, const View* views, const void*
   // pageable A: smaller chunks, bounced through pinned buffers by the copy threads (memcpy of chunk i+1 overlaps the DMA
   // of chunk i); pinned A: DMA straight from the caller's buffer
   const bool bounce = !is_pinned_host(a) && env_mb("TTV_B200_BOUNCE", 1) != 0;
-  const size_t chunk_target = bounce ? std::min<size_t>((size_t)env_mb("TTV_B200_H2D_CHUNK_MB", 128), (size_t)env_mb("TTV_B200_BOUNCE_CHUNK_MB", 32)) << 20
-                                     : (size_t)env_mb("TTV_B200_H2D_CHUNK_MB", 128) << 20;
+  size_t chunk_target = bounce ? std::min<size_t>((size_t)env_mb("TTV_B200_H2D_CHUNK_MB", 128), (size_t)env_mb("TTV_B200_BOUNCE_CHUNK_MB", 32)) << 20
+                               : (size_t)env_mb("TTV_B200_H2D_CHUNK_MB", 128) << 20;
+  // Pageable tensors of a few hundred MB: with 32 MiB chunks the memcpy of the first chunk and the DMA of the last one are
+  // a large share of the whole transfer.  About 16 chunks per tensor (not below 4 MiB each) keep the pipeline full.
+  if (bounce && env_mb("TTV_B200_BOUNCE_ADAPT", 1) != 0)
+    chunk_target = std::min(chunk_target, std::max<size_t>((size_t)4 << 20, (size_t)(total * s) / 16));
   const bool debug = env_mb("TTV_B200_DEBUG", 0) != 0;
   if (debug) fprintf(stderr, "[ttv_b200] host path: total=%llu slow=%llu chunk_target=%zu count=%llu\n", (unsigned long long)total,
                      (unsigned long long)slow, chunk_target, (unsigned long long)count);
