@@ -20,15 +20,16 @@ def main():
     ap.add_argument("--ksplit", type=int, default=0)
     ap.add_argument("--kernel", default="auto")
     ap.add_argument("--launches", type=int, default=4)
+    ap.add_argument("--set", default="all", help="config family of tools/sweep.py the name comes from (pad, padv, ... are not in 'all')")
     args = ap.parse_args()
-    for name, dt, na, pia, q, *rest in sweep.configs("all"):
+    for name, dt, na, pia, q, *rest in sweep.configs(args.set):
         if name == args.cfg and q == args.q and (not args.dtype or dt == args.dtype):
             opts = {}
             if args.ksplit:
                 opts["ksplit"] = args.ksplit
             if args.kernel != "auto":
                 opts["kernel"] = args.kernel
-            r = sweep.bench_one(dt, na, pia, q, reps=max(1, args.launches - 3), **opts)
+            r = sweep.bench_one(dt, na, pia, q, reps=max(1, args.launches - 3), wa=rest[0] if rest else None, **opts)
             print(name, dt, q, r)
             return
     raise SystemExit("no such config")

@@ -90,7 +90,10 @@ class CopyPool {
   {
     auto job = std::make_shared<Job>();
     job->dst = static_cast<char*>(dst); job->src = static_cast<const char*>(src); job->bytes = bytes;
-    job->parts = (bytes + kPart - 1) / kPart;
+    // about four parts per copier, between 64 KiB and 2 MiB each: a chunk of a few MiB still gets every thread
+    const size_t copiers = workers_.size() + 1;
+    job->part = std::min(kPart, std::max<size_t>((size_t)64 << 10, (bytes / (4 * copiers) + 4095) / 4096 * 4096));
+    job->parts = (bytes + job->part - 1) / job->part;
     job->remaining.store(job->parts);
     if (job->parts == 0) return;
     { std::lock_guard<std::mutex> lk(m_); cur_ = job; ++generation_; }
@@ -103,7 +106,7 @@ class CopyPool {
  private:
   static constexpr size_t kPart = 2u << 20;
   struct Job {
-    char* dst = nullptr; const char* src = nullptr; size_t bytes = 0, parts = 0;
+    char* dst = nullptr; const char* src = nullptr; size_t bytes = 0, parts = 0, part = kPart;
     std::atomic<size_t> next{0}, remaining{0};
   };
   void work(Job& j)
@@ -111,8 +114,8 @@ class CopyPool {
     for (;;) {
       const size_t i = j.next.fetch_add(1);
       if (i >= j.parts) return;
-      const size_t off = i * kPart;
-      std::memcpy(j.dst + off, j.src + off, std::min(kPart, j.bytes - off));
+      const size_t off = i * j.part;
+      std::memcpy(j.dst + off, j.src + off, std::min(j.part, j.bytes - off));
       if (j.remaining.fetch_sub(1) == 1) { std::lock_guard<std::mutex> lk(m_); done_.notify_all(); }
     }
   }

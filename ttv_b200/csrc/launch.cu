@@ -372,10 +372,12 @@ static int strided_form_forced()
 }
 
 template<int V>
-static cudaError_t launch_strided_vec(const StridedParams& S, int sm_count, cudaStream_t stream)
+static cudaError_t launch_strided_vec(StridedParams S, int sm_count, cudaStream_t stream)
 {
   if constexpr (V <= kVmax) {                           // (wider vectors than 16 bytes are never instantiated)
-    const uint64_t blocks = std::max<uint64_t>(1, std::min<uint64_t>((S.total / (uint64_t)V + 255) / 256, (uint64_t)sm_count * 32));
+    S.n0p = (S.n[0] / (uint64_t)V + 31) / 32 * 32;      // whole warps per row
+    const uint64_t lanes = (S.total / S.n[0]) * S.n0p;
+    const uint64_t blocks = std::max<uint64_t>(1, std::min<uint64_t>((lanes + 255) / 256, (uint64_t)sm_count * 32));
     ttv_strided_vec_kernel<elem_t, V><<<(unsigned)blocks, 256, 0, stream>>>(S);
     count_launch();
     return cudaGetLastError();
@@ -417,11 +419,12 @@ cudaError_t TTVB_CAT(strided_dtype_, TTVB_DTYPE)(const StridedParams& S, int sm_
     uint64_t align = (addr % sizeof(elem_t)) ? 1 : (uint64_t)(addr / sizeof(elem_t));
     align |= S.n[0] | S.wq;
     for (uint32_t d = 1; d < S.nfree; ++d) align |= S.wa[d] | S.wc[d];
-    // Measured (profiles/r01_padded_strides.txt, session 4): 16-byte vectors of 4-byte elements gain 7-12 % when a warp's
-    // 32 vectors never straddle two rows (slices of a 256^4 fp32 tensor that leave the rows whole: 6.2-6.4 -> 6.8-6.9 TB/s);
-    // on rows that are cut short (248 of 256 floats, 120 of 128 doubles) the vector form LOSES 5-9 %, and 8-byte elements
-    // gain nothing either way -- their thread-per-output loop is not issue-bound.  So: 4-byte elements, whole warps per row.
-    const bool pays = kVmax == 4 && S.n[0] % 128 == 0 && S.total / 4 >= (uint64_t)sm_count * 2048;
+    // Measured (profiles/r01_padded_strides.txt, session 4): 16-byte vectors of 4-byte elements gain 7-12 % over the
+    // thread-per-output form (slices of a 256^4 fp32 tensor: 6.2-6.4 -> 6.8-6.9 TB/s) as long as rows come in whole warps
+    // (see strided_kernel.cuh); 8-byte elements gain nothing either way -- their thread-per-output loop is not
+    // issue-bound.  So: 4-byte elements, at most 1/8 of the lanes idle, enough rows to fill the machine.
+    const uint64_t n0v = S.n[0] / 4, n0p = (n0v + 31) / 32 * 32;
+    const bool pays = kVmax == 4 && (n0p - n0v) * 8 <= n0p && S.total / 4 >= (uint64_t)sm_count * 2048;
     if (align % kVmax == 0 && (pays || forced == 2)) return launch_strided_vec<kVmax>(S, sm_count, stream);
     if (forced == 2 && kVmax >= 4 && align % 2 == 0) return launch_strided_vec<2>(S, sm_count, stream);
   }
