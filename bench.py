@@ -183,7 +183,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": round(m["gbs"], 2), "unit": "GB/s", "cores": m["cores"], "kind": m["kind"], "sample": sample},
             "e2e": {"value": round(m["gbs"], 2), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gflops": round(2 * EXT ** 3 * last * 4 / m["seconds_per_step"] / 1e9, 2)}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -358,7 +358,7 @@ def run_own_arm(args):
                 "frac_of_measured_peak": round(value / (peak * world), 4),
                 "frac_of_nominal_8000": round(value / (8000.0 * world), 4),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -497,7 +497,30 @@ def measure_e2e(torch, dist, ttv_b200, args, a, bs, cs, shards, na_global, pia, 
     return out
 
 
+_JSON_FD = None
+
+
+def _guard_stdout():
+    """Libraries print to the process's stdout behind Python's back (NCCL's version banner at NCCL_DEBUG=VERSION/WARN,
+    torchrun notices).  The contract is ONE JSON line on stdout: keep a private duplicate of fd 1 for that line and point
+    fd 1 itself at stderr for everything else."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
     ap.add_argument("--steps", type=int, default=20)
