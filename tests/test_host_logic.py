@@ -331,3 +331,25 @@ def test_layout_and_strides_of_numpy_arrays():
     assert _layout_of(np.broadcast_to(np.zeros(6), (4, 5, 6)), None) is None           # broadcast axes: copy
     pia, wa, honor = _layout_of(np.zeros((4, 1, 6)), None)
     assert ttv_b200.is_valid_strides(pia, wa) and not honor
+
+
+def test_bench_stdout_carries_only_the_json_line():
+    """bench.py's contract is ONE JSON line on stdout; libraries that write to fd 1 behind Python's back (NCCL's version
+    banner did at N = 2) must end up on stderr"""
+    import subprocess
+    import sys
+    code = (
+        "import sys, ctypes\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import bench\n"
+        "bench._guard_stdout()\n"
+        "libc = ctypes.CDLL(None)\n"
+        "libc.puts(b'NCCL version x.y.z')\n"
+        "libc.fflush(None)\n"
+        "print('a python print')\n"
+        "bench.emit({'metric': 'm', 'value': 1.5})\n"
+    )
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout == '{"metric": "m", "value": 1.5}\n', r.stdout
+    assert "NCCL version x.y.z" in r.stderr and "a python print" in r.stderr

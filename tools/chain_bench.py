@@ -4,16 +4,15 @@ reference's binding (ttvpy/src/wrapped_ttv.cpp:83-198).
 
   device   A and the vectors resident in HBM, intermediates stay there; CUDA events around the whole chain
   host     numpy in, numpy out: A crosses PCIe once, only the final vector comes back
-  ref      the reference's own compiled module (oracle/_ref/ttvpy_ref*.so, OpenMP, no BLAS) on the host cores
+  (the reference module's own timings on the host cores -- profiles/r01_ttvs_chain.txt, first block -- were taken once by
+   tests/chain_reference_timing.py; nothing under oracle/ is touched from here)
 
 GB/s = sum over the p-1 steps of the algorithmic bytes of that step (tensor + vector + result) / time.
-    python tools/chain_bench.py [--shape 256,256,256,128] [--reps 5] [--no-ref]
+    python tools/chain_bench.py [--shape 256,256,256,128] [--reps 5]
 """
 from __future__ import annotations
 
 import argparse
-import importlib.util
-import glob
 import json
 import os
 import sys
@@ -40,24 +39,11 @@ def chain_bytes(q, shape, order, item=8):
     return total
 
 
-def load_reference():
-    cands = glob.glob(os.path.join(ROOT, "oracle", "_ref", "ttvpy_ref*.so"))
-    if not cands:
-        return None
-    spec = importlib.util.spec_from_file_location("ttvpy_ref", cands[0])
-    try:
-        mod = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(mod)
-        return mod
-    except Exception:
-        return None
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--shape", default="256,256,256,128")
     ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--no-ref", action="store_true")
+    ap.add_argument("--no-ref", action="store_true", help="accepted for old command lines; there is no reference leg any more")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "chain.jsonl"))
     args = ap.parse_args()
     shape = [int(x) for x in args.shape.split(",")]
@@ -67,7 +53,6 @@ def main():
     ttv_b200.fill(dev, 0x77170001)
     A_dev = dev.view(*shape)
     A_host = A_dev.cpu().numpy()
-    ref = None if args.no_ref else load_reference()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "a") as f:
         for q in (1, p):
@@ -100,11 +85,6 @@ def main():
                 rec.update(ms_graph=ms_graph, gbs_graph=byt / ms_graph / 1e6,
                            graph_matches=bool(torch.equal(plan.result, ttvpy.ttvs(q, A_dev, vec_dev, order))))
                 del plan
-                if ref is not None:
-                    ref.ttvs(q, A_host, vec_host, order)                         # warm-up (thread pool, page faults)
-                    t0 = time.perf_counter(); want = ref.ttvs(q, A_host, vec_host, order); ms_ref = (time.perf_counter() - t0) * 1e3
-                    rec.update(ms_ref=ms_ref, gbs_ref=byt / ms_ref / 1e6, cores=os.cpu_count(),
-                               max_rel_diff=float(np.max(np.abs(got - want)) / max(1e-300, np.max(np.abs(want)))))
                 print(json.dumps(rec), flush=True)
                 f.write(json.dumps(rec) + "\n")
 
