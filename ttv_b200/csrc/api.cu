@@ -71,6 +71,10 @@ struct DeviceState {
   // pageable host memory: pinned bounce buffers, one per ring slot, filled by the copy threads
   void*  bounce[3] = {nullptr, nullptr, nullptr};
   size_t bounce_bytes = 0;
+  // ... and the way back: chunks of C on their way into pageable host memory
+  void*  bounce_out[3] = {nullptr, nullptr, nullptr};
+  size_t bounce_out_bytes = 0;
+  cudaEvent_t out_done[3] = {nullptr, nullptr, nullptr};
   // stream-ordered pool for the intermediates of a chain of products (ttv_b200_ttvs)
   cudaMemPool_t pool = nullptr;
 };
@@ -88,6 +92,7 @@ class CopyPool {
   }
   void copy(void* dst, const void* src, size_t bytes)
   {
+    if (bytes <= ((size_t)256 << 10)) { std::memcpy(dst, src, bytes); return; }   // not worth waking anybody
     auto job = std::make_shared<Job>();
     job->dst = static_cast<char*>(dst); job->src = static_cast<const char*>(src); job->bytes = bytes;
     // about four parts per copier, between 64 KiB and 2 MiB each: a chunk of a few MiB still gets every thread
@@ -323,6 +328,19 @@ int run_host_pipelined(int dtype, uint64_t count, const View* views, const void*
     max_b = std::max(max_b, ((size_t)views[i].nq * s + 255) / 256 * 256);
     sum_c += ((size_t)(views[i].outer * views[i].inner) * s + 255) / 256 * 256;
   }
+  // Results of free-split products that go to PAGEABLE memory leave chunk by chunk through pinned buffers too: one D2H of
+  // the whole C into pageable memory at the end runs at ~11 GB/s on these hosts, and with a short contraction (n_q = 2..16)
+  // C is a large fraction of A.  The copy threads move chunk ch-3 of C to the caller's array before slot r is reused.
+  std::vector<char> c_pinned(count), c_bounce(count, 0);
+  std::vector<size_t> out_off(count, 0);
+  size_t out_chunk_bytes = 0;
+  for (uint64_t i = 0; i < count; ++i) {
+    c_pinned[i] = (!bc_dev && is_pinned_host(c[i])) ? 1 : 0;
+    if (bc_dev || c_pinned[i] || views[i].outer == 1 || env_mb("TTV_B200_BOUNCE", 1) == 0 || env_mb("TTV_B200_BOUNCE_OUT", 1) == 0) continue;
+    c_bounce[i] = 1;
+    out_off[i] = out_chunk_bytes;
+    out_chunk_bytes += ((size_t)(per * (views[i].outer / slow) * views[i].inner) * s + 255) / 256 * 256;
+  }
   {
     std::lock_guard<std::mutex> lock(g_mutex);
     if (int rc = device_state(device, &st)) return rc;
@@ -341,17 +359,36 @@ int run_host_pipelined(int dtype, uint64_t count, const View* views, const void*
       }
       st->bounce_bytes = chunk_bytes;
     }
+    if (out_chunk_bytes) {
+      for (int r = 0; r < 3; ++r)
+        if (!st->out_done[r]) CUDA_TRY(cudaEventCreateWithFlags(&st->out_done[r], cudaEventDisableTiming), "cudaEventCreate");
+      if (st->bounce_out_bytes < out_chunk_bytes) {
+        for (int r = 0; r < 3; ++r) {
+          if (st->bounce_out[r]) { cudaFreeHost(st->bounce_out[r]); st->bounce_out[r] = nullptr; }
+          st->bounce_out_bytes = 0;
+          CUDA_TRY(cudaHostAlloc(&st->bounce_out[r], out_chunk_bytes, cudaHostAllocDefault), "cudaHostAlloc");
+        }
+        st->bounce_out_bytes = out_chunk_bytes;
+      }
+    }
     if (!bc_dev) {
       if (int rc = ensure(st->stage_b, max_b * count)) return rc;
       if (int rc = ensure(st->stage_c, sum_c)) return rc;
       db_ = static_cast<char*>(st->stage_b.ptr); dc_ = static_cast<char*>(st->stage_c.ptr);
     }
   }
+  struct Piece { char* dst; const char* src; size_t bytes; };
+  std::vector<Piece> pending[3];                        // chunks of C sitting in bounce_out[r], D2H queued behind out_done[r]
+  auto drain = [&](int r) -> int {
+    if (pending[r].empty()) return TTV_B200_OK;
+    CUDA_TRY(cudaEventSynchronize(st->out_done[r]), "cudaEventSynchronize");
+    for (const Piece& pc : pending[r]) copy_pool().copy(pc.dst, pc.src, pc.bytes);
+    pending[r].clear();
+    return TTV_B200_OK;
+  };
   // the vectors (and C when it is accumulated into) go first, on the compute stream
   std::vector<char*> dci(count);
   std::vector<const char*> dbi(count);
-  std::vector<char> c_pinned(count);
-  for (uint64_t i = 0; i < count; ++i) c_pinned[i] = (!bc_dev && is_pinned_host(c[i])) ? 1 : 0;
   size_t coff = 0;
   for (uint64_t i = 0; i < count; ++i) {
     if (bc_dev) { dci[i] = static_cast<char*>(c[i]); dbi[i] = static_cast<const char*>(b[i]); continue; }
@@ -371,6 +408,7 @@ int run_host_pipelined(int dtype, uint64_t count, const View* views, const void*
     const int r = (int)(ch % 3);
     const uint64_t s0 = ch * per, s1 = std::min(slow, s0 + per), ns = s1 - s0;
     if (ch >= 3) CUDA_TRY(cudaStreamWaitEvent(st->copy_stream, st->freed[r], 0), "cudaStreamWaitEvent");
+    if (int rc = drain(r)) return rc;                   // chunk ch-3 of C leaves bounce_out[r] before it is refilled
     const char* src = ah + (size_t)(s0 * slab) * s;
     if (bounce) {
       // bounce[r] was last read by the DMA of chunk ch-3, whose completion is ready[r]
@@ -404,14 +442,22 @@ int run_host_pipelined(int dtype, uint64_t count, const View* views, const void*
         const size_t bytes = (size_t)(v.outer * v.inner) * s;
         CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(c[i]) + (cdst - dci[i]), cdst, bytes, cudaMemcpyDeviceToHost, stream),
                  "cudaMemcpyAsync D2H C chunk");
+      } else if (!nq_split && c_bounce[i]) {
+        const size_t bytes = (size_t)(v.outer * v.inner) * s;
+        char* hb = static_cast<char*>(st->bounce_out[r]) + out_off[i];
+        CUDA_TRY(cudaMemcpyAsync(hb, cdst, bytes, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync D2H C chunk (bounce)");
+        pending[r].push_back(Piece{static_cast<char*>(c[i]) + (cdst - dci[i]), hb, bytes});
       }
     }
+    if (!pending[r].empty()) CUDA_TRY(cudaEventRecord(st->out_done[r], stream), "cudaEventRecord");
     CUDA_TRY(cudaEventRecord(st->freed[r], stream), "cudaEventRecord");
   }
   for (uint64_t i = 0; i < count && !bc_dev; ++i)
-    if (views[i].outer == 1 || !c_pinned[i])
+    if (views[i].outer == 1 || (!c_pinned[i] && !c_bounce[i]))
       CUDA_TRY(cudaMemcpyAsync(c[i], dci[i], (size_t)(views[i].outer * views[i].inner) * s, cudaMemcpyDeviceToHost, stream),
                "cudaMemcpyAsync D2H C");
+  for (uint64_t ch = chunks > 3 ? chunks - 3 : 0; ch < chunks; ++ch)      // the last chunks of C, oldest first
+    if (int rc = drain((int)(ch % 3))) return rc;
   CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
   return TTV_B200_OK;
 }
@@ -975,10 +1021,13 @@ void ttv_b200_release(void)
       if (b->ptr) { cudaFree(b->ptr); b->ptr = nullptr; b->bytes = 0; }
     for (int r = 0; r < 3; ++r) {
       if (st.bounce[r]) { cudaFreeHost(st.bounce[r]); st.bounce[r] = nullptr; }
+      if (st.bounce_out[r]) { cudaFreeHost(st.bounce_out[r]); st.bounce_out[r] = nullptr; }
+      if (st.out_done[r]) { cudaEventDestroy(st.out_done[r]); st.out_done[r] = nullptr; }
       if (st.ready[r]) { cudaEventDestroy(st.ready[r]); st.ready[r] = nullptr; }
       if (st.freed[r]) { cudaEventDestroy(st.freed[r]); st.freed[r] = nullptr; }
     }
     st.bounce_bytes = 0;
+    st.bounce_out_bytes = 0;
     if (st.copy_stream) { cudaStreamDestroy(st.copy_stream); st.copy_stream = nullptr; }
     if (st.pool) cudaMemPoolTrimTo(st.pool, 0);
     cudaGetLastError();
