@@ -551,6 +551,43 @@ def test_padded_tensors_with_aligned_rows_take_vector_loads(dtype, monkeypatch):
         assert np.all(c[~touched] == 55)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.int32, np.float64, np.complex64])
+def test_sliced_arrays_fuzz_both_general_stride_forms(dtype, monkeypatch):
+    """seeded fuzz over slices of C-contiguous arrays (order 3..5, random cuts on every axis, the contiguous axis cut at
+    multiples of the vector or anywhere), every q except the contiguous axis, host arrays and device tensors: the vector
+    form forced (TTV_B200_STRIDED_SCALAR=2, falls back by itself where alignment forbids it), the thread-per-output form
+    forced (=1) and the default rule must all give np.tensordot's result"""
+    import torch
+    rng = np.random.default_rng(20261017)
+    for trial in range(24):
+        p = int(rng.integers(3, 6))
+        full = [int(rng.choice([3, 4, 6, 9, 12])) for _ in range(p - 1)] + [int(rng.choice([16, 36, 64, 132, 200]))]
+        base = rng.integers(-8, 9, full).astype(dtype)
+        if np.dtype(dtype).kind == "c":
+            base = (base + 1j * rng.integers(-8, 9, full)).astype(dtype)
+        cuts = []
+        for ax, n in enumerate(full):
+            if ax == p - 1:
+                step = 4 if trial % 3 else 1                   # two trials out of three keep the rows vector-aligned
+                lo = int(rng.integers(0, n // (2 * step))) * step
+                hi = lo + max(step, int(rng.integers(1, (n - lo) // step + 1)) * step)
+            else:
+                lo = int(rng.integers(0, max(1, n // 2)))
+                hi = int(rng.integers(lo + 1, n + 1))
+            cuts.append(slice(lo, hi))
+        x = base[tuple(cuts)]
+        tx = torch.from_numpy(base).cuda()[tuple(cuts)]
+        for q in range(1, p):
+            b = rng.integers(-8, 9, x.shape[q - 1]).astype(dtype)
+            want = np.tensordot(x, b, axes=([q - 1], [0]))
+            for form in ("2", "1", "0"):
+                monkeypatch.setenv("TTV_B200_STRIDED_SCALAR", form)
+                got = ttv_b200.ttv(q, x, b)
+                assert got.shape == want.shape and np.array_equal(got, want), (full, cuts, q, form, "host")
+                tg = ttv_b200.ttv(q, tx, torch.from_numpy(b).cuda())
+                assert np.array_equal(tg.cpu().numpy(), want), (full, cuts, q, form, "device")
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int64])
 def test_arrays_that_are_not_contiguous_are_read_in_place(dtype):
     """numpy / torch front end: transposes, slices and strided views for EVERY q -- also the cases
