@@ -260,9 +260,41 @@ static unsigned stream_conflict_degree(uint64_t M, uint64_t inner, uint64_t s)
   return worst;
 }
 
+// Experiment switches (TTV_B200_*) are read on every call so that a running process can flip them -- but one getenv per
+// switch is ~30 scans of the environment per plan (2-3 us, as much as the launch itself).  choose_launch scans the
+// environment ONCE, keeps the TTV_B200_ entries (normally none) and env_int looks names up in that short list.
+extern "C" char** environ;
+
+namespace {
+struct EnvScan {
+  static constexpr int kMax = 48;
+  const char* entry[kMax];
+  int n = 0;
+  EnvScan()
+  {
+    for (char** e = environ; e && *e; ++e)
+      if (std::strncmp(*e, "TTV_B200_", 9) == 0 && n < kMax) entry[n++] = *e;
+  }
+  const char* find(const char* name) const
+  {
+    const size_t len = std::strlen(name);
+    for (int i = 0; i < n; ++i)
+      if (std::strncmp(entry[i], name, len) == 0 && entry[i][len] == '=') return entry[i] + len + 1;
+    return nullptr;
+  }
+};
+thread_local const EnvScan* t_env = nullptr;
+struct EnvScope {
+  EnvScan scan;
+  const EnvScan* prev;
+  EnvScope() : prev(t_env) { t_env = &scan; }
+  ~EnvScope() { t_env = prev; }
+};
+} // namespace
+
 static int env_int(const char* name, int fallback)
 {
-  const char* s = std::getenv(name);
+  const char* s = t_env ? t_env->find(name) : std::getenv(name);
   return (s && *s) ? std::atoi(s) : fallback;
 }
 
@@ -379,6 +411,7 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
   if (s == 0) return TTV_B200_ERR_DTYPE;
   if (sm_count <= 0) sm_count = 148;
   const uint64_t sms = (uint64_t)sm_count;
+  const EnvScope env_scope;                       // one scan of the environment for all the switches below
   const uint32_t flags = opts ? opts->flags : 0u;
   int forced = opts ? opts->kernel : 0;
   if (forced < 0 || forced >= TTV_B200_KERNEL_COUNT) return TTV_B200_ERR_OPTS;
