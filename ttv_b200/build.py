@@ -26,7 +26,7 @@ COMMON = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-O3,-Wal
 
 def units():
     """(source, object, extra flags)"""
-    out = [("api.cu", "api.o", []), ("plan.cpp", "plan.o", []), ("launch.cu", "launch.o", [])]
+    out = [("api.cu", "api.o", []), ("plan.cpp", "plan.o", []), ("hostcopy.cpp", "hostcopy.o", []), ("launch.cu", "launch.o", [])]
     out += [("launch.cu", f"launch_dtype{k}.o", [f"-DTTVB_DTYPE={k}"]) for k in range(N_DTYPES)]
     return out
 
@@ -42,7 +42,7 @@ def stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in ["api.cu", "plan.cpp", "launch.cu"] + HEADERS] + [os.path.abspath(__file__)]
+    deps = [os.path.join(CSRC, f) for f in ["api.cu", "plan.cpp", "hostcopy.cpp", "launch.cu"] + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -23,6 +23,8 @@
 
 using namespace ttvb;
 
+namespace ttvb { void host_copy(void* dst, const void* src, size_t bytes); }   // hostcopy.cpp: memcpy with streaming stores
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -120,7 +122,7 @@ class CopyPool {
       const size_t i = j.next.fetch_add(1);
       if (i >= j.parts) return;
       const size_t off = i * j.part;
-      std::memcpy(j.dst + off, j.src + off, std::min(j.part, j.bytes - off));
+      host_copy(j.dst + off, j.src + off, std::min(j.part, j.bytes - off));
       if (j.remaining.fetch_sub(1) == 1) { std::lock_guard<std::mutex> lk(m_); done_.notify_all(); }
     }
   }
