@@ -38,3 +38,25 @@ def test_host_copy_ragged_sizes_and_alignments(host_copy):
                 host_copy(dst_buf.ctypes.data + 64 + do, src_buf.ctypes.data + so, n)
                 assert np.array_equal(dst_buf[64 + do: 64 + do + n], src_buf[so: so + n]), (n, so, do)
                 assert np.all(dst_buf[: 64 + do] == 0xAB) and np.all(dst_buf[64 + do + n:] == 0xAB), ("wrote outside", n, so, do)
+
+
+@pytest.mark.parametrize("tsan", [False, True])
+def test_copy_pool_with_concurrent_callers(tsan):
+    """ttv_b200/csrc/copy_pool.h under several concurrent callers (tests/copy_pool_harness.cpp); the second build runs
+    under ThreadSanitizer, which must report no data race"""
+    exe = os.path.join(ROOT, "tests", "_refbin", "copy_pool_harness" + ("_tsan" if tsan else ""))
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    env = dict(os.environ); env.pop("CC", None); env.pop("CXX", None)
+    cmd = ["g++", "-O1" if tsan else "-O2", "-g", "-std=c++17", "-pthread", os.path.join(ROOT, "tests", "copy_pool_harness.cpp"), SRC, "-o", exe]
+    if tsan:
+        cmd.insert(1, "-fsanitize=thread")
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if tsan and r.returncode != 0 and "tsan" in (r.stderr + r.stdout).lower():
+        pytest.skip("ThreadSanitizer runtime is not installed")
+    assert r.returncode == 0, r.stderr[-3000:]
+    args = ["3", "5", "12"] if tsan else ["4", "7", "40"]
+    r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600)
+    if tsan and "FATAL: ThreadSanitizer" in r.stderr:      # e.g. an address-space layout TSan cannot map in this container
+        pytest.skip("ThreadSanitizer cannot run here: " + r.stderr.splitlines()[0])
+    assert r.returncode == 0 and " 0 bad" in r.stdout, r.stdout + r.stderr[-3000:]
+    assert "WARNING: ThreadSanitizer" not in r.stderr, r.stderr[-4000:]

@@ -17,7 +17,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(PKG, "libttv_b200.so")
-HEADERS = ["plan.h", "launch.h", "kernels.cuh", "stream_kernel.cuh", "colx_kernel.cuh", "colr_kernel.cuh", "dotf_kernel.cuh", "strided_kernel.cuh", "numeric.cuh", os.path.join("..", "..", "include", "ttv_b200.h")]
+HEADERS = ["plan.h", "launch.h", "copy_pool.h", "kernels.cuh", "stream_kernel.cuh", "colx_kernel.cuh", "colr_kernel.cuh", "dotf_kernel.cuh", "strided_kernel.cuh", "numeric.cuh", os.path.join("..", "..", "include", "ttv_b200.h")]
 N_DTYPES = 6
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
