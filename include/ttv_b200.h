@@ -255,7 +255,8 @@ int         ttv_b200_version(void);
 int         ttv_b200_device_count(void);       /* 0 when no usable CUDA device */
 uint64_t    ttv_b200_launch_count(void);       /* kernels launched by this library in this process */
 int         ttv_b200_dtype_size(int dtype);
-void        ttv_b200_release(void);            /* waits for queued work, frees workspaces / staging buffers / copy stream */
+void        ttv_b200_release(void);            /* waits for queued work, frees workspaces / staging buffers / copy stream;
+                                                  call it while no other entry point is running on another thread */
 
 #ifdef __cplusplus
 }
