@@ -143,3 +143,33 @@ def test_fold_matches_memory_order(oracle):
             view = a.reshape(outer, nq, inner)
             expect = np.einsum("okj,k->oj", view, b).reshape(-1)
             assert np.array_equal(oracle.ttv(q, a, na, pia, b), expect)
+
+
+# ---- 5. the chain of p-1 products (ttvpy::ttvs) ---------------------------------------------------------------------------
+def test_chain_schedule_with_the_oracle_reproduces_the_reference_module(oracle):
+    """The schedule ttv_b200_ttvs follows (ttv_b200_chain_plan, pure host code) executed step by step with the ORACLE's
+    ttv on last-order tensors must reproduce what the reference's own compiled module returned for ttvs(q, A, bs, order)
+    -- tests/golden/ttvpy_golden.npz -- for all three orders (wrapped_ttv.cpp:135-192): pins the schedule on the CPU."""
+    import ttv_b200
+    from ttv_b200 import api
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ttvpy_golden.npz")
+    g = np.load(path, allow_pickle=False)
+    checked = 0
+    for m in range(int(g["count"])):
+        A, q = g[f"ttv_A_{m}"], int(g[f"ttv_q_{m}"])
+        p = A.ndim
+        if p < 2:
+            continue
+        bs = [g[f"ttvs_b_{m}_{j}"] for j in range(p - 1)]
+        for order in ("forward", "backward", "optimal"):
+            cur, shape = np.ascontiguousarray(A).reshape(-1), list(A.shape)
+            for mode, j in api.chain_plan(q, list(A.shape), order):
+                pia = list(range(len(shape), 0, -1))                    # C-contiguous = last-order
+                cur = oracle.ttv(mode, cur, shape, pia, np.ascontiguousarray(bs[j], dtype=cur.dtype))
+                del shape[mode - 1]
+            want = g[f"ttvs_C_{m}_{order}"]
+            assert cur.shape == want.reshape(-1).shape, (m, order)
+            # the fixtures hold small integers in float64: every summation order is exact
+            assert np.array_equal(cur, want.reshape(-1)), (m, q, order)
+            checked += 1
+    assert checked >= 30
