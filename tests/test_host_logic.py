@@ -353,3 +353,25 @@ def test_bench_stdout_carries_only_the_json_line():
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout == '{"metric": "m", "value": 1.5}\n', r.stdout
     assert "NCCL version x.y.z" in r.stderr and "a python print" in r.stderr
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's own CPU implementation, oracle/_ref or the oracle port) needs no GPU:
+    one JSON line with the keys the driver reads.  Needs ~17 GiB of host memory for the 256^4 fp32 tensor."""
+    import json
+    import subprocess
+    import sys
+    import psutil
+    if psutil.virtual_memory().available < 24 * 2 ** 30:
+        pytest.skip("not enough free host memory for the 16 GiB workload")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[:2000]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "TTV effective HBM GB/s" and d["unit"] == "GB/s" and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "256" in d["config"]["workload"] and "model" not in d["config"]
