@@ -375,3 +375,22 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "256" in d["config"]["workload"] and "model" not in d["config"]
+
+
+def test_bench_reference_arm_under_torchrun_prints_once():
+    """launched the way the driver launches N > 1 (one rank per GPU): rank 0 alone runs the CPU arm and prints the line,
+    the other rank exits 0 without work"""
+    import json
+    import subprocess
+    import sys
+    import psutil
+    if psutil.virtual_memory().available < 24 * 2 ** 30:
+        pytest.skip("not enough free host memory for the 16 GiB workload")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29579", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1, r.stdout[:2000]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 0
