@@ -394,3 +394,15 @@ def test_bench_reference_arm_under_torchrun_prints_once():
     assert len(lines) == 1, r.stdout[:2000]
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_bench_own_arm_fails_loudly_without_a_gpu():
+    """no CPU fallback: without a CUDA device the product arm of bench.py must refuse to run, not print a number"""
+    import subprocess
+    import sys
+    if ttv_b200.device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
+                       timeout=600, cwd=ROOT)
+    assert r.returncode != 0
+    assert "no CPU fallback" in (r.stderr + r.stdout) and not any(l.startswith("{") for l in r.stdout.splitlines())
