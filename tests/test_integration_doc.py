@@ -1,0 +1,95 @@
+"""INTEGRATION.md section 2 shows the tag and the overload a maintainer of bassoy/ttv would add to route the reference's
+own low-level interface into the C-ABI shim.  This test takes that code FROM THE DOCUMENT, compiles it against the
+UNMODIFIED reference headers (in place under /root/reference, nothing is copied) and this repo's include/ttv_b200.h, links
+libttv_b200.so and calls tlib::ttv::ttv(execution_policy::b200, ...).  Without a GPU the call must surface the shim's
+"no CPU fallback" error as the reference's std::runtime_error -- which proves the call went through the shim."""
+from __future__ import annotations
+
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_INC = "/root/reference/include"
+
+MAIN = r'''
+#include <cstdio>
+#include <numeric>
+#include <vector>
+int main()
+{
+  std::vector<float> a(24), b(3, 1.0f), c(8, 0.0f);
+  std::iota(a.begin(), a.end(), 1.0f);
+  std::size_t na[] = {4, 3, 2}, wa[] = {1, 4, 12}, pia[] = {1, 2, 3}, nb[] = {3}, nc[] = {4, 2}, wc[] = {1, 4}, pic[] = {1, 2};
+  try {
+    tlib::ttv::ttv(tlib::ttv::execution_policy::b200, tlib::ttv::slicing_policy::subtensor, tlib::ttv::fusion_policy::all,
+                   std::size_t(2), std::size_t(3), a.data(), na, wa, pia, b.data(), nb, c.data(), nc, wc, pic);
+    std::printf("RESULT:");
+    for (float x : c) std::printf(" %g", x);
+    std::printf("\n");
+  } catch (std::runtime_error const& e) {
+    std::printf("EXC: %s\n", e.what());
+  }
+  // an invalid argument is reported with the reference's own text, through the same route
+  try {
+    tlib::ttv::ttv(tlib::ttv::execution_policy::b200, tlib::ttv::slicing_policy::subtensor, tlib::ttv::fusion_policy::all,
+                   std::size_t(4), std::size_t(3), a.data(), na, wa, pia, b.data(), nb, c.data(), nc, wc, pic);
+  } catch (std::runtime_error const& e) {
+    std::printf("EXC2: %s\n", e.what());
+  }
+  return 0;
+}
+'''
+
+
+def test_upstream_snippet_of_integration_md_compiles_and_routes_to_the_shim(tmp_path):
+    if not os.path.isdir(REF_INC):
+        pytest.skip("the reference tree is not present on this box")
+    import ttv_b200
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    section = doc[doc.index("## 2."):doc.index("## 3.")]
+    code = re.search(r"```cpp\n(.*?)```", section, flags=re.S).group(1)
+    marker = "// include/tlib/detail/tensor_times_vector.h"
+    assert marker in code and "// include/tlib/detail/tags.h" in code
+    tag_part, overload_part = code[:code.index(marker)], code[code.index(marker):]
+    tu = "\n".join([
+        "#include <complex>", "#include <type_traits>", "#include <stdexcept>",
+        "#include <tlib/detail/tags.h>                  // the reference's, unmodified",
+        tag_part,
+        "#include <tlib/detail/tensor_times_vector.h>   // the reference's overloads",
+        overload_part,
+        "#include <tlib/ttv.h>                          // the reference's public interface: its call now finds the new overload",
+        MAIN])
+    src = tmp_path / "upstream_snippet.cpp"
+    src.write_text(tu)
+    exe = tmp_path / "upstream_snippet"
+    libdir = os.path.join(ROOT, "ttv_b200")
+    env = dict(os.environ); env.pop("CC", None); env.pop("CXX", None)
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-DNDEBUG", f"-I{REF_INC}", f"-I{os.path.join(ROOT, 'include')}", str(src), "-o", str(exe),
+                        f"-L{libdir}", "-lttv_b200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr[-4000:]
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    if ttv_b200.device_count() > 0:
+        assert "RESULT: 15 18 21 24 51 54 57 60" in r.stdout, r.stdout        # example/interface3.cpp's known answer
+    else:
+        assert "EXC: Error in ttv_b200: CUDA failure (no CPU fallback exists)." in r.stdout, r.stdout
+    assert "EXC2: Error in tlib::tensor_times_vector: contraction mode should be greater zero or less than or equal to p." in r.stdout, r.stdout
+
+
+def test_ctypes_stub_of_integration_md_calls_the_library():
+    """section 4's ctypes stub, taken from the document: argument marshalling must be accepted by the library (without a
+    GPU the call returns status 40 = no CPU fallback; the value check of the stub itself runs where a GPU exists)"""
+    import sys
+    import ttv_b200
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    section = doc[doc.index("## 4."):doc.index("## 5.")]
+    code = re.search(r"```python\n(.*?)```", section, flags=re.S).group(1)
+    lines = code.rstrip().splitlines()
+    assert lines[-1].startswith("assert st == 0")
+    if ttv_b200.device_count() == 0:
+        lines[-1] = "assert st == 40, st"
+    r = subprocess.run([sys.executable, "-c", "\n".join(lines)], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
