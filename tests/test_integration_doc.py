@@ -93,3 +93,68 @@ def test_ctypes_stub_of_integration_md_calls_the_library():
         lines[-1] = "assert st == 40, st"
     r = subprocess.run([sys.executable, "-c", "\n".join(lines)], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_pybind_snippets_of_integration_md_build_inside_the_reference_binding(tmp_path):
+    """section 3: the two replacements shown for ttvpy/src/wrapped_ttv.cpp are applied to a scratch copy of that file
+    (outside the repo), the module is built with pybind11 against the unmodified reference headers and libttv_b200.so, and
+    both functions are called: without a GPU they must raise the shim's error as the binding's ValueError"""
+    import sys
+    import sysconfig
+    ref_src = "/root/reference/ttvpy/src/wrapped_ttv.cpp"
+    if not os.path.exists(ref_src):
+        pytest.skip("the reference tree is not present on this box")
+    try:
+        import pybind11
+    except ImportError:
+        pytest.skip("pybind11 is not installed")
+    import ttv_b200
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    section = doc[doc.index("## 3."):doc.index("## 4.")]
+    blocks = re.findall(r"```cpp\n(.*?)```", section, flags=re.S)
+    assert len(blocks) == 2
+    ttv_call = blocks[0].split("...\n", 1)[1]                       # after '#include <ttv_b200.h>' and the ellipsis
+    ttvs_body = blocks[1]
+    text = open(ref_src).read()
+    # (1) the three #if branches that pick a CPU policy -> one call into the shim
+    i0 = text.index("#ifndef _OPENMP\n    ttv<T>(execution_policy::seq")
+    i1 = text.index("#endif", i0) + len("#endif")
+    text = text[:i0] + ttv_call + text[i1:]
+    # (2) everything in ttvs after the argument checks -> one call of ttv_b200_ttvs
+    j0 = text.index("  // B[0]...B[p-2]")
+    j1 = text.index("  return c;", j0) + len("  return c;")
+    text = text[:j0] + ttvs_body + text[j1:]
+    text = "#include <ttv_b200.h>\n" + text
+    src = tmp_path / "wrapped_ttv_b200.cpp"
+    src.write_text(text)
+    out = tmp_path / ("ttvpy" + sysconfig.get_config_var("EXT_SUFFIX"))
+    libdir = os.path.join(ROOT, "ttv_b200")
+    env = dict(os.environ); env.pop("CC", None); env.pop("CXX", None)
+    cmd = ["g++", "-O1", "-DNDEBUG", "-shared", "-std=c++17", "-fPIC", f"-I{pybind11.get_include()}", f"-I{sysconfig.get_paths()['include']}",
+           "-I/root/reference/include", f"-I{os.path.join(ROOT, 'include')}", str(src), "-o", str(out), f"-L{libdir}", "-lttv_b200",
+           f"-Wl,-rpath,{libdir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr[-4000:]
+    gpu = ttv_b200.device_count() > 0
+    check = f'''
+import sys, numpy as np
+sys.path.insert(0, {str(tmp_path)!r})
+import ttvpy
+A = np.arange(24, dtype=np.float64).reshape(3, 2, 4)
+gpu = {gpu!r}
+for call, want in ((lambda: ttvpy.ttv(1, A, np.arange(3, dtype=np.float64)), np.einsum("ijk,i->jk", A, np.arange(3.0))),
+                   (lambda: ttvpy.ttvs(2, A, [np.arange(3.0), np.arange(4.0)], "optimal"), np.einsum("ijk,i,k->j", A, np.arange(3.0), np.arange(4.0)))):
+    try:
+        got = call()
+        assert gpu and np.array_equal(got, want), got
+    except ValueError as e:
+        assert not gpu and "no CPU fallback" in str(e), e
+try:
+    ttvpy.ttvs(2, A, [np.arange(3.0)], "optimal")
+    raise SystemExit("missing vector was accepted")
+except ValueError as e:
+    assert "number of input vectors" in str(e)
+print("binding ok")
+'''
+    r = subprocess.run([sys.executable, "-c", check], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "binding ok" in r.stdout, r.stdout + r.stderr[-3000:]
