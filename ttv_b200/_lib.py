@@ -92,12 +92,7 @@ def load() -> C.CDLL:
         _lib = lib
         return lib
     from . import build as _build
-    try:
-        if _build.stale():
-            _build.build()
-    except Exception as exc:  # no nvcc on this box: fine if a prebuilt library travelled with the tree
-        if not os.path.exists(LIB_PATH):
-            raise ImportError(f"ttv_b200: libttv_b200.so is missing and could not be built: {exc}") from exc
+    _build.build_or_warn()        # no nvcc on this box: fine if a prebuilt library travelled with the tree (warns if stale)
     lib = C.CDLL(LIB_PATH)
     for name, (restype, argtypes) in SYMBOLS.items():
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch; fail loudly

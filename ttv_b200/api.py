@@ -46,11 +46,16 @@ def _is_torch(x) -> bool:
     return type(x).__module__.split(".")[0] == "torch"
 
 
+_TORCH_CODES: dict = {}
+
+
 def dtype_code(x) -> int:
     if _is_torch(x):
-        import torch
-        table = {torch.float32: 0, torch.float64: 1, torch.complex64: 2, torch.complex128: 3, torch.int32: 4,
-                 torch.int64: 5}
+        table = _TORCH_CODES
+        if not table:
+            import torch
+            table.update({torch.float32: 0, torch.float64: 1, torch.complex64: 2, torch.complex128: 3, torch.int32: 4,
+                          torch.int64: 5})
         if x.dtype not in table:
             raise TTVError(31, f"Error in ttv_b200: unsupported element type {x.dtype}.")
         return table[x.dtype]
@@ -183,6 +188,28 @@ def generate_k_order_layout(p, k) -> list[int]:
     return list(_k_order_cached(int(p), int(k)))
 
 
+def _is_contiguous(x) -> bool:
+    return bool(x.is_contiguous()) if _is_torch(x) else bool(np.asarray(x).flags.c_contiguous or np.asarray(x).flags.f_contiguous)
+
+
+def _check_operands(a, b, c):
+    """a, b, c travel as raw pointers: whatever is array-like must agree in element type and in where it lives, and b / c
+    must be dense -- otherwise the library would silently read another type's bytes or write past the end of c."""
+    named = [(n, x) for n, x in (("a", a), ("b", b), ("c", c)) if x is not None and not isinstance(x, int)]
+    if not named:
+        return
+    codes = {n: dtype_code(x) for n, x in named}
+    if len(set(codes.values())) > 1:
+        names = {n: (str(x.dtype)) for n, x in named}
+        raise TTVError(31, f"Error in ttv_b200: a, b and c must have the same element type, got {names}.")
+    kinds = {n: (("cuda:%d" % x.device.index) if (_is_torch(x) and x.is_cuda) else "host") for n, x in named}
+    if len(set(kinds.values())) > 1:
+        raise TTVError(41, f"Error in ttv_b200: a, b and c must all be host buffers or all live on one device, got {kinds}.")
+    for n, x in named:
+        if n != "a" and not _is_contiguous(x):
+            raise TTVError(32, f"Error in ttv_b200: {n} must be a dense (contiguous) buffer.")
+
+
 # ---- the low-level interface -----------------------------------------------------------------------------------------
 def ttv_lowlevel(q: int, p: int, a, na, wa, pia, b, nb, c, nc, wc, pic, *, dtype: int | None = None,
                  opts: Opts | None = None, **opt_kwargs) -> None:
@@ -190,6 +217,7 @@ def ttv_lowlevel(q: int, p: int, a, na, wa, pia, b, nb, c, nc, wc, pic, *, dtype
     raw integer addresses, or None; the tuples are sequences of ints or None.  Raises TTVError with the
     reference's message on invalid arguments.  C is overwritten."""
     lib = _lib.load()
+    _check_operands(a, b, c)
     if dtype is None:
         probe = next((x for x in (a, b, c) if x is not None and not isinstance(x, int)), None)
         if probe is None:
@@ -441,16 +469,31 @@ def ttv(q: int, A, b, *, layout: Sequence[int] | None = None, out=None, **opt_kw
         wa = generate_strides(shape, pia)
     wc = generate_strides(nc, pic)
     n_out = int(np.prod(nc, dtype=object))
-    nb = [int(b.shape[0])] if b.ndim >= 1 else [1]
 
     if torch_in:
         import torch
         if not A.is_cuda:
             raise TTVError(40, "Error in ttv_b200: torch tensors must live on a CUDA device (there is no CPU fallback).")
+        if not _is_torch(b):
+            raise TTVError(41, "Error in ttv_b200: A is a torch tensor, so b must be one too (same device).")
+        if b.dim() == 1 and not b.is_contiguous():
+            b = b.contiguous()
         flat_c = out if out is not None else torch.empty(n_out, dtype=A.dtype, device=A.device)
     else:
         A = np.asarray(A)
+        if _is_torch(b):
+            raise TTVError(41, "Error in ttv_b200: A is a host array, so b must be one too.")
+        b = np.asarray(b)
+        if b.ndim == 1 and not b.flags.c_contiguous:
+            b = np.ascontiguousarray(b)
         flat_c = out if out is not None else np.empty(n_out, dtype=A.dtype)
+    if b.ndim > 1:
+        raise TTVError(13, "Error in ttv_b200: b must be a vector (one-dimensional).")
+    nb = [int(b.shape[0])] if b.ndim >= 1 else [1]
+    if out is not None:
+        n_have = int(out.numel()) if _is_torch(out) else int(np.asarray(out).size)
+        if n_have < n_out:
+            raise TTVError(15, f"Error in ttv_b200: out holds {n_have} elements, the product has {n_out}.")
     ttv_lowlevel(q, p, A, shape, wa, pia, b, nb, flat_c, nc, wc, pic, **opt_kwargs)
     if out is not None:
         return out

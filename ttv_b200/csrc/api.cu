@@ -63,7 +63,6 @@ struct DeviceState {
   // Host-pointer calls share the staging buffers, the chunk ring and the copy stream of their device: one such call at a
   // time per device (they are synchronous and PCIe-bound, so nothing is lost).  Always taken BEFORE g_mutex.
   std::mutex host_mutex;
-  std::map<cudaStream_t, Buffer> workspace;   // split-n_q partials, one per stream so that streams do not share it
   Buffer stage_a, stage_b, stage_c;           // staging for host-pointer calls
   // chunked host path: a copy stream and a ring of chunk buffers with their events
   cudaStream_t copy_stream = nullptr;
@@ -164,6 +163,28 @@ struct DeviceGuard {
   ~DeviceGuard() { if (active) cudaSetDevice(prev); }
 };
 
+// the stream-ordered pool of a device: split-n_q partials and the intermediates of a chain (ttv_b200_ttvs)
+int chain_pool(int device, cudaMemPool_t* out)
+{
+  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceState* st = nullptr;
+  if (int rc = device_state(device, &st)) return rc;
+  if (!st->pool) {
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    CUDA_TRY(cudaMemPoolCreate(&st->pool, &props), "cudaMemPoolCreate");
+    // blocks of up to 1 GiB stay with the pool across synchronisations (a chain on the same shapes allocates nothing new);
+    // anything above goes back to the driver so that other allocators of the process can have it
+    uint64_t keep = 1ull << 30;
+    CUDA_TRY(cudaMemPoolSetAttribute(st->pool, cudaMemPoolAttrReleaseThreshold, &keep), "cudaMemPoolSetAttribute");
+  }
+  *out = st->pool;
+  return TTV_B200_OK;
+}
+
 // runs the canonical view with device pointers on `device`
 int run_view_device(int dtype, const View& v, const void* a, const void* b, void* c, const ttv_b200_opts* opts,
                     int device, bool sync)
@@ -183,23 +204,19 @@ int run_view_device(int dtype, const View& v, const void* a, const void* b, void
   int rc = choose_launch(dtype, v, opts, alignment_of(a), alignment_of(b), alignment_of(c), st->sm_count, &l);
   if (rc) return fail(rc);
 
+  // The partials of a split n_q live in a stream-ordered allocation of this call only: the tile kernel writes them, the
+  // reduce kernel reads them, cudaFreeAsync hands the block back behind the reduce.  Calls on the same stream from several
+  // host threads (torch's default stream is shared by all of them) therefore never see each other's partials, whichever way
+  // their launches interleave, and nothing is freed under a kernel that still reads it.
   void* ws = nullptr;
   if (l.workspace_bytes) {
-    // one workspace per (device, stream); calls on ONE stream must come from one thread at a time, as for any CUDA stream
-    std::unique_lock<std::mutex> lock(g_mutex);
-    Buffer& buf = st->workspace[stream];
-    if (buf.bytes < l.workspace_bytes) {
-      // the old block may still be in use by work queued on this stream
-      if (buf.ptr) {
-        lock.unlock();
-        CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
-        lock.lock();
-      }
-      if (int r2 = ensure(buf, (size_t)l.workspace_bytes)) return r2;
-    }
-    ws = buf.ptr;
+    cudaMemPool_t pool = nullptr;
+    if (int r2 = chain_pool(device, &pool)) return r2;
+    CUDA_TRY(cudaMallocFromPoolAsync(&ws, (size_t)l.workspace_bytes, pool, stream), "cudaMallocFromPoolAsync (split-n_q partials)");
   }
-  CUDA_TRY(launch_view(dtype, v, l, a, b, c, ws, accumulate, st->sm_count, stream), "kernel launch");
+  cudaError_t le = launch_view(dtype, v, l, a, b, c, ws, accumulate, st->sm_count, stream);
+  if (ws && cudaFreeAsync(ws, stream) != cudaSuccess) cudaGetLastError();
+  CUDA_TRY(le, "kernel launch");
   if (sync) CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
   return TTV_B200_OK;
 }
@@ -465,15 +482,19 @@ int run_any(int dtype, const View& v, const void* a, const void* b, void* c, con
 // Which mode each step contracts and with which vector: vector j belongs to mode r = j+1 (j+1 < q) or j+2.
 //   backward: r = p, p-1, ... (skipping q)      wrapped_ttv.cpp:135-146
 //   forward : r = 1, 2, ...   (skipping q)      wrapped_ttv.cpp:147-156
-//   optimal : longest vector first, so that the tensor shrinks as fast as possible (:157-192; ties: smaller mode first)
+//   optimal : longest vector first, so that the tensor shrinks as fast as possible (:157-192).  The reference sorts its
+//             (vector, mode) pairs ASCENDING by length (std::sort, which is an insertion sort -- stable -- below 16
+//             elements) and walks them from the back, so among equal lengths the LARGER mode goes first.
 // modes[i] is numbered in the tensor that is left when step i runs (contracted modes drop out, later ones move down).
 int chain_plan(uint64_t q, uint64_t p, const uint64_t* na, int order, uint64_t* modes, uint64_t* vectors)
 {
   std::vector<uint64_t> seq;                                     // original modes in the order they are contracted
   for (uint64_t r = 1; r <= p; ++r) if (r != q) seq.push_back(r);
   if (order == TTV_B200_CHAIN_BACKWARD) std::reverse(seq.begin(), seq.end());
-  else if (order == TTV_B200_CHAIN_OPTIMAL)
-    std::stable_sort(seq.begin(), seq.end(), [na](uint64_t x, uint64_t y) { return na[x - 1] > na[y - 1]; });
+  else if (order == TTV_B200_CHAIN_OPTIMAL) {
+    std::stable_sort(seq.begin(), seq.end(), [na](uint64_t x, uint64_t y) { return na[x - 1] < na[y - 1]; });
+    std::reverse(seq.begin(), seq.end());
+  }
   std::vector<uint64_t> alive;
   for (uint64_t r = 1; r <= p; ++r) alive.push_back(r);
   for (size_t i = 0; i < seq.size(); ++i) {
@@ -483,27 +504,6 @@ int chain_plan(uint64_t q, uint64_t p, const uint64_t* na, int order, uint64_t* 
     vectors[i] = r < q ? r - 1 : r - 2;
     alive.erase(it);
   }
-  return TTV_B200_OK;
-}
-
-int chain_pool(int device, cudaMemPool_t* out)
-{
-  std::lock_guard<std::mutex> lock(g_mutex);
-  DeviceState* st = nullptr;
-  if (int rc = device_state(device, &st)) return rc;
-  if (!st->pool) {
-    cudaMemPoolProps props{};
-    props.allocType = cudaMemAllocationTypePinned;
-    props.handleTypes = cudaMemHandleTypeNone;
-    props.location.type = cudaMemLocationTypeDevice;
-    props.location.id = device;
-    CUDA_TRY(cudaMemPoolCreate(&st->pool, &props), "cudaMemPoolCreate");
-    // blocks of up to 1 GiB stay with the pool across synchronisations (a chain on the same shapes allocates nothing new);
-    // anything above goes back to the driver so that other allocators of the process can have it
-    uint64_t keep = 1ull << 30;
-    CUDA_TRY(cudaMemPoolSetAttribute(st->pool, cudaMemPoolAttrReleaseThreshold, &keep), "cudaMemPoolSetAttribute");
-  }
-  *out = st->pool;
   return TTV_B200_OK;
 }
 
@@ -948,8 +948,6 @@ void ttv_b200_release(void)
     DeviceGuard guard;
     if (guard.set(ds.first) != cudaSuccess) { cudaGetLastError(); continue; }
     cudaDeviceSynchronize();                                    // queued kernels may still read a workspace
-    for (auto& w : st.workspace) if (w.second.ptr) cudaFree(w.second.ptr);
-    st.workspace.clear();
     for (Buffer* b : {&st.stage_a, &st.stage_b, &st.stage_c, &st.ring[0], &st.ring[1], &st.ring[2]})
       if (b->ptr) { cudaFree(b->ptr); b->ptr = nullptr; b->bytes = 0; }
     for (int r = 0; r < 3; ++r) {

@@ -24,20 +24,50 @@ from . import api
 __all__ = ["ttv", "ttvs", "chain_plan", "CapturedTtvs"]
 
 
-def _as_c_array(x):
+def _common_dtype(*arrays):
+    """The element type a product of these operands is computed in: numpy's promotion of ALL operands, mapped to an
+    element type of the C-ABI.  The reference binds `py::array_t<double>` (wrapped_ttv.cpp:205-206) and lets pybind11 convert
+    every operand to float64; promoting keeps that meaning (an integer A with a fractional or complex b is NOT truncated to
+    A's type) while float32 / complex / integer operands that agree keep their own type (an extension: the reference would
+    hand back the same values as float64)."""
+    dt = np.result_type(*[np.asarray(x).dtype if not isinstance(x, np.dtype) else x for x in arrays])
+    if dt in api._NP_CODES:
+        return dt
+    if dt.kind == "c":
+        return np.dtype(np.complex128)
+    if dt.kind == "f":
+        return np.dtype(np.float32) if dt.itemsize < 4 else np.dtype(np.float64)
+    if dt.kind in "iub":
+        if dt.kind != "u" and dt.itemsize <= 4 or dt.kind == "b" or (dt.kind == "u" and dt.itemsize < 4):
+            return np.dtype(np.int32)
+        if dt.kind == "i" or dt.itemsize < 8:
+            return np.dtype(np.int64)
+    return np.dtype(np.float64)             # uint64, objects that convert, ...: what the reference does with everything
+
+
+def _as_c_array(x, dtype=None):
     a = np.asarray(x)
-    if a.dtype not in api._NP_CODES:
-        a = a.astype(np.float64)            # the reference binds double only and lets pybind11 convert
-    return np.ascontiguousarray(a)
+    return np.ascontiguousarray(a, dtype=dtype if dtype is not None else _common_dtype(a))
 
 
-def _as_array(x):
+def _as_array(x, dtype=None):
     """like _as_c_array but WITHOUT packing: slices and transposes are read in place through their strides (the
     reference silently reads them as if they were C-contiguous, wrapped_ttv.cpp:44-45)"""
     a = np.asarray(x)
-    if a.dtype not in api._NP_CODES:
-        a = a.astype(np.float64)
-    return a
+    dtype = dtype if dtype is not None else _common_dtype(a)
+    return a if a.dtype == dtype else a.astype(dtype)
+
+
+def _torch_common(A, bs):
+    """torch operands: promote like numpy does (torch.result_type pairwise), on A's device"""
+    import torch
+    dt = A.dtype
+    for b in bs:
+        dt = torch.promote_types(dt, b.dtype if api._is_torch(b) else torch.from_numpy(np.asarray(b)).dtype)
+    if dt not in (torch.float32, torch.float64, torch.complex64, torch.complex128, torch.int32, torch.int64):
+        dt = torch.float64 if not dt.is_complex else torch.complex128
+    conv = lambda x: (x if api._is_torch(x) else torch.from_numpy(np.asarray(x))).to(device=A.device, dtype=dt)
+    return conv(A), [conv(b).contiguous() for b in bs]
 
 
 def ttv(q: int, A, b):
@@ -48,9 +78,13 @@ def ttv(q: int, A, b):
             raise ValueError("Error calling ttvpy::ttv: input tensor order should be greater than zero.")
         if q == 0 or q > p:
             raise ValueError("Error calling ttvpy::ttv: contraction mode should be greater than zero or less than or equal to p.")
-        return api.ttv(q, A, b.contiguous())
-    A = _as_array(A)
-    b = np.ascontiguousarray(np.asarray(b), dtype=A.dtype)
+        A, (b,) = _torch_common(A, [b])
+        return api.ttv(q, A, b)
+    A = np.asarray(A)
+    b = np.asarray(b)
+    dt = _common_dtype(A, b)
+    A = _as_array(A, dt)
+    b = np.ascontiguousarray(b, dtype=dt)
     p = A.ndim
     if p == 0:
         raise ValueError("Error calling ttvpy::ttv: input tensor order should be greater than zero.")
@@ -69,8 +103,9 @@ def chain_plan(q: int, shape, order: str = "optimal"):
         seq = sorted(modes, key=lambda t: -t[0])
     elif order == "forward":
         seq = sorted(modes, key=lambda t: t[0])
-    else:  # "optimal": the longest vector first, so that the tensor shrinks as fast as possible
-        seq = sorted(modes, key=lambda t: (-int(shape[t[0] - 1]), t[0]))
+    else:  # "optimal": the longest vector first, so that the tensor shrinks as fast as possible.  The reference sorts
+        # ascending (stable for fewer than 16 vectors) and walks the list backwards (:170-188): ties -> larger mode first
+        seq = sorted(modes, key=lambda t: int(shape[t[0] - 1]))[::-1]
     out = []
     alive = list(range(1, p + 1))           # original mode numbers still present, in order
     for r, j in seq:
@@ -85,7 +120,8 @@ def ttvs(q: int, A, bs, order: str = "optimal"):
         raise ValueError("Error calling ttvpy::ttvs: multiplication order should be either 'optimal', 'backward' or 'forward'.")
     on_device = api._is_torch(A)
     if not on_device:
-        A = _as_c_array(A)
+        A = np.asarray(A)
+    bs = [bj if api._is_torch(bj) else np.asarray(bj) for bj in bs]
     p = A.ndim
     if p == 0:
         raise ValueError("Error calling ttvpy::ttvs: input tensor order should be greater than zero.")
@@ -99,6 +135,12 @@ def ttvs(q: int, A, bs, order: str = "optimal"):
     want = [shape[r - 1] for r in range(1, p + 1) if r != q]
     if [int(bj.shape[0]) for bj in bs] != want:
         raise ValueError("Error calling ttvpy::ttvs: vector dimension is not compatible with the dimension of a tensor mode.")
+    if on_device:
+        A, bs = _torch_common(A, list(bs))
+    else:
+        dt = _common_dtype(A, *bs)                          # promote over A and every vector, never cast down to A's type
+        A = _as_c_array(A, dt)
+        bs = [np.ascontiguousarray(np.asarray(bj), dtype=dt) for bj in bs]
     if p == 1:
         return A
 
@@ -106,10 +148,8 @@ def ttvs(q: int, A, bs, order: str = "optimal"):
         # the native chain (ttv_b200_ttvs): one call, intermediates in a stream-ordered pool in HBM, only c comes back
         last_order = list(range(p, 0, -1))                  # a C-contiguous array is a last-order tensor (wrapped_ttv.cpp:44-45)
         if on_device:
-            vecs = [bj.to(dtype=A.dtype, device=A.device).contiguous() for bj in bs]
-            return api.ttvs(q, A.contiguous(), shape, last_order, vecs, order)
-        vecs = [np.ascontiguousarray(np.asarray(bj), dtype=A.dtype) for bj in bs]
-        return api.ttvs(q, A, shape, last_order, vecs, order)
+            return api.ttvs(q, A.contiguous(), shape, last_order, bs, order)
+        return api.ttvs(q, A, shape, last_order, bs, order)
     return _ttvs_stepwise(q, A, bs, order, on_device, shape)
 
 
