@@ -15,6 +15,15 @@ metric = effective HBM GB/s = algorithmic bytes / time, algorithmic bytes per pr
 (read A once, read b once, write C once).  Inputs (16 GiB) are far larger than L2 (126 MB), so no flush is
 needed between iterations.  `value` has the inputs resident in HBM; `e2e` is the same step through the public API
 with HOST (pinned) buffers, host<->device copies inside the timed region.
+
+Beside the contract's keys the line carries (none of them inside the timed region of `value`):
+  configs   N = 1: EVERY named BASELINE config (ttv_b200/workloads.py "named": cfg1, the symmetric fp32/fp64 sweep, the
+            asymmetric fp32/int32 sweep, the complex family with last-order / random layouts, the cfg5 slab: 210 products)
+            timed device-resident AND checked on sampled fibers against a host long-double dot (bit-exact for int32):
+            n, min / median GB/s, everything below 0.8 x 8 TB/s, parity failures, the whole table
+  cfg5      BASELINE configs[4]: 2048^3 fp64 STRONG scaling over the N ranks, q = 1 (free split) and q = 3 (n_q split +
+            fused exchange), per-rank times, checked the same way
+  multi_gpu_selfcheck   N > 1: small integer tensors through every exchange form against numpy, bit for bit
 """
 from __future__ import annotations
 
@@ -37,6 +46,10 @@ DTYPE = "f32"
 ELEM = 4
 SEED_A, SEED_B = 0x77170001, 0x77170002
 METRIC = "TTV effective HBM GB/s"
+# how oracle/_ref is compiled (oracle/Makefile REFFLAGS): built in the build container and shipped to the GPU box, whose CPU
+# is not known there, so it targets x86-64-v3 (AVX2 + FMA) instead of BASELINE.md's -march=native; OpenBLAS picks its
+# kernels at run time (DYNAMIC_ARCH), so the gemv inside is unaffected
+REF_BUILD = "g++ -O3 -march=x86-64-v3 -fopenmp -DNDEBUG, not -march=native: built off the box"
 
 
 def algo_bytes(na, q, elem=ELEM):
@@ -158,6 +171,39 @@ def cpu_measure(last_extent, steps, warmup, budget_s=None, a=None):
             "gbs": total_bytes / statistics.mean(times) / 1e9, "kind": kind, "cores": cores, "blas": blas, "na": na}
 
 
+def cpu_measure_shape(dt, na, pia, qs, combo, steps, warmup, budget_s):
+    """the reference's CPU path on one more shape / policy (cpu_baseline_asym): seconds per step = all q of qs"""
+    ref, helpers, kind = load_reference()
+    npdt = {"f32": np.float32, "i32": np.int32, "f64": np.float64}[dt]
+    n = int(np.prod(na))
+    a = np.empty(n, npdt)
+    chunk = 1 << 24
+    pattern = helpers.fill(dt, chunk, SEED_A)
+    for s0 in range(0, n, chunk):
+        a[s0:s0 + chunk] = pattern[: min(chunk, n - s0)]
+    bs = {q: helpers.fill(dt, na[q - 1], SEED_B + q) for q in qs}
+    cs = {q: np.zeros(n // na[q - 1], npdt) for q in qs}
+    times = []
+    t_start = time.perf_counter()
+    for it in range(warmup + steps):
+        for c in cs.values():
+            c.fill(0)
+        t0 = time.perf_counter()
+        for q in qs:
+            if kind == "reference":
+                ref.ttv(q, a, na, pia, bs[q], combo=combo, helpers=helpers, c0=cs[q])
+            else:
+                cs[q][:] = helpers.ttv(q, a, na, pia, bs[q], slicing=combo[1])
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+        if budget_s is not None and time.perf_counter() - t_start > budget_s and times:
+            break
+    elem = np.dtype(npdt).itemsize
+    total_bytes = sum(algo_bytes(na, q, elem) for q in qs)
+    return {"gbs": total_bytes / statistics.mean(times) / 1e9, "steps_done": len(times), "kind": kind,
+            "cores": ref.cores() if ref is not None else 1, "blas": bool(ref is not None and ref.blas)}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -174,12 +220,15 @@ def run_reference_arm(args):
     while last > 8 and (4 * algo_bytes([EXT, EXT, EXT, last], 1) / rate > want_s or 4 * EXT ** 3 * last * 2.5 > avail):
         last //= 2
     m = cpu_measure(last, args.steps, args.warmup)
-    sample = (f"unmodified reference headers ({'OpenBLAS ' if m['blas'] else 'non-BLAS '}par_loop/subtensor/all, OpenMP), "
+    sample = (f"unmodified reference headers ({'OpenBLAS ' if m['blas'] else 'non-BLAS '}par_loop/subtensor/all, OpenMP; {REF_BUILD}), "
               f"n=({EXT},{EXT},{EXT},{last}) fp32 {'= the full per-GPU tensor' if last == EXT else 'slab of the 256^4 tensor'}, q=1..4 per step")
     line = {"impl": "reference", "metric": METRIC, "value": round(m["gbs"], 2), "unit": "GB/s", "n_gpus": args.gpus,
             "steps": m["steps_done"], "warmup": args.warmup, "ms_per_step": round(m["seconds_per_step"] * 1e3, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
-            "config": {"workload": workload_name(args.gpus), "timed_on": "host CPU cores"},
+            "config": {"workload": workload_name(args.gpus), "timed_on": "host CPU cores",
+                       # what this arm actually times: a rate (GB/s) on a bounded sample of the PER-GPU tensor, not the N x tensor
+                       "sampled_shape": [EXT, EXT, EXT, last], "sampled_bytes_per_step": m["bytes_per_step"],
+                       "sample_is": "the whole per-GPU 256^4 tensor" if last == EXT else "a slab of the per-GPU 256^4 tensor along mode 4"},
             "cpu_baseline": {"value": round(m["gbs"], 2), "unit": "GB/s", "cores": m["cores"], "kind": m["kind"], "sample": sample},
             "e2e": {"value": round(m["gbs"], 2), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gflops": round(2 * EXT ** 3 * last * 4 / m["seconds_per_step"] / 1e9, 2)}
@@ -246,7 +295,8 @@ def run_own_arm(args):
 
     def step():
         for q in range(1, ORDER + 1):
-            live[q] = ttv_sharded(q, a, na_global, pia, bs[q], rank=rank, world=world, c_local=cs[q], reduce_to=0, exchange=exchange)
+            live[q] = ttv_sharded(q, a, na_global, pia, bs[q], rank=rank, world=world, c_local=cs[q], reduce_to=0, exchange=exchange,
+                                  asynchronous=True)          # enqueue only: no host round trip between the four products
 
     def barrier():
         if world > 1:
@@ -310,15 +360,30 @@ def run_own_arm(args):
     col_bytes = [algo_bytes(list(shards[q].na_local), q) for q in col_q]
     col_ms = [per_q[q] for q in col_q]
     achieved = sum(col_bytes) / (sum(col_ms) * 1e-3) / 1e9
-    traffic = None
+    # the kernel the chooser actually launches for these products (ttv_b200_plan: the same code path the launch takes), and
+    # the ncu DRAM traffic recorded for exactly that kernel -- a chooser change makes the labels differ and traffic null
+    ctype = {"f32": "float", "f64": "double"}[DTYPE]
+    labels = []
+    for q in col_q:
+        pl = ttv_b200.plan(q, list(shards[q].na_local), pia, dtype=DTYPE)
+        fam = {1: "dot", 2: "col", 3: "stream", 4: "colx", 5: "dotf"}.get(pl["kernel"], "?")
+        labels.append(f"ttv_{fam}_kernel<{ctype},{pl['vec']},{pl['nu']},{pl['ku']}>")
+    kernel_name = max(set(labels), key=labels.count)
+    traffic, traffic_note = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("col_kernel_dram_bytes_per_launch")
+        rec = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        if rec.get("kernel") == kernel_name and all(l == kernel_name for l in labels):
+            traffic = rec.get("col_kernel_dram_bytes_per_launch")
+            traffic_note = rec.get("source")
+        else:
+            traffic_note = f"profiles/roofline_traffic.json was captured for {rec.get('kernel')}, this run launched {sorted(set(labels))}"
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "ttv_col_kernel<float,4,1,8>", "achieved": round(achieved, 1), "peak": peak,
+    roofline = {"bound": "hbm", "kernel": kernel_name, "kernel_per_product": dict(zip([f"q{q}" for q in col_q], labels)),
+                "achieved": round(achieved, 1), "peak": peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                 "unit": "GB/s", "frac": round(achieved / peak, 4), "frac_of_nominal_8000": round(achieved / 8000.0, 4),
-                "traffic": traffic, "algorithmic_bytes_per_launch": int(statistics.mean(col_bytes)),
+                "traffic": traffic, "traffic_source": traffic_note, "algorithmic_bytes_per_launch": int(statistics.mean(col_bytes)),
                 "per_product": {f"q{q}": {"ms": round(per_q[q], 4),
                                           "gbs": round(algo_bytes(list(shards[q].na_local), q) / (per_q[q] * 1e-3) / 1e9, 1)}
                                 for q in range(1, ORDER + 1)}}
@@ -328,8 +393,9 @@ def run_own_arm(args):
     if not args.no_e2e:
         e2e = measure_e2e(torch, dist, ttv_b200, args, a, bs, cs, shards, na_global, pia, rank, world, dev, total_bytes, exchange)
 
-    cpu = None
+    cpu, cpu_asym = None, None
     if rank == 0 and world == 1 and not args.no_cpu:
+        a_np = None
         try:
             # the host copy of the tensor the e2e leg just used (16 GiB, already resident): the whole workload, a few steps
             a_np = e2e.pop("_a_host", None) if e2e else None
@@ -337,16 +403,41 @@ def run_own_arm(args):
             m = cpu_measure(last, 5, 1, budget_s=25.0, a=a_np)
             cpu = {"value": round(m["gbs"], 2), "unit": "GB/s", "cores": m["cores"], "kind": m["kind"],
                    "sample": (f"{'unmodified reference headers' if m['kind'] == 'reference' else 'oracle port'} "
-                              f"({'OpenBLAS ' if m['blas'] else 'non-BLAS '}par_loop/subtensor/all), "
+                              f"({'OpenBLAS ' if m['blas'] else 'non-BLAS '}par_loop/subtensor/all; {REF_BUILD}), "
                               f"{'the whole' if last == EXT else f'slab n=(256,256,256,{last}) fp32 of the'} 256^4 tensor, q=1..4, "
                               f"{m['steps_done']} steps after 1 warm-up")}
         except Exception as exc:  # the baseline is reported, never required for the GPU number
             cpu = {"value": None, "unit": "GB/s", "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
+        del a_np
+        # the asymmetric family with the policy the reference's README states for it, (par_loop, slice, all)
+        # (/root/reference README.md:79, detail/tensor_times_vector.h:706): one member of the sweep, every q
+        try:
+            na_asym = [16, 1024, 4, 1 << 14]
+            m2 = cpu_measure_shape("f32", na_asym, [1, 2, 3, 4], [1, 2, 3, 4], ("par_loop", "slice", "all"), 3, 1, 12.0)
+            cpu_asym = {"value": round(m2["gbs"], 2), "unit": "GB/s", "cores": m2["cores"], "kind": m2["kind"],
+                        "sample": (f"{'unmodified reference headers' if m2['kind'] == 'reference' else 'oracle port'} "
+                                   f"({'OpenBLAS ' if m2['blas'] else 'non-BLAS '}par_loop/slice/all; {REF_BUILD}), asymmetric sweep member "
+                                   f"n=(16,1024,4,16384) fp32 first-order, q=1..4, {m2['steps_done']} steps after 1 warm-up")}
+        except Exception as exc:
+            cpu_asym = {"value": None, "unit": "GB/s", "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
 
     if e2e:
         e2e.pop("_a_host", None)
         if world > 1:
             e2e["host_bound_to_gpu_socket"] = bool(numa_bound)
+
+    # ---- everything below is outside every timed region above: free the 16 GiB workload first ---------------------
+    del a, cs, live
+    torch.cuda.empty_cache()
+    mg_check = None
+    if world > 1 and not args.no_selfcheck:
+        mg_check = multi_gpu_selfcheck(torch, dist, rank, world, dev)
+    cfg5 = None
+    if not args.no_cfg5:
+        cfg5 = cfg5_leg(torch, dist, ttv_b200, rank, world, dev, args)
+    sweep = None
+    if world == 1 and not args.no_sweep:
+        sweep = sweep_leg(torch, ttv_b200, args)
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
@@ -358,9 +449,182 @@ def run_own_arm(args):
                 "frac_of_measured_peak": round(value / (peak * world), 4),
                 "frac_of_nominal_8000": round(value / (8000.0 * world), 4),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk}
+        if cpu_asym is not None:
+            line["cpu_baseline_asym"] = cpu_asym
+        if sweep is not None:
+            line["configs"] = sweep
+        if cfg5 is not None:
+            line["cfg5"] = cfg5
+        if mg_check is not None:
+            line["multi_gpu_selfcheck"] = mg_check
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def sweep_leg(torch, ttv_b200, args):
+    """EVERY named BASELINE config, full size, device-resident: timed (CUDA events around each launch, A rotated over several
+    buffers when it is not much larger than L2) and checked (sampled outputs against a host long-double dot on regenerated
+    fibers; int32 bit-exact).  Not part of any timed region of the headline numbers."""
+    from ttv_b200.measure import Arena, kernel_label, measure_config
+    from ttv_b200.workloads import configs
+    arena_a, arena_c = Arena(int(17.5e9)), Arena(int(8.8e9))
+    rng = np.random.default_rng(20261017)
+    rows, failures, checked, errors = [], 0, 0, []
+    t0 = time.perf_counter()
+    for name, dt, na, pia, q, *rest in configs(args.sweep_set):
+        try:
+            pl = ttv_b200.plan(q, na, pia, dtype=dt)
+            r = measure_config(dt, na, pia, q, reps=args.sweep_reps, warmup=2, arena_a=arena_a, arena_c=arena_c, rng=rng)
+        except Exception as exc:
+            errors.append(f"{name} {dt} q={q}: {exc}")
+            continue
+        failures += r.get("failures", 0)
+        checked += r.get("checked", 0)
+        rows.append({"name": name, "dtype": dt, "q": q, "view": [pl["outer"], pl["nq"], pl["inner"]], "kernel": kernel_label(pl),
+                     "ms": round(r["ms_med"], 4), "gbs": round(r["gbs_med"], 1), "failures": r.get("failures", 0)})
+    del arena_a, arena_c
+    torch.cuda.empty_cache()
+    if not rows:
+        return {"n": 0, "errors": errors}
+    gbs = sorted(x["gbs"] for x in rows)
+    worst = min(rows, key=lambda x: x["gbs"])
+    below = [f"{x['name']} {x['dtype']} q={x['q']}: {x['gbs']:.0f}" for x in rows if x["gbs"] < 0.8 * 8000.0]
+    out = {"set": args.sweep_set, "n": len(rows), "min_gbs": worst["gbs"], "min_name": f"{worst['name']} {worst['dtype']} q={worst['q']}",
+           "median_gbs": gbs[len(gbs) // 2], "geomean_gbs": round(float(np.exp(np.mean(np.log(gbs)))), 1),
+           "below_0p8_nominal": below, "n_at_or_above_0p8_nominal": len(rows) - len(below),
+           "parity_failures": failures, "samples_checked": checked, "errors": errors,
+           "tolerance": "int32 bit-exact; float/complex |c - ref| <= 2 n_q eps sum|a_k||b_k| per component against a host long-double dot",
+           "timing": f"median of {args.sweep_reps} launches, CUDA events around each launch, A rotated over 2-4 buffers below 8 x L2",
+           "seconds": round(time.perf_counter() - t0, 1)}
+    c12 = [x for x in rows if x["name"] == "cfg1" and x["q"] == 2]
+    if c12:
+        out["cfg1_q2"] = {"workload": "BASELINE configs[0]: 512^3 fp32, q=2, first-order", "ms": c12[0]["ms"], "gbs": c12[0]["gbs"],
+                          "frac_of_nominal_8000": round(c12[0]["gbs"] / 8000.0, 4), "kernel": c12[0]["kernel"]}
+    out["table"] = [[x["name"], x["dtype"], x["q"], x["gbs"], x["kernel"]] for x in rows]
+    return out
+
+
+def cfg5_leg(torch, dist, ttv_b200, rank, world, dev, args):
+    """BASELINE configs[4]: order-3 fp64 n = (2048, 2048, 2048) (68.7 GB), STRONG scaling over the N ranks: sharded along mode 3,
+    q = 1 and q = 2 are free splits (no communication), q = 3 contracts the split mode (n_q split; N > 1: exchange fused into
+    the kernel's stores, N = 1: the plain kernel).  Launches are enqueued back to back (asynchronous), timed with CUDA events
+    per rank; the line carries the max over ranks and the spread."""
+    from ttv_b200 import selfcheck
+    from ttv_b200.sharded import PeerExchange, make_shard, ttv_sharded
+    na, pia, dt = [2048, 2048, 2048], [1, 2, 3], "f64"
+    free_b, _ = torch.cuda.mem_get_info(dev)
+    need = 8 * (2048 ** 3) // world + (2 << 30)
+    if free_b < need:
+        return {"skipped": f"needs {need >> 30} GiB of free HBM per GPU, {free_b >> 30} GiB free"}
+    shards = {q: make_shard(q, na, pia, rank, world) for q in (1, 2, 3)}
+    sh = shards[1]
+    a = torch.empty(sh.a_count, dtype=torch.float64, device=dev)
+    ttv_b200.fill(a, SEED_A, first=sh.a_offset)
+    bs = {}
+    for q in (1, 2, 3):
+        bs[q] = torch.empty(na[q - 1], dtype=torch.float64, device=dev)
+        ttv_b200.fill(bs[q], SEED_B + q)
+    cs = {q: torch.full((shards[q].c_count,), float("nan"), dtype=torch.float64, device=dev) for q in (1, 2, 3)}
+    exchange = None
+    if world > 1 and not args.nccl_reduce:
+        try:
+            exchange = PeerExchange(shards[3].c_count, torch.float64, dev)
+        except Exception as exc:
+            print(f"bench.py: rank {rank}: cfg5: peer-memory exchange unavailable ({exc}); using ncclReduce", file=sys.stderr)
+        ok = torch.tensor([1 if exchange is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            exchange = None
+    out = {"workload": f"BASELINE configs[4]: order-3 fp64 n=(2048,2048,2048) first-order, strong scaling over {world} GPU(s), sharded along mode 3",
+           "scaling": "strong", "per_gpu_tensor_bytes": sh.a_count * 8,
+           "exchange": None if world == 1 else ("fused into the kernel's stores over NVLink peer memory" if exchange is not None else "ncclReduce")}
+    reps = max(5, min(args.steps, 20))
+    rng = np.random.default_rng(55 + rank)
+    for q in (1, 2, 3):
+        def once():
+            return ttv_sharded(q, a, na, pia, bs[q], rank=rank, world=world, c_local=cs[q], reduce_to=0, exchange=exchange, asynchronous=True)
+        for _ in range(3):
+            c, s = once()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            c, s = once()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_local = e0.elapsed_time(e1) / reps
+        ms_all = [ms_local]
+        if world > 1:
+            t = torch.zeros(world, device=dev, dtype=torch.float64)
+            t[rank] = ms_local
+            dist.all_reduce(t)
+            ms_all = [float(x) for x in t.tolist()]
+        ms = max(ms_all)
+        # parity of this rank's piece of C on sampled fibers (global indices: the slab was filled with first = its offset)
+        bad = 0
+        nchk = 0
+        if not (s.kind == "nq" and world > 1 and rank != 0):
+            nchk, bad, _ = selfcheck.check_product(c, dt, na, pia, q, SEED_A, bs[q], samples=32, rng=rng, c_first=s.c_offset)
+        if world > 1:
+            t = torch.tensor([bad, nchk], device=dev, dtype=torch.int64)
+            dist.all_reduce(t)
+            bad, nchk = int(t[0].item()), int(t[1].item())
+        byt = 8 * (2048 ** 3 + 2048 + 2048 ** 2)
+        pl = ttv_b200.plan(q, list(shards[q].na_local), pia, dtype=dt) if shards[q].count else {}
+        from ttv_b200.measure import kernel_label
+        out[f"q{q}"] = {"split": "free (no communication)" if shards[q].kind == "free" else "n_q split",
+                        "ms": round(ms, 4), "gbs": round(byt / ms / 1e6, 1), "gbs_per_gpu": round(byt / ms / 1e6 / world, 1),
+                        "frac_of_nominal_8000_per_gpu": round(byt / ms / 1e6 / world / 8000.0, 4),
+                        "rank_ms_min": round(min(ms_all), 4), "rank_ms_max": round(max(ms_all), 4),
+                        "kernel": ("ttv_col_scatter_kernel + barrier + ttv_reduce_kernel" if (s.kind == "nq-scattered") else kernel_label(pl)),
+                        "samples_checked": nchk, "parity_failures": bad}
+    del a, cs
+    torch.cuda.empty_cache()
+    return out
+
+
+def multi_gpu_selfcheck(torch, dist, rank, world, dev):
+    """Small integer-valued tensors through every exchange form of the sharded path -- free split, n_q split + NCCL all-reduce,
+    n_q split fused with the exchange over peer memory -- compared bit for bit with numpy's tensordot of the global problem
+    (int32, and float64 / complex64 holding small integers: every partial sum is exact).  Uneven splits included."""
+    from ttv_b200 import selfcheck
+    from ttv_b200.sharded import PeerExchange, make_shard, ttv_sharded
+    cases = [((37, 21, 40), (1, 2, 3)), ((16, 33, 9, 12), (2, 1, 4, 3)), ((300, 17), (1, 2)), ((17, 300), (2, 1)), ((5, 6, 7, 19), (4, 3, 2, 1))]
+    products, bad, fused = 0, 0, 0
+    for npdt in (np.int32, np.float64, np.complex64):
+        tdt = torch.from_numpy(np.zeros(1, npdt)).dtype
+        try:
+            ex = PeerExchange(40000, tdt, dev)
+        except Exception:
+            ex = None
+        rng = np.random.default_rng(99)                     # the same data on every rank
+        for na, pia in cases:
+            n = int(np.prod(na))
+            a_full = rng.integers(-6, 7, n).astype(npdt)
+            for q in range(1, len(na) + 1):
+                b = rng.integers(-6, 7, na[q - 1]).astype(npdt)
+                want = selfcheck.full_product(a_full, na, pia, q, b)
+                sh = make_shard(q, na, pia, rank, world)
+                a_loc = torch.from_numpy(a_full[sh.a_offset: sh.a_offset + sh.a_count].copy()).to(dev)
+                tb = torch.from_numpy(b).to(dev)
+                c, s2 = ttv_sharded(q, a_loc, na, pia, tb, rank=rank, world=world, reduce_to=None)
+                got = c.cpu().numpy()
+                ref = want[s2.c_offset: s2.c_offset + s2.c_count] if s2.kind == "free" else want
+                bad += 0 if np.array_equal(got, ref) else 1
+                products += 1
+                if s2.kind != "free" and ex is not None and na[s2.mode - 1] >= world:
+                    for _ in range(2):                      # both halves of the workspace
+                        c2, s3 = ttv_sharded(q, a_loc, na, pia, tb, rank=rank, world=world, exchange=ex)
+                        bad += 0 if np.array_equal(c2.cpu().numpy(), want[s3.c_offset: s3.c_offset + s3.c_count]) else 1
+                        products += 1
+                        fused += 1
+    t = torch.tensor([products, bad, fused], device=dev, dtype=torch.int64)
+    dist.all_reduce(t)
+    return {"products_checked_all_ranks": int(t[0].item()), "failures": int(t[1].item()), "fused_exchange_products": int(t[2].item()),
+            "against": "numpy tensordot of the global tensor, bit for bit (integer-valued data)"}
 
 
 def local_product(ttv_b200, q, a, shard, pia, b, c):
@@ -530,6 +794,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not pin the rank to the CPUs next to its GPU")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the every-named-config leg (N = 1)")
+    ap.add_argument("--sweep-set", default="named", help="config family of ttv_b200/workloads.py for the sweep leg")
+    ap.add_argument("--sweep-reps", type=int, default=7)
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the 2048^3 fp64 strong-scaling leg")
+    ap.add_argument("--no-selfcheck", action="store_true", help="N > 1: skip the small-tensor parity check of the sharded path")
     ap.add_argument("--nccl-reduce", action="store_true", help="N > 1: plain kernel + ncclReduce for the n_q-split product instead of the fused exchange")
     args = ap.parse_args()
     if args.impl == "reference":

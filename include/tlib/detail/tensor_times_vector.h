@@ -71,4 +71,21 @@ inline void ttv(execution_t, slicing_t, fusion_t,
   if (status != TTV_B200_OK) abi::raise(status);
 }
 
+// the same call for a host tensor that keeps its copy in HBM between products (tensor::keep_on_device, ttv_b200_run_resident)
+template<class value_t, class size_t, class execution_t, class slicing_t, class fusion_t>
+inline void ttv_resident(ttv_b200_resident* twin, execution_t, slicing_t, fusion_t,
+                         std::size_t const m, std::size_t const p,
+                         value_t const* const a, size_t const* const na, size_t const* const wa, size_t const* const pia,
+                         value_t const* const b, size_t const* const nb,
+                         value_t* const c, size_t const* const nc, size_t const* const wc, size_t const* const pic)
+{
+  abi::require_supported<value_t>();
+  std::size_t const pc = p > 0u ? p - 1u : 0u;
+  abi::tuple64<size_t> na_(na, p), wa_(wa, p), pia_(pia, p), nb_(nb, 1), nc_(nc, pc), wc_(wc, pc), pic_(pic, pc);
+  ttv_b200_opts opts = abi::make_opts<execution_t, slicing_t, fusion_t>();
+  int const status = ttv_b200_run_resident(twin, abi::dtype_v<value_t>, m, p, a, na_.get(), wa_.get(), pia_.get(), b, nb_.get(),
+                                           c, nc_.get(), wc_.get(), pic_.get(), &opts);
+  if (status != TTV_B200_OK) abi::raise(status);
+}
+
 } // namespace tlib::ttv::detail

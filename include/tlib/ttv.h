@@ -4,6 +4,8 @@
 //   (1) auto C = A(q) * b;                                               operator*            reference ttv.h:122-127
 //   (2) auto C = tlib::ttv::ttv(q, A, b, ep, sp, fp);                    tensor-level         reference ttv.h:99-114
 //   (3) tlib::ttv::ttv(ep, sp, fp, q, p, a, na, wa, pia, b, nb, c, nc, wc, pic);   C-like     reference ttv.h:54-92
+// (1) and (2) also exist on tlib::ttv::device_tensor (detail/device_tensor.h): operands and result stay in HBM; and a host
+// tensor can keep a device copy between products (tensor::keep_on_device, detail/tensor.h).
 //
 // The arithmetic runs on the GPU (hand-written sm_100a kernels behind the C-ABI of include/ttv_b200.h; link with
 // -lttv_b200).  a, b, c may be host pointers (staged inside the call) or device pointers (used in place).  There is no
@@ -16,6 +18,7 @@
 #include "detail/tags.h"
 #include "detail/tensor.h"
 #include "detail/tensor_times_vector.h"
+#include "detail/device_tensor.h"
 
 namespace tlib::ttv {
 
@@ -50,10 +53,33 @@ inline auto ttv(std::size_t q, tensor<value_t> const& a, tensor<value_t> const& 
   auto c = tensor<value_t>(detail::generate_output_shape(a.shape(), q), detail::generate_output_layout(a.layout(), q));
   auto const wa = a.strides();
   auto const wc = c.strides();
+  if (ttv_b200_resident* twin = a.device_twin()) {
+    // A keeps its copy in HBM (tensor::keep_on_device): same thirteen arguments, same checks, A crosses PCIe once
+    detail::ttv_resident(twin, ep, sp, fp, q, a.order(),
+                         a.data().data(), a.shape().data(), wa.data(), a.layout().data(),
+                         b.data().data(), b.shape().data(),
+                         c.data().data(), c.shape().data(), wc.data(), c.layout().data());
+    return c;
+  }
   ttv(ep, sp, fp, q, a.order(),
       a.data().data(), a.shape().data(), wa.data(), a.layout().data(),
       b.data().data(), b.shape().data(),
       c.data().data(), c.shape().data(), wc.data(), c.layout().data());
+  return c;
+}
+
+/** Tensor-level interface on DEVICE tensors (device_tensor.h): A, b and the result live in HBM, nothing crosses PCIe. */
+template<class value_t, class execution_t, class slicing_t, class fusion_t>
+inline auto ttv(std::size_t q, device_tensor<value_t> const& a, device_tensor<value_t> const& b, execution_t ep, slicing_t sp, fusion_t fp)
+{
+  auto c = device_tensor<value_t>(detail::generate_output_shape(a.shape(), q), detail::generate_output_layout(a.layout(), q),
+                                  a.device(), /*zero=*/false);
+  auto const wa = a.strides();
+  auto const wc = c.strides();
+  ttv(ep, sp, fp, q, a.order(),
+      a.data(), a.shape().data(), wa.data(), a.layout().data(),
+      b.data(), b.shape().data(),
+      c.data(), c.shape().data(), wc.data(), c.layout().data());
   return c;
 }
 
@@ -62,6 +88,14 @@ inline auto ttv(std::size_t q, tensor<value_t> const& a, tensor<value_t> const& 
 /** auto C = A(q) * b;   uses (par_loop, subtensor, all) like the reference.                      reference ttv.h:122-127 */
 template<class value_t>
 inline auto operator*(tlib::ttv::tensor_view<value_t> const& a, tlib::ttv::tensor<value_t> const& b)
+{
+  return tlib::ttv::ttv(a.contraction_mode(), a.get_tensor(), b, tlib::ttv::execution_policy::par_loop,
+                        tlib::ttv::slicing_policy::subtensor, tlib::ttv::fusion_policy::all);
+}
+
+/** auto C = A(q) * b;  on device tensors: the result is a device tensor too. */
+template<class value_t>
+inline auto operator*(tlib::ttv::device_tensor_view<value_t> const& a, tlib::ttv::device_tensor<value_t> const& b)
 {
   return tlib::ttv::ttv(a.contraction_mode(), a.get_tensor(), b, tlib::ttv::execution_policy::par_loop,
                         tlib::ttv::slicing_policy::subtensor, tlib::ttv::fusion_policy::all);

@@ -21,10 +21,11 @@
  *     the reference's non-BLAS column kernel (matrix_times_vector.h:124).
  *   - Argument checks, their order and their messages follow ttv.h:64-89 and tensor_times_vector.h:147-168.
  *   - The call is synchronous unless TTV_B200_FLAG_ASYNC is set together with device pointers.
- *   - Threads: every entry point may be called from several host threads.  Device-pointer calls only share a small
- *     table (looked up under a short lock, never held across a launch or a wait) and one split-n_q workspace per
- *     (device, stream) -- as with any CUDA stream, one stream is fed by one thread at a time.  Host-pointer calls
- *     share the staging buffers of their device and therefore run one at a time per device (they are PCIe-bound).
+ *   - Threads: every entry point may be called from several host threads, also on ONE stream (torch's default stream is
+ *     shared by all threads of a process).  Device-pointer calls only share a small table (looked up under a short lock,
+ *     never held across a launch or a wait); the partial sums of a split n_q are a stream-ordered allocation of the call
+ *     itself, so interleaved launches never see each other's partials.  Host-pointer calls share the staging buffers of
+ *     their device and therefore run one at a time per device (they are PCIe-bound).
  *     The reference is re-entrant apart from its process-global BLAS/OpenMP settings (tensor_times_vector.h:90-143).
  *   - There is no CPU fallback: without a usable CUDA device every compute entry returns TTV_B200_ERR_CUDA.
  *     ttv_b200_plan() is pure host code and needs no device.
@@ -38,7 +39,7 @@
 extern "C" {
 #endif
 
-#define TTV_B200_VERSION 100
+#define TTV_B200_VERSION 110
 
 /* element types ----------------------------------------------------------------------------------------- */
 enum ttv_b200_dtype {
@@ -104,7 +105,9 @@ enum ttv_b200_kernel {
   TTV_B200_KERNEL_COLX   = 4,  /* column GEMV for rows that start off 16-byte boundaries: phase lanes along n_q   */
   TTV_B200_KERNEL_DOTF   = 5,  /* mode q contiguous, short fibers: A read as one flat stream, partials via smem    */
   TTV_B200_KERNEL_STRIDED = 6, /* reported only: non-packed strides (case 8), general-stride kernel; cannot be forced  */
-  TTV_B200_KERNEL_COUNT  = 6
+  TTV_B200_KERNEL_COLT   = 7,  /* column GEMV with A staged through shared memory by TMA tensor tiles (cp.async.bulk.tensor),
+                                  producer warp + mbarrier ring; chosen only when forced (measured against COL) */
+  TTV_B200_KERNEL_COUNT  = 8
 };
 
 enum ttv_b200_flags {
@@ -238,6 +241,50 @@ int ttv_b200_reduce_slots(int dtype, const void* ws, void* c, uint64_t n, uint64
  * is the counter-based splitmix64 one of SURVEY 8(d); oracle/ttv_oracle.c carries the identical host version, so
  * tensors too large for host memory can be checked by sampling. */
 int ttv_b200_fill(int dtype, void* x, uint64_t first, uint64_t count, uint64_t seed, const ttv_b200_opts* opts);
+
+/* ---- device / pinned memory for header-style hosts that do not include the CUDA runtime --------------------------------
+ * tlib::ttv::device_tensor (include/tlib/detail/device_tensor.h) is built on these.  ttv_b200_copy moves bytes in any
+ * direction (host <-> device, device <-> device); large transfers from or to PAGEABLE host memory are pipelined through the
+ * library's pinned bounce buffers and copy threads, like the host-pointer path of ttv_b200_run.  Synchronous. */
+int ttv_b200_device_alloc(void** ptr, uint64_t bytes, int device /* -1 = current */, int zero);
+int ttv_b200_device_free(void* ptr);
+int ttv_b200_host_alloc(void** ptr, uint64_t bytes);      /* page-locked host memory: H2D / D2H by DMA straight from it */
+int ttv_b200_host_free(void* ptr);
+int ttv_b200_copy(void* dst, const void* src, uint64_t bytes, const ttv_b200_opts* opts);
+
+/* ---- a HOST tensor that keeps its copy in HBM between products -----------------------------------------------------------
+ * The reference's benchmark protocol contracts every mode q = 1..p of one tensor (README.md:59-64), and its tensor class is
+ * a std::vector in host memory (detail/tensor.h:56-114): called as a drop-in, every `A(q) * b` would move all of A across
+ * PCIe again.  A ttv_b200_resident is the device-side twin of ONE host tensor: the first product after creation /
+ * invalidation streams A across PCIe in chunks under its own kernels (as ttv_b200_run does) but INTO a buffer that stays;
+ * every later product with the same (a, bytes) reads HBM and only b and C cross the bus.  The caller says when the host data
+ * changed (ttv_b200_resident_invalidate); tlib::ttv::tensor does so from its mutating accessors when
+ * tensor::keep_on_device(true) was asked for.  a, b, c are HOST pointers.  Same checks, semantics and status codes as
+ * ttv_b200_run.  One resident object serves one thread at a time. */
+typedef struct ttv_b200_resident ttv_b200_resident;
+int  ttv_b200_resident_create(ttv_b200_resident** r, int device /* -1 = current */);
+void ttv_b200_resident_destroy(ttv_b200_resident* r);
+void ttv_b200_resident_invalidate(ttv_b200_resident* r);
+int  ttv_b200_resident_valid(const ttv_b200_resident* r);    /* 1: the next product of the same tensor will not upload A */
+int  ttv_b200_run_resident(ttv_b200_resident* r, int dtype, uint64_t q, uint64_t p,
+                           const void* a, const uint64_t* na, const uint64_t* wa, const uint64_t* pia,
+                           const void* b, const uint64_t* nb,
+                           void* c, const uint64_t* nc, const uint64_t* wc, const uint64_t* pic,
+                           const ttv_b200_opts* opts);
+
+/* ---- one HOST tensor over several GPUs of this process ------------------------------------------------------------------
+ * ttv_b200_run with host pointers, the work cut along the slowest mode of A's layout over `n_devices` GPUs, one host thread
+ * per GPU, every GPU pulling its slab over its OWN PCIe link (SURVEY 8b "device list", 8e): q not the slowest mode -> free
+ * split, every GPU returns its slab of C; q the slowest mode -> n_q split, the partial sums meet on devices[0] (peer copies)
+ * and are added there in device order by ttv_reduce_kernel (deterministic), then C goes back.  Pays off for PINNED host
+ * tensors (ttv_b200_host_alloc, cudaHostRegister, torch pin_memory): pageable memory is bounced through copy threads, whose
+ * memcpy rate one GPU's link already matches.  devices may repeat (tests on a single-GPU box).  Small or strided inputs run
+ * on devices[0] alone. */
+int ttv_b200_run_devices(int dtype, uint64_t q, uint64_t p,
+                         const void* a, const uint64_t* na, const uint64_t* wa, const uint64_t* pia,
+                         const void* b, const uint64_t* nb,
+                         void* c, const uint64_t* nc, const uint64_t* wc, const uint64_t* pic,
+                         const ttv_b200_opts* opts, const int32_t* devices, uint32_t n_devices);
 
 /* L0 helpers of the reference, restated (shape.h, layout.h, strides.h); pure host code ------------------- */
 int ttv_b200_is_valid_shape  (const uint64_t* n,  uint64_t p);                       /* shape.h:30-34    */

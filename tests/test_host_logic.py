@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} is declared in include/ttv_b200.h but not exported"
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
-    assert lib.ttv_b200_version() == 100
+    assert lib.ttv_b200_version() == 110
 
 
 def test_struct_layouts_match_header():

@@ -825,3 +825,75 @@ def test_calls_from_several_host_threads(oracle, monkeypatch):
     for t in threads:
         t.join()
     assert not errors, errors[:5]
+
+
+def test_split_nq_from_several_threads_on_the_default_stream(oracle):
+    """torch's default stream is shared by every host thread of a process.  The split-n_q variant is two launches (tiles ->
+    partials, reduce -> C): the partials are a stream-ordered allocation of the call (api.cu: cudaMallocFromPoolAsync /
+    cudaFreeAsync), so calls whose launches interleave on ONE stream -- A.tile, B.tile, A.reduce, B.reduce -- must still each
+    read their own partials.  Asynchronous calls from four threads on the NULL stream, different shapes and partition counts."""
+    import threading
+    import torch
+    rng = np.random.default_rng(72)
+    cases = []
+    for na, pia, dtype in [((64, 50, 203), (1, 2, 3), np.float32), ((3000, 211), (1, 2), np.int32), ((211, 3000), (2, 1), np.int64),
+                           ((33, 47, 21), (3, 1, 2), np.float64), ((17, 9, 40, 23), (2, 1, 4, 3), np.complex64)]:
+        for q in range(1, len(na) + 1):
+            a, b = random_case(rng, na, q, dtype)
+            ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+            cases.append((q, na, pia, ta, tb, oracle.ttv(q, a, na, pia, b)))
+    torch.cuda.synchronize()
+    errors = []
+    barrier = threading.Barrier(4)
+
+    def worker(tid):
+        try:
+            barrier.wait()
+            for rep in range(6):
+                outs = []
+                for i in range(tid % 2, len(cases), 2):
+                    q, na, pia, ta, tb, want = cases[i]
+                    tc = torch.full((want.size,), 77, dtype=ta.dtype, device="cuda")
+                    nc = ttv_b200.generate_output_shape(na, q); pic = ttv_b200.generate_output_layout(pia, q)
+                    ttv_b200.ttv_lowlevel(q, len(na), ta, na, ttv_b200.generate_strides(na, pia), pia, tb, [int(tb.numel())], tc, nc,
+                                          ttv_b200.generate_strides(nc, pic), pic, ksplit=2 + (rep + tid + i) % 5, flags=2, stream=0)
+                    outs.append((i, tc))
+                torch.cuda.synchronize()
+                for i, tc in outs:
+                    if not np.array_equal(tc.cpu().numpy(), cases[i][5]):
+                        errors.append((tid, rep, cases[i][1], cases[i][2], cases[i][0]))
+        except Exception as e:                                # noqa: BLE001 - reported below
+            errors.append((tid, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:5]
+
+
+@pytest.mark.parametrize("dtype", ALL_DTYPES)
+def test_colt_kernel_tma_tensor_tiles(dtype, oracle, monkeypatch):
+    """kernel="colt": A through shared memory by cp.async.bulk.tensor tiles (colt_kernel.cuh).  Rows narrower and wider than a
+    box, rows that are not a power of two of words (zero-filled columns), contractions shorter / longer than a box and not a
+    multiple of it (zero-filled rows), several slabs, n_q split across work items, few and many stages, accumulate."""
+    rng = np.random.default_rng(23)
+    name = {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64", np.dtype(np.complex64): "c64",
+            np.dtype(np.complex128): "c128", np.dtype(np.int32): "i32", np.dtype(np.int64): "i64"}[np.dtype(dtype)]
+    vec = 16 // np.dtype(dtype).itemsize
+    cases = [((64 * vec, 40, 3), (1, 2, 3), 2), ((1024 * vec, 33), (1, 2), 2), ((4 * vec, 300, 5), (1, 2, 3), 2), ((100 * vec, 7, 9), (1, 2, 3), 2),
+             ((36 * vec, 5, 130, 4), (1, 2, 3, 4), 3), ((48, 17 * vec, 50), (2, 1, 3), 3), ((333 * vec, 257), (1, 2), 2), ((16 * vec, 2, 11), (1, 2, 3), 2)]
+    for stages, stage_kb in (("4", "32"), ("2", "4"), ("8", "8")):
+        monkeypatch.setenv("TTV_B200_COLT_STAGES", stages)
+        monkeypatch.setenv("TTV_B200_COLT_STAGE_KB", stage_kb)
+        for na, pia, q in cases:
+            a, b = random_case(rng, na, q, dtype)
+            want = oracle.ttv(q, a, na, pia, b)
+            assert ttv_b200.plan(q, na, pia, dtype=name, kernel="colt")["kernel"] == 7
+            for ks in (0, 3):
+                assert np.array_equal(run_lowlevel(q, a, na, pia, b, kernel="colt", ksplit=ks), want), (na, pia, q, dtype, stages, ks)
+            c0 = np.full(want.size, 3, dtype)
+            assert np.array_equal(run_lowlevel(q, a, na, pia, b, c0=c0, kernel="colt", flags=1), want + 3)
+    with pytest.raises(ttv_b200.TTVError):                          # rows that are not whole 16-byte vectors
+        ttv_b200.plan(2, (64 * vec + 1, 9), (1, 2), dtype=name, kernel="colt") if vec > 1 else ttv_b200.plan(1, (9, 64), (1, 2), dtype=name, kernel="colt")

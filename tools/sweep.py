@@ -2,7 +2,10 @@
 """tools/sweep.py -- effective HBM GB/s of the TTV kernels over the BASELINE.json config families (device-resident,
 CUDA events, inputs larger than L2 or rotated).  Development / evidence tool; writes JSON lines.
 
-    python tools/sweep.py [--set quick|cfg1|sym|asym|complex|fp64|all] [--out gpurun_out/sweep.jsonl] [--variants]
+    python tools/sweep.py [--set quick|cfg1|sym|asym|complex|fp64|all|cplxall|named] [--out gpurun_out/sweep.jsonl] [--variants]
+
+Every product is also CHECKED: sampled outputs of the last launch against a host long-double dot on regenerated fibers
+(ttv_b200/selfcheck.py; bit-exact for int32).  The same engine (ttv_b200/measure.py) runs inside bench.py.
 """
 from __future__ import annotations
 
@@ -21,112 +24,34 @@ import ttv_b200  # noqa: E402
 
 TORCH_DT = {"f32": torch.float32, "f64": torch.float64, "c64": torch.complex64, "c128": torch.complex128,
             "i32": torch.int32, "i64": torch.int64}
-SIZE = {"f32": 4, "f64": 8, "c64": 8, "c128": 16, "i32": 4, "i64": 8}
-L2 = 126 * 2 ** 20
+from ttv_b200.measure import Arena, measure_config  # noqa: E402
+from ttv_b200.workloads import configs  # noqa: E402  (the named config families live in the package: bench.py uses them too)
+
 B2B = 0          # --b2b N: also time N launches back to back inside one event pair
+_ARENAS = {}
 
 
-def configs(which):
-    out = []
-    first = lambda p: list(range(1, p + 1))
-    last = lambda p: list(range(p, 0, -1))
-    if which in ("quick", "cfg1", "all"):
-        out += [("cfg1", "f32", [512, 512, 512], first(3), q) for q in (1, 2, 3)]
-    if which == "scal":      # size series of the cfg1 shape: fixed cost per launch against streaming rate
-        out += [("scal%d" % m, "f32", [512, 512, m], first(3), q) for m in (128, 256, 512, 1024, 2048, 4096) for q in (1, 2, 3)]
-    if which == "dotk":      # fibers of 1 .. 16 KB at 4 GiB and at 512 MiB: lanes per fiber / CTA size of the DOT kernel
-        out += [("dotk%d" % m, "f32", [m, (1 << 30) // m], first(2), 1) for m in (256, 512, 1024, 2048, 4096)]
-        out += [("dots%d" % m, "f32", [m, (1 << 27) // m], first(2), 1) for m in (256, 512, 1024, 2048, 4096)]
-    if which == "cplxall":   # BASELINE configs[3] in full: order 4..6, complex<float> / complex<double>, last-order + 2 seeded random layouts, every q
-        for pp, ext in ((4, 128), (5, 48), (6, 25)):
-            lays = [("L", last(pp))]
-            for seed in (1, 2):
-                perm = [int(x) + 1 for x in np.random.default_rng(seed).permutation(pp)]
-                lays.append(("R%d" % seed, perm))
-            for dt in ("c64", "c128"):
-                for tag, pia in lays:
-                    out += [("cx%d%s" % (pp, tag), dt, [ext] * pp, pia, q) for q in range(1, pp + 1)]
-    if which == "pad":       # slices of a packed 256^4 tensor, read in place through wa (TTV_B200_FLAG_HONOR_STRIDES)
-        w4 = [1, 256, 256 ** 2, 256 ** 3]
-        out += [("pad3", "f32", [256, 256, 250, 256], first(4), q, w4) for q in (1, 2, 3, 4)]      # A[:, :, :250, :]
-        out += [("pad1", "f32", [250, 256, 256, 256], first(4), q, w4) for q in (1, 2, 3, 4)]      # A[:250]: padded rows
-        out += [("pad12", "f64", [120, 250, 128, 128], first(4), q, [1, 128, 128 * 256, 128 * 256 * 128]) for q in (1, 2, 3, 4)]
-    if which == "padv":      # what decides between the vector and the thread-per-output form of the general-stride kernel
-        w4 = [1, 256, 256 ** 2, 256 ** 3]
-        out += [("pad1b", "f32", [248, 256, 256, 256], first(4), q, w4) for q in (2, 3, 4)]       # rows of 248 of 256 floats
-        out += [("pad12L", "f64", [120, 250, 256, 256], first(4), q, [1, 128, 128 * 256, 128 * 256 * 256]) for q in (2, 3, 4)]
-        out += [("pad3h", "f32", [256, 256, 250, 32], first(4), q, w4) for q in (2, 3, 4)]         # 2 GB: fewer waves
-        out += [("pad3c", "c64", [128, 256, 250, 128], first(4), q, [1, 128, 128 * 256, 128 * 256 * 256]) for q in (2, 3, 4)]
-    if which in ("quick", "sym", "all"):
-        out += [("sym4", "f32", [256] * 4, first(4), q) for q in (1, 2, 3, 4)]
-    if which in ("sym", "all"):
-        out += [("sym2", "f32", [65536, 65536], first(2), q) for q in (1, 2)]
-        out += [("sym3", "f32", [1625] * 3, first(3), q) for q in (1, 2, 3)]
-        out += [("sym5", "f32", [84] * 5, first(5), q) for q in range(1, 6)]
-        out += [("sym6", "f32", [40] * 6, first(6), q) for q in range(1, 7)]
-        out += [("sym7", "f32", [23] * 7, first(7), q) for q in range(1, 8)]
-    if which in ("fp64", "all"):
-        out += [("cfg5/8", "f64", [2048, 2048, 256], first(3), q) for q in (1, 2, 3)]
-        out += [("sym2d", "f64", [46340] * 2, first(2), q) for q in (1, 2)]
-        out += [("sym3d", "f64", [1290] * 3, first(3), q) for q in (1, 2, 3)]
-        out += [("sym4d", "f64", [215] * 4, first(4), q) for q in range(1, 5)]
-        out += [("sym5d", "f64", [73] * 5, first(5), q) for q in range(1, 6)]
-        out += [("sym6d", "f64", [36] * 6, first(6), q) for q in range(1, 7)]
-        out += [("sym7d", "f64", [21] * 7, first(7), q) for q in range(1, 8)]
-    if which in ("asym", "all"):
-        for dt in ("f32", "i32"):
-            out += [("asym5", dt, [4, 1 << 18, 2, 2, 256], first(5), q) for q in (1, 2, 3, 4, 5)]
-            out += [("asym4", dt, [16, 1024, 4, 1 << 14], first(4), q) for q in (1, 2, 3, 4)]
-            out += [("asym6", dt, [2, 3, 1 << 20, 2, 4, 16], first(6), q) for q in (1, 2, 3, 4, 6)]
-            out += [("asym8", dt, [4, 1 << 16, 2, 2, 3, 2, 2, 64], first(8), q) for q in (1, 2, 5, 8)]
-            out += [("asym10", dt, [2, 2, 4, 2, 1 << 15, 2, 3, 2, 2, 128], first(10), q) for q in (1, 3, 5, 7, 10)]
-    if which in ("complex", "all"):
-        out += [("cplx4", "c64", [128] * 4, last(4), q) for q in (1, 2, 4)]
-        out += [("cplx4r", "c64", [128] * 4, [3, 1, 4, 2], q) for q in (1, 2, 3, 4)]
-        out += [("cplx5", "c128", [40] * 5, last(5), q) for q in (1, 3, 5)]
-        out += [("cplx6", "c128", [25, 24, 25, 24, 20, 22], [2, 5, 1, 6, 3, 4], q) for q in (1, 2, 5, 6)]
-    return out
-
-
-def bench_one(dt, na, pia, q, reps=10, wa=None, **opts):
-    n = int(np.prod(na, dtype=object))
-    s = SIZE[dt]
-    copies = max(1, min(4, -(-4 * L2 // (n * s))))         # rotate when A is not much larger than L2
-    As = []
-    span = n if wa is None else 1 + sum((e - 1) * w for e, w in zip(na, wa))
-    for i in range(copies):
-        a = torch.empty(span, dtype=TORCH_DT[dt], device="cuda")
-        ttv_b200.fill(a, 0x77170001 + i)
-        As.append(a)
-    b = torch.empty(na[q - 1], dtype=TORCH_DT[dt], device="cuda")
-    ttv_b200.fill(b, 0x77170002)
-    nc = ttv_b200.generate_output_shape(na, q); pic = ttv_b200.generate_output_layout(pia, q)
-    flags = 2 if wa is None else 2 | 8
-    wa = ttv_b200.generate_strides(na, pia) if wa is None else list(wa)
-    wc = ttv_b200.generate_strides(nc, pic)
-    c = torch.empty(n // na[q - 1], dtype=TORCH_DT[dt], device="cuda")
-    run = lambda a: ttv_b200.ttv_lowlevel(q, len(na), a, na, wa, pia, b, [na[q - 1]], c, nc, wc, pic, flags=flags, **opts)
-    for i in range(3):
-        run(As[i % copies])
-    torch.cuda.synchronize()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-    for i, (e0, e1) in enumerate(evs):
-        e0.record(); run(As[i % copies]); e1.record()
-    torch.cuda.synchronize()
-    ts = sorted(e0.elapsed_time(e1) for e0, e1 in evs)
-    byt = s * (n + na[q - 1] + n // na[q - 1])
-    out = {"ms_med": ts[len(ts) // 2], "ms_min": ts[0], "gbs_med": byt / ts[len(ts) // 2] / 1e6, "gbs_best": byt / ts[0] / 1e6, "bytes": byt}
-    if B2B:
+def bench_one(dt, na, pia, q, reps=10, wa=None, check=True, **opts):
+    """one product: timing (CUDA events around every launch) + sampled parity of the last launch (ttv_b200.selfcheck)"""
+    if not _ARENAS:
+        _ARENAS["a"] = Arena(int(17.5e9))
+        _ARENAS["c"] = Arena(int(8.8e9))
+    out = measure_config(dt, na, pia, q, wa=wa, reps=reps, check=check, arena_a=_ARENAS["a"], arena_c=_ARENAS["c"], **opts)
+    if B2B and wa is None:
         # the same launches back to back inside ONE event pair: per-launch time without the event / launch gaps
+        a = _ARENAS["a"].buf[: int(np.prod(na, dtype=object)) * ttv_b200.workloads.SIZE[dt]].view(TORCH_DT[dt])
+        b = torch.empty(na[q - 1], dtype=TORCH_DT[dt], device="cuda"); ttv_b200.fill(b, 0x77170002)
+        nc = ttv_b200.generate_output_shape(na, q); pic = ttv_b200.generate_output_layout(pia, q)
+        c = _ARENAS["c"].buf[: (int(np.prod(na, dtype=object)) // na[q - 1]) * ttv_b200.workloads.SIZE[dt]].view(TORCH_DT[dt])
+        wa_, wc = ttv_b200.generate_strides(na, pia), ttv_b200.generate_strides(nc, pic)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(B2B):
-            run(As[i % copies])
+            ttv_b200.ttv_lowlevel(q, len(na), a, na, wa_, pia, b, [na[q - 1]], c, nc, wc, pic, flags=2, **opts)
         e1.record()
         torch.cuda.synchronize()
         out["ms_b2b"] = e0.elapsed_time(e1) / B2B
-        out["gbs_b2b"] = byt / out["ms_b2b"] / 1e6
-    del As
+        out["gbs_b2b"] = out["bytes"] / out["ms_b2b"] / 1e6
     return out
 
 
@@ -141,6 +66,7 @@ def main():
     ap.add_argument("--ksplits", default="", help="comma-separated forced n_q splits to try on each config, e.g. '2,4,8'")
     ap.add_argument("--qs", default="", help="comma-separated modes to keep")
     ap.add_argument("--b2b", type=int, default=0, help="also time N launches back to back inside one event pair")
+    ap.add_argument("--no-check", action="store_true", help="skip the sampled parity check of every product")
     args = ap.parse_args()
     global B2B
     B2B = args.b2b
@@ -171,7 +97,7 @@ def main():
                 opts = {k: v for k, v in var.items() if k != "env"}
                 try:
                     pl = ttv_b200.plan(q, na, pia, dtype=dt, wa=wa, **({**opts, "flags": 8} if wa else opts))
-                    r = bench_one(dt, na, pia, q, reps=args.reps, wa=wa, **opts)
+                    r = bench_one(dt, na, pia, q, reps=args.reps, wa=wa, check=not args.no_check, **opts)
                 except Exception as exc:
                     r, pl = {"error": str(exc)}, {}
                 for k in env:
@@ -184,6 +110,8 @@ def main():
                     print(f"{name:8s} {dt:5s} q={q} view={rec['view']} k={rec['kernel']} v={rec['vec']} tx={rec['tx']} ty={rec['ty']} "
                           f"ks={rec['ksplit']} nu={pl.get('nu')} ku={pl.get('ku')} ctas={rec['ctas']} {rec['variant']}  {r['ms_med']:.4f} ms  {r['gbs_med']:.0f} GB/s ({rec['frac_measured']:.2f})"
                           + (f"  b2b {r['gbs_b2b']:.0f}" if "gbs_b2b" in r else ""), flush=True)
+                    if r.get("failures"):
+                        print(f"   PARITY FAILURE: {r['failures']} of {r['checked']} sampled outputs, worst err/tol {r['worst_err_over_tol']:.3g}", flush=True)
                 else:
                     print(f"{name:8s} {dt:5s} q={q} ERROR {r['error']}", flush=True)
                 f.write(json.dumps(rec) + "\n"); f.flush()

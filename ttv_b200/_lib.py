@@ -58,6 +58,17 @@ SYMBOLS = {
                                         C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(Opts)]),
     "ttv_b200_reduce_slots": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(Opts)]),
     "ttv_b200_fill": (C.c_int, [C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(Opts)]),
+    "ttv_b200_device_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64, C.c_int, C.c_int]),
+    "ttv_b200_device_free": (C.c_int, [C.c_void_p]),
+    "ttv_b200_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
+    "ttv_b200_host_free": (C.c_int, [C.c_void_p]),
+    "ttv_b200_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(Opts)]),
+    "ttv_b200_resident_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "ttv_b200_resident_destroy": (None, [C.c_void_p]),
+    "ttv_b200_resident_invalidate": (None, [C.c_void_p]),
+    "ttv_b200_resident_valid": (C.c_int, [C.c_void_p]),
+    "ttv_b200_run_resident": (C.c_int, [C.c_void_p, C.c_int] + _RUN_ARGS),
+    "ttv_b200_run_devices": (C.c_int, [C.c_int] + _RUN_ARGS + [C.POINTER(C.c_int32), C.c_uint32]),
     "ttv_b200_is_valid_shape": (C.c_int, [u64p, C.c_uint64]),
     "ttv_b200_is_valid_layout": (C.c_int, [u64p, C.c_uint64]),
     "ttv_b200_is_valid_strides": (C.c_int, [u64p, C.c_uint64, u64p]),

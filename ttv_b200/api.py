@@ -29,7 +29,7 @@ EXECUTION = {"seq": 0, "seq_blas": 1, "par": 2, "par_loop": 3, "par_taskloop": 4
              "par_blas_loop": 7}
 SLICING = {"slice": 0, "subtensor": 1}
 FUSION = {"none": 0, "outer": 1, "all": 2}
-KERNELS = {"auto": 0, "dot": 1, "col": 2, "stream": 3, "colx": 4, "dotf": 5}
+KERNELS = {"auto": 0, "dot": 1, "col": 2, "stream": 3, "colx": 4, "dotf": 5, "colt": 7}
 
 FLAG_ACCUMULATE, FLAG_ASYNC, FLAG_NO_VEC = 1, 2, 4
 
@@ -233,6 +233,105 @@ def ttv_lowlevel(q: int, p: int, a, na, wa, pia, b, nb, c, nc, wc, pic, *, dtype
     (na_, wa_, pia_, nb_, nc_, wc_, pic_) = [k[1] for k in keep]
     st = lib.ttv_b200_run(dtype, q, p, _ptr(a), na_, wa_, pia_, _ptr(b), nb_, _ptr(c), nc_, wc_, pic_, C.byref(opts))
     _check(st)
+
+
+def prepared_lowlevel(q: int, p: int, a, na, wa, pia, b, nb, c, nc, wc, pic, *, opts: Opts | None = None, **opt_kwargs):
+    """ttv_lowlevel with everything that does not change between calls done ONCE (operand checks, tuple conversion, the opts
+    block): returns `run()`, which is one ctypes call of ttv_b200_run -- a few microseconds of host time instead of the
+    ~40 of the convenience wrapper.  For loops over short products (a 512 MiB tensor is an 80 us kernel) where the host
+    must stay ahead of the GPU.  The operands are captured: refill them in place between calls."""
+    lib = _lib.load()
+    _check_operands(a, b, c)
+    dtype = dtype_code(next(x for x in (a, b, c) if x is not None and not isinstance(x, int)))
+    if opts is None:
+        if "stream" not in opt_kwargs:
+            dev = next((x for x in (a, b, c) if x is not None and _is_torch(x) and x.is_cuda), None)
+            if dev is not None:
+                opt_kwargs["stream"] = _current_torch_stream(dev)
+        opts = make_opts(**opt_kwargs)
+    keep = [_tuple(v) for v in (na, wa, pia, nb, nc, wc, pic)]
+    (na_, wa_, pia_, nb_, nc_, wc_, pic_) = [k[1] for k in keep]
+    pa, pb, pc = _ptr(a), _ptr(b), _ptr(c)
+    ref = C.byref(opts)
+    fn = lib.ttv_b200_run
+
+    def run(_keep=(a, b, c, keep, opts)):
+        st = fn(dtype, q, p, pa, na_, wa_, pia_, pb, nb_, pc, nc_, wc_, pic_, ref)
+        if st:
+            _check(st)
+
+    return run
+
+
+class Resident:
+    """Device-side twin of ONE host tensor (ttv_b200_resident): the first product after creation / invalidate() streams A
+    across PCIe under its own kernels into a buffer that stays in HBM; later products of the same array only move b and C.
+    This is what tlib::ttv::tensor::keep_on_device(true) uses behind `A(q) * b`; call invalidate() when the host data
+    changed."""
+
+    def __init__(self, device: int = -1):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        _check(self._lib.ttv_b200_resident_create(C.byref(h), int(device)))
+        self._h = h
+
+    def invalidate(self) -> None:
+        self._lib.ttv_b200_resident_invalidate(self._h)
+
+    @property
+    def valid(self) -> bool:
+        return bool(self._lib.ttv_b200_resident_valid(self._h))
+
+    def ttv_lowlevel(self, q: int, p: int, a, na, wa, pia, b, nb, c, nc, wc, pic, *, opts: Opts | None = None, **opt_kwargs) -> None:
+        """ttv_lowlevel with HOST buffers whose A keeps its copy on the device (ttv_b200_run_resident)"""
+        _check_operands(a, b, c)
+        if opts is None:
+            opts = make_opts(**opt_kwargs)
+        keep = [_tuple(v) for v in (na, wa, pia, nb, nc, wc, pic)]
+        (na_, wa_, pia_, nb_, nc_, wc_, pic_) = [k[1] for k in keep]
+        _check(self._lib.ttv_b200_run_resident(self._h, dtype_code(a), q, p, _ptr(a), na_, wa_, pia_, _ptr(b), nb_, _ptr(c), nc_, wc_,
+                                               pic_, C.byref(opts)))
+
+    def close(self) -> None:
+        if self._h is not None and self._h.value:
+            self._lib.ttv_b200_resident_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def ttv_lowlevel_devices(devices: Sequence[int], q: int, p: int, a, na, wa, pia, b, nb, c, nc, wc, pic, *, opts: Opts | None = None,
+                         **opt_kwargs) -> None:
+    """ttv_lowlevel with HOST buffers, the work cut along the slowest mode of A over several GPUs of this process, one
+    host thread and one PCIe link per GPU (ttv_b200_run_devices)."""
+    lib = _lib.load()
+    _check_operands(a, b, c)
+    if opts is None:
+        opts = make_opts(**opt_kwargs)
+    keep = [_tuple(v) for v in (na, wa, pia, nb, nc, wc, pic)]
+    (na_, wa_, pia_, nb_, nc_, wc_, pic_) = [k[1] for k in keep]
+    devs = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+    _check(lib.ttv_b200_run_devices(dtype_code(a), q, p, _ptr(a), na_, wa_, pia_, _ptr(b), nb_, _ptr(c), nc_, wc_, pic_, C.byref(opts),
+                                    devs, len(devices)))
+
+
+def pinned_empty(count: int, dtype) -> np.ndarray:
+    """a numpy array in page-locked host memory (ttv_b200_host_alloc): H2D / D2H run by DMA straight from it.  The memory is
+    released when the array (and every view of it) is gone."""
+    lib = _lib.load()
+    dt = np.dtype(dtype)
+    nbytes = int(count) * dt.itemsize
+    ptr = C.c_void_p()
+    _check(lib.ttv_b200_host_alloc(C.byref(ptr), nbytes))
+
+    import weakref
+    buf = (C.c_char * max(nbytes, 1)).from_address(ptr.value)
+    weakref.finalize(buf, lib.ttv_b200_host_free, C.c_void_p(ptr.value))      # numpy keeps `buf` alive through arr.base
+    return np.frombuffer(buf, dtype=dt, count=int(count))
 
 
 def ttv_multi(qs: Sequence[int], a, na, pia, bs, cs=None, *, wa=None, opts: Opts | None = None, **opt_kwargs):

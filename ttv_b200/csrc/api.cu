@@ -21,6 +21,7 @@
 #include <memory>
 #include <thread>
 #include <algorithm>
+#include <new>
 
 using namespace ttvb;
 
@@ -234,8 +235,10 @@ int env_mb(const char* name, int fallback)
 // buffers of A live on the device, so the tensor may be larger than what is free in HBM.
 // Returns -1 when the call is not eligible (small, strided, one indivisible slab): the caller takes the plain path.
 int run_host_pipelined(int dtype, uint64_t count, const View* views, const void* a, const void* const* b, void* const* c,
-                       const ttv_b200_opts* opts, int device, bool bc_dev = false)
+                       const ttv_b200_opts* opts, int device, bool bc_dev = false, char* resident = nullptr)
 {
+  // resident: the chunks of A land side by side in this device buffer (|A| bytes) instead of the three-slot ring, and stay
+  // there for the products that follow (ttv_b200_run_resident); nothing is ever overwritten, so no slot has to be freed
   // bc_dev: the vectors and the results are DEVICE buffers (the first product of a chain): nothing of them is staged
   const size_t s = (size_t)dtype_size(dtype);
   const View& v0 = views[0];
@@ -301,7 +304,7 @@ int run_host_pipelined(int dtype, uint64_t count, const View* views, const void*
         CUDA_TRY(cudaEventCreateWithFlags(&st->freed[r], cudaEventDisableTiming), "cudaEventCreate");
       }
     }
-    for (int r = 0; r < 3; ++r) if (int rc = ensure(st->ring[r], chunk_bytes)) return rc;
+    if (!resident) for (int r = 0; r < 3; ++r) if (int rc = ensure(st->ring[r], chunk_bytes)) return rc;
     if (bounce && st->bounce_bytes < chunk_bytes) {
       for (int r = 0; r < 3; ++r) {
         if (st->bounce[r]) { cudaFreeHost(st->bounce[r]); st->bounce[r] = nullptr; }
@@ -357,8 +360,9 @@ int run_host_pipelined(int dtype, uint64_t count, const View* views, const void*
   for (uint64_t ch = 0; ch < chunks; ++ch) {
     const int r = (int)(ch % 3);
     const uint64_t s0 = ch * per, s1 = std::min(slow, s0 + per), ns = s1 - s0;
-    if (ch >= 3) CUDA_TRY(cudaStreamWaitEvent(st->copy_stream, st->freed[r], 0), "cudaStreamWaitEvent");
+    if (ch >= 3 && !resident) CUDA_TRY(cudaStreamWaitEvent(st->copy_stream, st->freed[r], 0), "cudaStreamWaitEvent");
     if (int rc = drain(r)) return rc;                   // chunk ch-3 of C leaves bounce_out[r] before it is refilled
+    void* const slot = resident ? static_cast<void*>(resident + (size_t)(s0 * slab) * s) : st->ring[r].ptr;
     const char* src = ah + (size_t)(s0 * slab) * s;
     if (bounce) {
       // bounce[r] was last read by the DMA of chunk ch-3, whose completion is ready[r]
@@ -366,7 +370,7 @@ int run_host_pipelined(int dtype, uint64_t count, const View* views, const void*
       copy_pool().copy(st->bounce[r], src, (size_t)(ns * slab) * s);
       src = static_cast<const char*>(st->bounce[r]);
     }
-    CUDA_TRY(cudaMemcpyAsync(st->ring[r].ptr, src, (size_t)(ns * slab) * s, cudaMemcpyHostToDevice, st->copy_stream),
+    CUDA_TRY(cudaMemcpyAsync(slot, src, (size_t)(ns * slab) * s, cudaMemcpyHostToDevice, st->copy_stream),
              "cudaMemcpyAsync H2D A chunk");
     CUDA_TRY(cudaEventRecord(st->ready[r], st->copy_stream), "cudaEventRecord");
     CUDA_TRY(cudaStreamWaitEvent(stream, st->ready[r], 0), "cudaStreamWaitEvent");
@@ -387,7 +391,7 @@ int run_host_pipelined(int dtype, uint64_t count, const View* views, const void*
       }
       local.flags &= ~(uint32_t)TTV_B200_FLAG_ASYNC;
       local.stream = stream;
-      if (int rc = run_view_device(dtype, v, st->ring[r].ptr, bsrc, cdst, &local, device, false)) return rc;
+      if (int rc = run_view_device(dtype, v, slot, bsrc, cdst, &local, device, false)) return rc;
       if (!nq_split && c_pinned[i]) {      // (a copy into pageable memory would block the host and with it the next chunk)
         const size_t bytes = (size_t)(v.outer * v.inner) * s;
         CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(c[i]) + (cdst - dci[i]), cdst, bytes, cudaMemcpyDeviceToHost, stream),
@@ -477,6 +481,118 @@ int run_any(int dtype, const View& v, const void* a, const void* b, void* c, con
   const bool async = opts && (opts->flags & TTV_B200_FLAG_ASYNC);
   return run_view_device(dtype, v, a, b, c, opts, da, !async);
 }
+
+// ---- plain copies between host and device, pageable memory pipelined through the pinned bounce buffers --------------------
+// Caller holds the device's host_mutex and has the device current.  Both return after the copy has completed.
+int ensure_bounce_in(DeviceState* st, size_t chunk)
+{
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (!st->copy_stream) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&st->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (int r = 0; r < 3; ++r) {
+      CUDA_TRY(cudaEventCreateWithFlags(&st->ready[r], cudaEventDisableTiming), "cudaEventCreate");
+      CUDA_TRY(cudaEventCreateWithFlags(&st->freed[r], cudaEventDisableTiming), "cudaEventCreate");
+    }
+  }
+  if (st->bounce_bytes < chunk) {
+    for (int r = 0; r < 3; ++r) {
+      if (st->bounce[r]) { cudaFreeHost(st->bounce[r]); st->bounce[r] = nullptr; }
+      st->bounce_bytes = 0;
+      CUDA_TRY(cudaHostAlloc(&st->bounce[r], chunk, cudaHostAllocDefault), "cudaHostAlloc");
+    }
+    st->bounce_bytes = chunk;
+  }
+  return TTV_B200_OK;
+}
+
+int ensure_bounce_out(DeviceState* st, size_t chunk)
+{
+  std::lock_guard<std::mutex> lock(g_mutex);
+  for (int r = 0; r < 3; ++r)
+    if (!st->out_done[r]) CUDA_TRY(cudaEventCreateWithFlags(&st->out_done[r], cudaEventDisableTiming), "cudaEventCreate");
+  if (st->bounce_out_bytes < chunk) {
+    for (int r = 0; r < 3; ++r) {
+      if (st->bounce_out[r]) { cudaFreeHost(st->bounce_out[r]); st->bounce_out[r] = nullptr; }
+      st->bounce_out_bytes = 0;
+      CUDA_TRY(cudaHostAlloc(&st->bounce_out[r], chunk, cudaHostAllocDefault), "cudaHostAlloc");
+    }
+    st->bounce_out_bytes = chunk;
+  }
+  return TTV_B200_OK;
+}
+
+size_t bounce_chunk(size_t bytes)
+{
+  // ~16 chunks per transfer, 4 .. 32 MiB each: the memcpy of the first chunk and the DMA of the last one are the only parts
+  // of the pipeline that do not overlap
+  return std::min<size_t>((size_t)32 << 20, std::max<size_t>((size_t)4 << 20, (bytes / 16 + 4095) / 4096 * 4096));
+}
+
+int copy_h2d(DeviceState* st, void* dst, const void* src, size_t bytes, cudaStream_t stream)
+{
+  if (bytes == 0) return TTV_B200_OK;
+  if (bytes < ((size_t)8 << 20) || is_pinned_host(src) || env_mb("TTV_B200_BOUNCE", 1) == 0) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync H2D");
+    CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+    return TTV_B200_OK;
+  }
+  const size_t chunk = bounce_chunk(bytes);
+  if (int rc = ensure_bounce_in(st, chunk)) return rc;
+  size_t off = 0;
+  for (uint64_t ch = 0; off < bytes; ++ch, off += chunk) {
+    const int r = (int)(ch % 3);
+    const size_t n = std::min(chunk, bytes - off);
+    if (ch >= 3) CUDA_TRY(cudaEventSynchronize(st->ready[r]), "cudaEventSynchronize");      // the DMA of chunk ch-3 has read bounce[r]
+    copy_pool().copy(st->bounce[r], static_cast<const char*>(src) + off, n);
+    CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(dst) + off, st->bounce[r], n, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync H2D chunk");
+    CUDA_TRY(cudaEventRecord(st->ready[r], stream), "cudaEventRecord");
+  }
+  CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+  return TTV_B200_OK;
+}
+
+int copy_d2h(DeviceState* st, void* dst, const void* src, size_t bytes, cudaStream_t stream)
+{
+  if (bytes == 0) return TTV_B200_OK;
+  if (bytes < ((size_t)8 << 20) || is_pinned_host(dst) || env_mb("TTV_B200_BOUNCE", 1) == 0 || env_mb("TTV_B200_BOUNCE_OUT", 1) == 0) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync D2H");
+    CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+    return TTV_B200_OK;
+  }
+  const size_t chunk = bounce_chunk(bytes);
+  if (int rc = ensure_bounce_out(st, chunk)) return rc;
+  const uint64_t chunks = (bytes + chunk - 1) / chunk;
+  auto land = [&](uint64_t ch) -> int {                   // chunk ch sits in bounce_out[ch % 3] once out_done[ch % 3] has fired
+    const int r = (int)(ch % 3);
+    CUDA_TRY(cudaEventSynchronize(st->out_done[r]), "cudaEventSynchronize");
+    copy_pool().copy(static_cast<char*>(dst) + ch * chunk, st->bounce_out[r], std::min(chunk, bytes - (size_t)ch * chunk));
+    return TTV_B200_OK;
+  };
+  for (uint64_t ch = 0; ch < chunks; ++ch) {
+    const int r = (int)(ch % 3);
+    if (ch >= 3) if (int rc = land(ch - 3)) return rc;
+    const size_t n = std::min(chunk, bytes - (size_t)ch * chunk);
+    CUDA_TRY(cudaMemcpyAsync(st->bounce_out[r], static_cast<const char*>(src) + ch * chunk, n, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync D2H chunk");
+    CUDA_TRY(cudaEventRecord(st->out_done[r], stream), "cudaEventRecord");
+  }
+  for (uint64_t ch = chunks > 3 ? chunks - 3 : 0; ch < chunks; ++ch) if (int rc = land(ch)) return rc;
+  return TTV_B200_OK;
+}
+
+} // namespace
+
+// a host tensor's twin in HBM (include/ttv_b200.h: ttv_b200_resident)
+struct ttv_b200_resident {
+  std::mutex  mutex;
+  int         device = -1;
+  void*       dev = nullptr;       // |A| bytes on `device`
+  size_t      capacity = 0;
+  const void* host = nullptr;      // the host tensor the copy was made from ...
+  size_t      bytes = 0;           // ... and how much of it
+  bool        valid = false;
+};
+
+namespace {
 
 // ---- the chain of p-1 products (reference ttvpy/src/wrapped_ttv.cpp:83-198) ----------------------------------------
 // Which mode each step contracts and with which vector: vector j belongs to mode r = j+1 (j+1 < q) or j+2.
@@ -904,6 +1020,291 @@ int ttv_b200_fill(int dtype, void* x, uint64_t first, uint64_t count, uint64_t s
   CUDA_TRY(launch_fill(dtype, x, first, count, seed, sm, stream), "fill launch");
   if (!(opts && (opts->flags & TTV_B200_FLAG_ASYNC))) CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
   return TTV_B200_OK;
+}
+
+// ---- device / pinned memory helpers ---------------------------------------------------------------------------------
+int ttv_b200_device_alloc(void** ptr, uint64_t bytes, int device, int zero)
+{
+  if (!ptr) return fail(TTV_B200_ERR_OPTS, "ttv_b200_device_alloc: ptr must not be null");
+  *ptr = nullptr;
+  if (device < 0) CUDA_TRY(cudaGetDevice(&device), "cudaGetDevice (is a CUDA device visible?)");
+  DeviceGuard guard;
+  CUDA_TRY(guard.set(device), "cudaSetDevice");
+  CUDA_TRY(cudaMalloc(ptr, std::max<size_t>((size_t)bytes, 256)), "cudaMalloc");
+  if (zero) {
+    const cudaError_t e = cudaMemset(*ptr, 0, (size_t)bytes);
+    if (e != cudaSuccess) { cudaFree(*ptr); *ptr = nullptr; return fail_cuda(e, "cudaMemset"); }
+  }
+  return TTV_B200_OK;
+}
+
+int ttv_b200_device_free(void* ptr)
+{
+  if (!ptr) return TTV_B200_OK;
+  CUDA_TRY(cudaFree(ptr), "cudaFree");
+  return TTV_B200_OK;
+}
+
+int ttv_b200_host_alloc(void** ptr, uint64_t bytes)
+{
+  if (!ptr) return fail(TTV_B200_ERR_OPTS, "ttv_b200_host_alloc: ptr must not be null");
+  *ptr = nullptr;
+  CUDA_TRY(cudaHostAlloc(ptr, std::max<size_t>((size_t)bytes, 64), cudaHostAllocPortable), "cudaHostAlloc");
+  return TTV_B200_OK;
+}
+
+int ttv_b200_host_free(void* ptr)
+{
+  if (!ptr) return TTV_B200_OK;
+  CUDA_TRY(cudaFreeHost(ptr), "cudaFreeHost");
+  return TTV_B200_OK;
+}
+
+int ttv_b200_copy(void* dst, const void* src, uint64_t bytes, const ttv_b200_opts* opts)
+{
+  if (bytes == 0) return TTV_B200_OK;
+  if (!dst || !src) return fail(TTV_B200_ERR_A_NULL);
+  Where wd = Where::Host, ws = Where::Host;
+  int dd = -1, ds = -1;
+  if (int rc = classify(dst, &wd, &dd)) return rc;
+  if (int rc = classify(src, &ws, &ds)) return rc;
+  cudaStream_t stream = opts ? static_cast<cudaStream_t>(opts->stream) : nullptr;
+  if (wd == Where::Host && ws == Where::Host) { copy_pool().copy(dst, src, (size_t)bytes); return TTV_B200_OK; }
+  const int device = wd == Where::Device ? dd : ds;
+  DeviceGuard guard;
+  CUDA_TRY(guard.set(device), "cudaSetDevice");
+  if (wd == Where::Device && ws == Where::Device) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, stream), "cudaMemcpyAsync D2D");
+    CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+    return TTV_B200_OK;
+  }
+  DeviceState* st = nullptr;
+  if (int rc = device_state_locked(device, &st)) return rc;
+  std::lock_guard<std::mutex> host_lock(st->host_mutex);        // the bounce buffers are per device
+  return wd == Where::Device ? copy_h2d(st, dst, src, (size_t)bytes, stream) : copy_d2h(st, dst, src, (size_t)bytes, stream);
+}
+
+// ---- resident tensors ---------------------------------------------------------------------------------------------
+int ttv_b200_resident_create(ttv_b200_resident** r, int device)
+{
+  if (!r) return fail(TTV_B200_ERR_OPTS, "ttv_b200_resident_create: r must not be null");
+  *r = nullptr;
+  if (device < 0) CUDA_TRY(cudaGetDevice(&device), "cudaGetDevice (is a CUDA device visible?)");
+  ttv_b200_resident* obj = new (std::nothrow) ttv_b200_resident;
+  if (!obj) return fail(TTV_B200_ERR_CUDA, "out of host memory");
+  obj->device = device;
+  *r = obj;
+  return TTV_B200_OK;
+}
+
+void ttv_b200_resident_destroy(ttv_b200_resident* r)
+{
+  if (!r) return;
+  {
+    std::lock_guard<std::mutex> lock(r->mutex);
+    if (r->dev) {
+      DeviceGuard guard;
+      if (guard.set(r->device) == cudaSuccess) cudaFree(r->dev);      // cudaFree waits for work that still reads the buffer
+      cudaGetLastError();
+      r->dev = nullptr;
+    }
+  }
+  delete r;
+}
+
+void ttv_b200_resident_invalidate(ttv_b200_resident* r)
+{
+  if (!r) return;
+  std::lock_guard<std::mutex> lock(r->mutex);
+  r->valid = false;
+}
+
+int ttv_b200_resident_valid(const ttv_b200_resident* r)
+{
+  if (!r) return 0;
+  std::lock_guard<std::mutex> lock(const_cast<ttv_b200_resident*>(r)->mutex);
+  return r->valid ? 1 : 0;
+}
+
+int ttv_b200_run_resident(ttv_b200_resident* r, int dtype, uint64_t q, uint64_t p,
+                          const void* a, const uint64_t* na, const uint64_t* wa, const uint64_t* pia,
+                          const void* b, const uint64_t* nb,
+                          void* c, const uint64_t* nc, const uint64_t* wc, const uint64_t* pic,
+                          const ttv_b200_opts* opts)
+{
+  if (!r) return fail(TTV_B200_ERR_OPTS, "ttv_b200_run_resident: r must not be null");
+  const size_t s = (size_t)dtype_size(dtype);
+  if (s == 0) return fail(TTV_B200_ERR_DTYPE);
+  View v;
+  if (int rc = validate_and_fold(q, p, a, na, wa, pia, b, nb, c, nc, wc, pic, opts ? opts->flags : 0u, &v)) return fail(rc);
+  Where w = Where::Host; int dx = -1;
+  for (const void* ptr : {a, b, static_cast<const void*>(c)}) {
+    if (int rc = classify(ptr, &w, &dx)) return rc;
+    if (w != Where::Host) return fail(TTV_B200_ERR_MIXED_POINTERS, "ttv_b200_run_resident takes host pointers (device tensors need no twin)");
+  }
+  std::lock_guard<std::mutex> rlock(r->mutex);
+  const int device = r->device;
+  DeviceGuard guard;
+  CUDA_TRY(guard.set(device), "cudaSetDevice");
+  DeviceState* st = nullptr;
+  if (int rc = device_state_locked(device, &st)) return rc;
+  std::lock_guard<std::mutex> host_lock(st->host_mutex);
+
+  const size_t bytes_a = (size_t)(v.strided ? v.span_a : v.outer * v.nq * v.inner) * s;
+  const size_t bytes_b = (size_t)v.nq * s;
+  const size_t bytes_c = (size_t)(v.strided ? v.span_c : v.outer * v.inner) * s;
+  cudaStream_t stream = opts ? static_cast<cudaStream_t>(opts->stream) : nullptr;
+  const bool c_goes_up = (opts && (opts->flags & TTV_B200_FLAG_ACCUMULATE)) || v.strided;
+  ttv_b200_opts local = opts ? *opts : ttv_b200_opts{-1, 0, 0, 0, 0, 0, 0, 0, nullptr};
+  local.device = device;
+  local.flags &= ~(uint32_t)TTV_B200_FLAG_ASYNC;
+
+  if (r->valid && (r->host != a || r->bytes != bytes_a)) r->valid = false;      // another tensor (or another extent of it)
+  if (!r->valid) {
+    if (r->capacity < bytes_a) {
+      if (r->dev) { CUDA_TRY(cudaFree(r->dev), "cudaFree"); r->dev = nullptr; r->capacity = 0; }
+      CUDA_TRY(cudaMalloc(&r->dev, std::max<size_t>(bytes_a, 256)), "cudaMalloc (resident copy of A)");
+      r->capacity = bytes_a;
+    }
+    // first product: A crosses PCIe chunk by chunk under this product's own kernels, into the buffer that stays
+    const void* bs[1] = {b};
+    void* cs[1] = {c};
+    const int rc = run_host_pipelined(dtype, 1, &v, a, bs, cs, &local, device, false, static_cast<char*>(r->dev));
+    if (rc > 0) return rc;
+    if (rc == 0) { r->host = a; r->bytes = bytes_a; r->valid = true; return TTV_B200_OK; }
+    // not eligible for the chunked path (small, strided, one indivisible slab): one copy, then the device path below
+    if (int rc2 = copy_h2d(st, r->dev, a, bytes_a, stream)) return rc2;
+    r->host = a; r->bytes = bytes_a; r->valid = true;
+  }
+  // A is in HBM: only b goes up and C comes back
+  void *db = nullptr, *dc = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (int rc = ensure(st->stage_b, bytes_b)) return rc;
+    if (int rc = ensure(st->stage_c, bytes_c)) return rc;
+    db = st->stage_b.ptr; dc = st->stage_c.ptr;
+  }
+  CUDA_TRY(cudaMemcpyAsync(db, b, bytes_b, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync H2D b");
+  if (c_goes_up) if (int rc = copy_h2d(st, dc, c, bytes_c, stream)) return rc;
+  if (int rc = run_view_device(dtype, v, r->dev, db, dc, &local, device, false)) return rc;
+  return copy_d2h(st, c, dc, bytes_c, stream);
+}
+
+// ---- one host tensor over several GPUs ---------------------------------------------------------------------------------
+int ttv_b200_run_devices(int dtype, uint64_t q, uint64_t p,
+                         const void* a, const uint64_t* na, const uint64_t* wa, const uint64_t* pia,
+                         const void* b, const uint64_t* nb,
+                         void* c, const uint64_t* nc, const uint64_t* wc, const uint64_t* pic,
+                         const ttv_b200_opts* opts, const int32_t* devices, uint32_t n_devices)
+{
+  const size_t s = (size_t)dtype_size(dtype);
+  if (s == 0) return fail(TTV_B200_ERR_DTYPE);
+  if (!devices || n_devices == 0 || n_devices > 64) return fail(TTV_B200_ERR_OPTS, "ttv_b200_run_devices: need 1..64 devices");
+  const int visible = ttv_b200_device_count();
+  for (uint32_t d = 0; d < n_devices; ++d)
+    if (devices[d] < 0 || devices[d] >= visible) return fail(TTV_B200_ERR_OPTS, "ttv_b200_run_devices: device %d is not visible (%d devices)", (int)devices[d], visible);
+  View v;
+  if (int rc = validate_and_fold(q, p, a, na, wa, pia, b, nb, c, nc, wc, pic, opts ? opts->flags : 0u, &v)) return fail(rc);
+  Where w = Where::Host; int dx = -1;
+  for (const void* ptr : {a, b, static_cast<const void*>(c)}) {
+    if (int rc = classify(ptr, &w, &dx)) return rc;
+    if (w != Where::Host) return fail(TTV_B200_ERR_MIXED_POINTERS, "ttv_b200_run_devices takes host pointers");
+  }
+  ttv_b200_opts base = opts ? *opts : ttv_b200_opts{-1, 0, 0, 0, 0, 0, 0, 0, nullptr};
+  base.flags &= ~(uint32_t)TTV_B200_FLAG_ASYNC;
+  base.stream = nullptr;                                          // a stream belongs to one device
+  const bool accumulate = (base.flags & TTV_B200_FLAG_ACCUMULATE) != 0;
+
+  const uint64_t total = v.outer * v.nq * v.inner;
+  const uint64_t slow = v.slow_extent ? v.slow_extent : (v.outer > 1 ? v.outer : v.nq);
+  const bool nq_split = v.outer == 1 || (v.outer % slow) != 0;
+  const bool divisible = !v.strided && slow >= 2 && (!nq_split || (v.outer == 1 && v.nq == slow));
+  const uint64_t min_bytes = (uint64_t)env_mb("TTV_B200_MULTI_MIN_MB", 64) << 20;
+  if (n_devices == 1 || !divisible || total * s < min_bytes) {
+    base.device = devices[0];
+    return run_view_host(dtype, v, a, b, c, &base);
+  }
+  const uint32_t G = (uint32_t)std::min<uint64_t>(n_devices, slow);
+  const uint64_t slab = total / slow;                             // elements of A per index of the slowest mode
+  std::vector<uint64_t> begin(G + 1);
+  for (uint32_t d = 0; d <= G; ++d) begin[d] = slow / G * d + std::min<uint64_t>(d, slow % G);
+
+  std::vector<int> status(G, TTV_B200_OK);
+  std::vector<std::string> message(G);
+  std::vector<void*> partial(G, nullptr);                          // n_q split: device d's partial C, in ITS memory
+  const uint64_t n_out = v.outer * v.inner;
+
+  auto worker = [&](uint32_t d) {
+    ttv_b200_opts o = base;
+    o.device = devices[d];
+    View sub = v;
+    const char* ap = static_cast<const char*>(a) + (size_t)(begin[d] * slab) * s;
+    const uint64_t count = begin[d + 1] - begin[d];
+    int rc = TTV_B200_OK;
+    if (!nq_split) {
+      const uint64_t rows = v.outer / slow;                        // rows of `outer` per index of the slowest mode
+      sub.outer = count * rows;
+      sub.slow_extent = count;
+      char* cp = static_cast<char*>(c) + (size_t)(begin[d] * rows * v.inner) * s;
+      rc = run_view_host(dtype, sub, ap, b, cp, &o);
+    } else {
+      // rows [begin, end) of the contraction with the matching slice of b; the partial stays on the device
+      sub.nq = count;
+      sub.slow_extent = count;
+      o.flags &= ~(uint32_t)TTV_B200_FLAG_ACCUMULATE;
+      DeviceGuard guard;
+      cudaError_t e = guard.set(devices[d]);
+      void *pb = nullptr, *pc = nullptr;
+      if (e == cudaSuccess) e = cudaMalloc(&pb, std::max<size_t>((size_t)count * s, 256));
+      if (e == cudaSuccess) e = cudaMalloc(&pc, std::max<size_t>((size_t)n_out * s, 256));
+      if (e == cudaSuccess) e = cudaMemcpy(pb, static_cast<const char*>(b) + (size_t)begin[d] * s, (size_t)count * s, cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) { rc = fail_cuda(e, "ttv_b200_run_devices: staging of one GPU's share"); if (pc) cudaFree(pc); pc = nullptr; }
+      else rc = run_view_host(dtype, sub, ap, pb, pc, &o, /*bc_dev=*/true);
+      if (pb) cudaFree(pb);
+      if (rc != TTV_B200_OK && pc) { cudaFree(pc); pc = nullptr; }
+      partial[d] = pc;
+    }
+    status[d] = rc;
+    if (rc != TTV_B200_OK) message[d] = g_last_error;              // thread-local: carry it to the caller's thread
+  };
+  {
+    std::vector<std::thread> threads;
+    for (uint32_t d = 1; d < G; ++d) threads.emplace_back(worker, d);
+    worker(0);
+    for (auto& t : threads) t.join();
+  }
+  int rc = TTV_B200_OK;
+  for (uint32_t d = 0; d < G; ++d)
+    if (status[d] != TTV_B200_OK && rc == TTV_B200_OK) { rc = status[d]; g_last_error = message[d]; }
+
+  if (nq_split && rc == TTV_B200_OK) {
+    // the partials meet on devices[0]: slots [G][n_out], summed in device order (deterministic), then C goes back
+    DeviceGuard guard;
+    cudaError_t e = guard.set(devices[0]);
+    void *slots = nullptr, *dc = nullptr;
+    if (e == cudaSuccess) e = cudaMalloc(&slots, std::max<size_t>((size_t)G * n_out * s, 256));
+    if (e == cudaSuccess) e = cudaMalloc(&dc, std::max<size_t>((size_t)n_out * s, 256));
+    for (uint32_t d = 0; d < G && e == cudaSuccess; ++d)
+      e = cudaMemcpyPeer(static_cast<char*>(slots) + (size_t)d * n_out * s, devices[0], partial[d], devices[d], (size_t)n_out * s);
+    if (e == cudaSuccess && accumulate) e = cudaMemcpy(dc, c, (size_t)n_out * s, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+      DeviceState* st = nullptr;
+      rc = device_state_locked(devices[0], &st);
+      if (rc == TTV_B200_OK) {
+        e = launch_reduce_slots(dtype, slots, dc, n_out, n_out, G, accumulate, st->sm_count, nullptr);
+        if (e == cudaSuccess) {
+          std::lock_guard<std::mutex> host_lock(st->host_mutex);
+          rc = copy_d2h(st, c, dc, (size_t)n_out * s, nullptr);
+        }
+      }
+    }
+    if (e != cudaSuccess) rc = fail_cuda(e, "ttv_b200_run_devices: gathering the partial sums");
+    if (slots) cudaFree(slots);
+    if (dc) cudaFree(dc);
+  }
+  for (uint32_t d = 0; d < G; ++d)
+    if (partial[d]) { DeviceGuard guard; if (guard.set(devices[d]) == cudaSuccess) cudaFree(partial[d]); cudaGetLastError(); }
+  return rc;
 }
 
 // ---- L0 helpers ------------------------------------------------------------------------------------------------

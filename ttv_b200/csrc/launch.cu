@@ -11,6 +11,7 @@
 #include "dotf_kernel.cuh"
 #include "strided_kernel.cuh"
 #include "scatter_kernel.cuh"
+#include "colt_kernel.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -26,6 +27,7 @@ using fill_fn_t   = cudaError_t (*)(void*, uint64_t, uint64_t, uint64_t, int, cu
 using stream_fn_t = cudaError_t (*)(const StreamParams&, const Launch&, cudaStream_t);
 using dotf_fn_t   = cudaError_t (*)(const DotfParams&, const Launch&, cudaStream_t);
 using strided_fn_t = cudaError_t (*)(const StridedParams&, int, cudaStream_t);
+using colt_fn_t   = cudaError_t (*)(const CUtensorMap&, const ColtParams&, const Launch&, cudaStream_t);
 
 #define TTVB_DECLARE(k)                                                                                          \
   cudaError_t tile_dtype_##k(const TileParams&, const Launch&, cudaStream_t);                                    \
@@ -34,7 +36,8 @@ using strided_fn_t = cudaError_t (*)(const StridedParams&, int, cudaStream_t);
   cudaError_t fill_dtype_##k(void*, uint64_t, uint64_t, uint64_t, int, cudaStream_t);                            \
   cudaError_t stream_dtype_##k(const StreamParams&, const Launch&, cudaStream_t);                               \
   cudaError_t dotf_dtype_##k(const DotfParams&, const Launch&, cudaStream_t);                                   \
-  cudaError_t strided_dtype_##k(const StridedParams&, int, cudaStream_t);
+  cudaError_t strided_dtype_##k(const StridedParams&, int, cudaStream_t);                                         \
+  cudaError_t colt_dtype_##k(const CUtensorMap&, const ColtParams&, const Launch&, cudaStream_t);
 TTVB_DECLARE(0) TTVB_DECLARE(1) TTVB_DECLARE(2) TTVB_DECLARE(3) TTVB_DECLARE(4) TTVB_DECLARE(5)
 #undef TTVB_DECLARE
 
@@ -53,6 +56,50 @@ static const stream_fn_t k_stream[] = {stream_dtype_0, stream_dtype_1, stream_dt
 static const dotf_fn_t   k_dotf[]   = {dotf_dtype_0, dotf_dtype_1, dotf_dtype_2, dotf_dtype_3, dotf_dtype_4, dotf_dtype_5};
 static const scatter_fn_t k_scatter[] = {scatter_dtype_0, scatter_dtype_1, scatter_dtype_2, scatter_dtype_3, scatter_dtype_4, scatter_dtype_5};
 static const strided_fn_t k_strided[] = {strided_dtype_0, strided_dtype_1, strided_dtype_2, strided_dtype_3, strided_dtype_4, strided_dtype_5};
+static const colt_fn_t   k_colt[]   = {colt_dtype_0, colt_dtype_1, colt_dtype_2, colt_dtype_3, colt_dtype_4, colt_dtype_5};
+
+// cuTensorMapEncodeTiled lives in the driver library; the runtime hands out its address, so nothing links against libcuda
+using encode_fn_t = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_fn_t tensor_map_encoder()
+{
+  static encode_fn_t fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+    }
+    return reinterpret_cast<encode_fn_t>(p);
+  }();
+  return fn;
+}
+
+// COLT: A as a 3-D tensor of 32-bit words (inner*s/4, n_q, outer), boxes of wt words x kt rows of one slab
+static cudaError_t launch_colt(int dtype, const View& v, const Launch& l, const void* a, const void* b, void* c, void* workspace,
+                               bool accumulate, cudaStream_t stream)
+{
+  encode_fn_t encode = tensor_map_encoder();
+  if (!encode) return cudaErrorNotSupported;
+  const uint64_t s = (uint64_t)dtype_size(dtype);
+  CUtensorMap map;
+  const cuuint64_t gdim[3] = {v.inner * s / 4, v.nq, v.outer};
+  const cuuint64_t gstride[2] = {v.inner * s, v.nq * v.inner * s};                 // bytes between rows / between slabs
+  const cuuint32_t box[3] = {l.wt, l.kt, 1};
+  const cuuint32_t estride[3] = {1, 1, 1};
+  if (encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(a), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return cudaErrorInvalidValue;
+  ColtParams P;
+  P.b = b; P.c = l.ksplit > 1 ? workspace : c;
+  P.outer = v.outer; P.nq = v.nq; P.inner = v.inner;
+  P.itiles = l.itiles; P.items = l.tiles;
+  P.wt = l.wt; P.kt = l.kt; P.kboxes = l.kboxes;
+  P.tx = l.tx; P.ty = l.ty; P.stages = l.stages; P.ksplit = l.ksplit;
+  P.accumulate = (accumulate && l.ksplit == 1) ? 1u : 0u;
+  return k_colt[dtype](map, P, l, stream);
+}
 
 cudaError_t launch_strided(int dtype, const View& v, const void* a, const void* b, void* c, bool accumulate, int sm_count,
                            cudaStream_t stream)
@@ -84,6 +131,11 @@ cudaError_t launch_view(int dtype, const View& v, const Launch& l, const void* a
     S.stage_bytes = l.stage_bytes;
     S.accumulate = accumulate ? 1u : 0u;
     return k_stream[dtype](S, l, stream);
+  }
+  if (l.kernel == TTV_B200_KERNEL_COLT) {
+    cudaError_t e = launch_colt(dtype, v, l, a, b, c, workspace, accumulate, stream);
+    if (e != cudaSuccess || l.ksplit <= 1) return e;
+    return k_reduce[dtype](workspace, c, v.outer * v.inner, l.ksplit, accumulate, v.outer * v.inner, sm_count, stream);
   }
   if (l.kernel == TTV_B200_KERNEL_DOTF) {
     DotfParams D;
@@ -430,6 +482,17 @@ cudaError_t TTVB_CAT(strided_dtype_, TTVB_DTYPE)(const StridedParams& S, int sm_
   }
   const uint64_t blocks = std::max<uint64_t>(1, std::min<uint64_t>((S.total + 255) / 256, (uint64_t)sm_count * 32));
   ttv_strided_kernel<elem_t><<<(unsigned)blocks, 256, 0, stream>>>(S);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t TTVB_CAT(colt_dtype_, TTVB_DTYPE)(const CUtensorMap& map, const ColtParams& P, const Launch& l, cudaStream_t stream)
+{
+  constexpr int V = 16 / (int)sizeof(elem_t);
+  auto kern = ttv_colt_kernel<elem_t, V>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes);
+  if (e != cudaSuccess) return e;
+  kern<<<(unsigned)l.ctas, kColtThreads, l.smem_bytes, stream>>>(map, P);
   count_launch();
   return cudaGetLastError();
 }

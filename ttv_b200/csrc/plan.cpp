@@ -414,8 +414,56 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
   const EnvScope env_scope;                       // one scan of the environment for all the switches below
   const uint32_t flags = opts ? opts->flags : 0u;
   int forced = opts ? opts->kernel : 0;
-  if (forced < 0 || forced >= TTV_B200_KERNEL_COUNT) return TTV_B200_ERR_OPTS;
+  if (forced < 0 || forced >= TTV_B200_KERNEL_COUNT || forced == TTV_B200_KERNEL_STRIDED) return TTV_B200_ERR_OPTS;
   Launch l;
+  // COLT: A through shared memory by TMA tensor tiles (colt_kernel.cuh).  Needs rows that are whole 16-byte vectors (the
+  // tensor map's strides), a 16-byte aligned A and C, b resident in shared memory, and tensor-map extents below 2^32.
+  // Only taken when forced (opts.kernel / TTV_B200_USE_COLT=1): measured against COL it does not win.
+  {
+    const uint64_t row_words = v.inner * s / 4;
+    const bool eligible = v.inner > 1 && (v.inner * s) % 16 == 0 && (align_a % 16) == 0 && (align_c % 16) == 0 && row_words >= 16 &&
+                          row_words < (1ull << 32) && v.nq < (1ull << 32) && v.outer < (1ull << 32) && v.nq * s <= 64 * 1024 &&
+                          v.nq * v.inner * s < (1ull << 40) && !(flags & TTV_B200_FLAG_NO_VEC);
+    if (forced == TTV_B200_KERNEL_COLT && !eligible) return TTV_B200_ERR_OPTS;
+    const bool pick = forced == TTV_B200_KERNEL_COLT || (forced == 0 && eligible && env_int("TTV_B200_USE_COLT", 0) == 1);
+    if (pick) {
+      l.kernel = TTV_B200_KERNEL_COLT;
+      l.threads = 288;                                              // 256 consumers + the producer warp
+      l.vec = (int)(16 / s); l.nu = 1; l.stream = 1; l.udir = 0;
+      uint64_t wt = std::min<uint64_t>(256, pow2_ceil(row_words));   // words of a row per box (power of two: tx divides 256)
+      wt = std::max<uint64_t>(4, std::min<uint64_t>(wt, (uint64_t)env_int("TTV_B200_COLT_WT", 256)));
+      l.wt = (uint32_t)wt;
+      l.tx = (uint32_t)(wt / 4); l.ty = 256 / l.tx; l.to = 1;
+      const uint64_t stage_target = (uint64_t)env_int("TTV_B200_COLT_STAGE_KB", 32) * 1024;
+      uint64_t kt = std::max<uint64_t>(l.ty, std::min<uint64_t>(256, stage_target / (wt * 4)) / l.ty * l.ty);
+      kt = std::min<uint64_t>(kt, ceil_div(v.nq, l.ty) * l.ty);      // never taller than the contraction
+      l.kt = (uint32_t)kt;
+      l.ku = (int)(kt / l.ty);
+      int want = opts ? opts->ksplit : 0;
+      if (want == 0) want = env_int("TTV_B200_KSPLIT", 0);
+      const uint64_t boxes_all = ceil_div(v.nq, kt);
+      uint64_t ksplit = want > 0 ? (uint64_t)want : 1;
+      ksplit = std::max<uint64_t>(1, std::min(ksplit, boxes_all));
+      const uint64_t boxes_per = ceil_div(boxes_all, ksplit);
+      ksplit = ceil_div(boxes_all, boxes_per);
+      l.ksplit = (uint32_t)ksplit;
+      l.kchunk = boxes_per * kt;
+      l.kboxes = (uint32_t)boxes_per;
+      l.itiles = ceil_div(row_words, wt);
+      l.otiles = v.outer;
+      l.tiles = l.itiles * l.otiles * ksplit;
+      l.stages = (uint32_t)std::max(2, std::min(8, env_int("TTV_B200_COLT_STAGES", 4)));
+      const uint64_t b_bytes = (boxes_per * ksplit * kt * s + 15) / 16 * 16;  // all of b, zero-padded to whole boxes
+      l.kb = (uint32_t)(boxes_per * ksplit * kt);
+      l.smem_bytes = (uint64_t)l.stages * wt * kt * 4 + b_bytes + 256 * 16 + 2 * (uint64_t)l.stages * 8 + 128;
+      if (l.smem_bytes > 227 * 1024) return TTV_B200_ERR_OPTS;
+      const uint64_t per_sm = std::max<uint64_t>(1, std::min<uint64_t>((227 * 1024) / (l.smem_bytes + 1024), (uint64_t)env_int("TTV_B200_COLT_CTAS", 2)));
+      l.ctas = std::min<uint64_t>(l.tiles, sms * per_sm);
+      l.workspace_bytes = ksplit > 1 ? ksplit * v.outer * v.inner * s : 0;
+      *out = l;
+      return TTV_B200_OK;
+    }
+  }
   // STREAM: small slabs staged through shared memory by TMA bulk copies (stream_kernel.cuh).  Eligible when a slab and
   // b are small, A is 16-byte aligned and n_q is not split.
   {

@@ -65,6 +65,8 @@ struct Launch {
   uint64_t wcols = 0;
   uint32_t bdirect = 0;     // b read straight from global memory / L2 (lanes along n_q, b too long to stay resident)
   uint32_t warp = 0;        // COLX: warp-autonomous form (ttv_colw_kernel)
+  // COLT kernel only: box of the TMA tensor tile (wt 32-bit words of a row x kt rows), boxes per column tile
+  uint32_t wt = 0, kt = 0, kboxes = 0;
 };
 
 int dtype_size(int dtype);          // bytes, 0 if unknown
