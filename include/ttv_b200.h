@@ -236,6 +236,22 @@ int ttv_b200_view_scatter(int dtype, uint64_t outer, uint64_t nq, uint64_t inner
                           void* const* peer_ws, uint32_t world, uint32_t rank, uint64_t blk, const ttv_b200_opts* opts);
 int ttv_b200_reduce_slots(int dtype, const void* ws, void* c, uint64_t n, uint64_t blk, uint32_t slots,
                           const ttv_b200_opts* opts);
+/* The same exchange in ONE kernel launch per GPU: product + scatter as above, then -- inside the kernel -- a barrier across the
+ * GPUs (the last CTA of a GPU to finish writes `token` into flag[rank] of every GPU's flag array over NVLink; every CTA waits
+ * with ld.acquire.sys until all `world` flags of its own array show the token) and the sum of the `world` slots of this GPU's
+ * workspace, in rank order, into c_block (n_block <= blk elements: this GPU's block of the flat C).  No library barrier, no
+ * second and third launch.
+ *   peer_flags[j]  GPU j's flag array (>= 16 x uint32, zero before the first round), mapped like peer_ws
+ *   token          round number of the group: 1, 2, 3, ... (every GPU passes the same value; flags only grow)
+ *   scratch        16 bytes of LOCAL device memory, zeroed once: arrival counter (8) + error flag (4)
+ *   max_ctas       cap of the persistent grid; 0 = every CTA the device can hold at once (all CTAs must be resident:
+ *                  they spin on the flags).  Peer workspaces must alternate between two halves from round to round.
+ * Asynchronous with TTV_B200_FLAG_ASYNC; a wait longer than 10 s (TTV_B200_EXCHANGE_TIMEOUT_MS) sets the error flag, which
+ * synchronous calls report as TTV_B200_ERR_CUDA. */
+int ttv_b200_view_exchange(int dtype, uint64_t outer, uint64_t nq, uint64_t inner, const void* a, const void* b,
+                           void* const* peer_ws, void* const* peer_flags, uint32_t world, uint32_t rank, uint64_t blk,
+                           void* c_block, uint64_t n_block, uint32_t token, void* scratch, uint32_t max_ctas,
+                           const ttv_b200_opts* opts);
 
 /* x[i] = synth(seed, first + i), i < count, written on the device by a kernel (x is a DEVICE pointer).  The generator
  * is the counter-based splitmix64 one of SURVEY 8(d); oracle/ttv_oracle.c carries the identical host version, so

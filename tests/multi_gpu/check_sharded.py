@@ -1,7 +1,8 @@
 """Multi-GPU parity of ttv_b200.sharded, one process per GPU (NCCL):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/multi_gpu/check_sharded.py
 Every rank builds the same global integer-valued tensor, owns its slab, and the three exchange forms -- free split (none),
-n_q split + NCCL reduce / all-reduce, n_q split fused with the exchange over peer memory (PeerExchange) -- are compared
+n_q split + NCCL reduce / all-reduce, n_q split fused with the exchange over peer memory (PeerExchange, as one kernel per
+GPU with an in-kernel barrier and as scatter kernel + library barrier + reduce kernel) -- are compared
 bit for bit with the oracle on the global problem.  Prints "multi-gpu parity ok" on rank 0."""
 import os
 import sys
@@ -28,7 +29,8 @@ def main():
     checked = 0
     for dtype in (np.float32, np.float64, np.int32, np.complex64):
         tdt = torch.from_numpy(np.zeros(1, dtype)).dtype
-        ex = PeerExchange(40000, tdt, dev)
+        ex = PeerExchange(40000, tdt, dev)                          # ONE kernel per GPU: scatter + in-kernel barrier + sum
+        ex3 = PeerExchange(40000, tdt, dev, single_kernel=False)   # scatter kernel + symmetric-memory barrier + reduce kernel
         rng = np.random.default_rng(99)                     # the same data on every rank
         for na, pia in CASES:
             n = int(np.prod(na))
@@ -47,11 +49,13 @@ def main():
                 else:
                     assert np.array_equal(got, want), (na, pia, q, "nccl", rank)
                     # fused exchange over peer memory: this rank's block of C
-                    for _ in range(3):                      # several rounds: both halves of the workspace and their reuse
-                        c2, s3 = ttv_sharded(q, a_loc, na, pia, tb, rank=rank, world=world, exchange=ex)
+                    for rnd in range(4):                    # several rounds: both halves of the workspace and their reuse
+                        form = ex if rnd != 2 else ex3
+                        c2, s3 = ttv_sharded(q, a_loc, na, pia, tb, rank=rank, world=world, exchange=form)
                         if na[s3.mode - 1] >= world:
                             assert s3.kind == "nq-scattered"
-                            assert np.array_equal(c2.cpu().numpy(), want[s3.c_offset: s3.c_offset + s3.c_count]), (na, pia, q, "fused", rank)
+                            assert np.array_equal(c2.cpu().numpy(), want[s3.c_offset: s3.c_offset + s3.c_count]), (na, pia, q, "fused", rank, rnd)
+                    assert not ex.timed_out(), (na, pia, q, "a single-kernel exchange timed out", rank)
                 checked += 1
     t = torch.tensor([checked], device=dev)
     dist.all_reduce(t)

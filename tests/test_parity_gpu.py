@@ -897,3 +897,52 @@ def test_colt_kernel_tma_tensor_tiles(dtype, oracle, monkeypatch):
             assert np.array_equal(run_lowlevel(q, a, na, pia, b, c0=c0, kernel="colt", flags=1), want + 3)
     with pytest.raises(ttv_b200.TTVError):                          # rows that are not whole 16-byte vectors
         ttv_b200.plan(2, (64 * vec + 1, 9), (1, 2), dtype=name, kernel="colt") if vec > 1 else ttv_b200.plan(1, (9, 64), (1, 2), dtype=name, kernel="colt")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.complex64, np.complex128])
+def test_single_kernel_exchange_emulated_on_one_gpu(dtype, oracle, monkeypatch):
+    """ttv_b200_view_exchange: product + scatter + in-kernel flag barrier + sum of the slots in ONE kernel per rank.  The
+    `world` ranks are `world` kernels on separate streams of one device, each capped at a few CTAs so that all of them are
+    resident together (every CTA spins until all ranks have delivered).  Several rounds: tokens grow, the two workspace
+    halves alternate, the arrival counter resets itself.  The timeout is short so that a protocol bug fails instead of
+    hanging the device."""
+    import torch
+    from ttv_b200.sharded import PeerExchange, split_range
+    monkeypatch.setenv("TTV_B200_EXCHANGE_TIMEOUT_MS", "3000")
+    rng = np.random.default_rng(62)
+    token = 0
+    for (outer, nq, inner), world in [((1, 37, 5000), 3), ((1, 64, 1031), 4), ((5, 29, 700), 2), ((1, 8, 77), 8), ((3, 40, 256), 5), ((1, 200, 40000), 2)]:
+        na, pia = (inner, nq, outer), (1, 2, 3)
+        n = outer * inner
+        blk = PeerExchange.block(n, world)
+        tdt = torch.from_numpy(np.zeros(1, dtype)).dtype
+        ws = [torch.full((2 * world * blk,), 99, dtype=tdt, device="cuda") for _ in range(world)]        # two halves per rank
+        flags = [torch.zeros(16, dtype=torch.int32, device="cuda") for _ in range(world)]
+        scratch = [torch.zeros(4, dtype=torch.int32, device="cuda") for _ in range(world)]
+        streams = [torch.cuda.Stream() for _ in range(world)]
+        torch.cuda.synchronize()
+        for rnd in range(3):
+            a = rng.integers(-8, 9, outer * nq * inner).astype(dtype)
+            b = rng.integers(-8, 9, nq).astype(dtype)
+            want = oracle.ttv(2, a, na, pia, b)
+            a3 = torch.from_numpy(a).cuda().view(outer, nq, inner)
+            tb = torch.from_numpy(b).cuda()
+            parts = []
+            for r in range(world):
+                k0, kc = split_range(nq, world, r)
+                parts.append((a3[:, k0:k0 + kc, :].contiguous(), tb[k0:k0 + kc].contiguous()))
+            got = torch.full((n,), 55, dtype=tdt, device="cuda")
+            token += 1
+            half = (token % 2) * world * blk
+            itemsize = np.dtype(dtype).itemsize
+            torch.cuda.synchronize()
+            for r in range(world):
+                first = min(n, r * blk); cnt = max(0, min(blk, n - first))
+                with torch.cuda.stream(streams[r]):
+                    ttv_b200.ttv_view_exchange(outer, parts[r][0].shape[1], inner, parts[r][0], parts[r][1],
+                                               [w.data_ptr() + half * itemsize for w in ws], [f.data_ptr() for f in flags], r, blk,
+                                               got[first:first + cnt] if cnt else None, token, scratch[r], max_ctas=max(1, 96 // world),
+                                               stream=streams[r].cuda_stream)
+            torch.cuda.synchronize()
+            assert all(int(s[2].item()) == 0 for s in scratch), "an emulated rank timed out waiting for the others"
+            assert np.array_equal(got.cpu().numpy(), want), ((outer, nq, inner), world, dtype, rnd)

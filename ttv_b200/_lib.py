@@ -56,6 +56,9 @@ SYMBOLS = {
     "ttv_b200_plan_view": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(Opts), C.POINTER(Plan)]),
     "ttv_b200_view_scatter": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
                                         C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(Opts)]),
+    "ttv_b200_view_exchange": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
+                                         C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32,
+                                         C.c_void_p, C.c_uint32, C.POINTER(Opts)]),
     "ttv_b200_reduce_slots": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(Opts)]),
     "ttv_b200_fill": (C.c_int, [C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(Opts)]),
     "ttv_b200_device_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64, C.c_int, C.c_int]),

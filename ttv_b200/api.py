@@ -454,6 +454,23 @@ def ttv_view_scatter(outer: int, nq: int, inner: int, a, b, peer_ptrs, rank: int
     _check(lib.ttv_b200_view_scatter(dtype_code(a), outer, nq, inner, _ptr(a), _ptr(b), arr, world, rank, blk, C.byref(opts)))
 
 
+def ttv_view_exchange(outer: int, nq: int, inner: int, a, b, peer_ptrs, flag_ptrs, rank: int, blk: int, c_block, token: int, scratch,
+                      max_ctas: int = 0, **opt_kwargs) -> None:
+    """The whole n_q-split exchange in ONE kernel per GPU (ttv_b200_view_exchange): product + scatter into the peers' slots,
+    in-kernel flag barrier across the GPUs, sum of the received slots into c_block.  Asynchronous on the current torch stream."""
+    lib = _lib.load()
+    if "stream" not in opt_kwargs and _is_torch(a):
+        opt_kwargs["stream"] = _current_torch_stream(a)
+    opt_kwargs["flags"] = int(opt_kwargs.get("flags", 0)) | 2
+    opts = make_opts(**opt_kwargs)
+    world = len(peer_ptrs)
+    ws = (C.c_void_p * world)(*[int(p) for p in peer_ptrs])
+    fl = (C.c_void_p * world)(*[int(p) for p in flag_ptrs])
+    n_block = int(c_block.numel()) if c_block is not None else 0
+    _check(lib.ttv_b200_view_exchange(dtype_code(a), outer, nq, inner, _ptr(a), _ptr(b), ws, fl, world, rank, blk, _ptr(c_block), n_block,
+                                      int(token), _ptr(scratch), int(max_ctas), C.byref(opts)))
+
+
 def reduce_slots(ws, c, n: int, blk: int, slots: int, **opt_kwargs) -> None:
     """c[j] = sum over the `slots` rows of ws [slots][blk], j < n, in row order (ttv_b200_reduce_slots); asynchronous on the
     current torch stream."""

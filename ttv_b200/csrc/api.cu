@@ -975,6 +975,49 @@ int ttv_b200_view_scatter(int dtype, uint64_t outer, uint64_t nq, uint64_t inner
   return TTV_B200_OK;
 }
 
+int ttv_b200_view_exchange(int dtype, uint64_t outer, uint64_t nq, uint64_t inner, const void* a, const void* b,
+                           void* const* peer_ws, void* const* peer_flags, uint32_t world, uint32_t rank, uint64_t blk,
+                           void* c_block, uint64_t n_block, uint32_t token, void* scratch, uint32_t max_ctas,
+                           const ttv_b200_opts* opts)
+{
+  const uint64_t s = (uint64_t)dtype_size(dtype);
+  if (s == 0) return fail(TTV_B200_ERR_DTYPE);
+  if (outer == 0 || nq == 0 || inner == 0) return fail(TTV_B200_ERR_SHAPE_A);
+  if (!a) return fail(TTV_B200_ERR_A_NULL);
+  if (!b) return fail(TTV_B200_ERR_B_NULL);
+  if (!peer_ws || !peer_flags || !scratch || (!c_block && n_block)) return fail(TTV_B200_ERR_C_NULL);
+  if (world == 0 || world > 16 || rank >= world || blk == 0 || blk * world < outer * inner || n_block > blk || token == 0)
+    return fail(TTV_B200_ERR_OPTS, "ttv_b200_view_exchange: need 1 <= world <= 16, rank < world, world*blk >= outer*inner, n_block <= blk, token > 0");
+  for (uint32_t j = 0; j < world; ++j) if (!peer_ws[j] || !peer_flags[j]) return fail(TTV_B200_ERR_C_NULL);
+  Where w; int dev = -1;
+  if (int rc = classify(a, &w, &dev)) return rc;
+  if (w != Where::Device) return fail(TTV_B200_ERR_MIXED_POINTERS, "ttv_b200_view_exchange needs device pointers");
+  uint64_t align = std::min(alignment_of(a), (uint64_t)256);
+  for (uint32_t j = 0; j < world; ++j) align = std::min(align, alignment_of(peer_ws[j]));
+  if (c_block) align = std::min(align, alignment_of(c_block));
+  uint64_t vec = s >= 16 ? 1 : 16 / s;
+  while (vec > 1 && !((inner % vec) == 0 && (blk % vec) == 0 && (align % (vec * s)) == 0)) vec /= 2;
+  DeviceGuard guard;
+  CUDA_TRY(guard.set(dev), "cudaSetDevice");
+  cudaStream_t stream = opts ? static_cast<cudaStream_t>(opts->stream) : nullptr;
+  const bool accumulate = opts && (opts->flags & TTV_B200_FLAG_ACCUMULATE);
+  DeviceState* st = nullptr;
+  if (int rc = device_state_locked(dev, &st)) return rc;
+  View v;
+  v.outer = outer; v.nq = nq; v.inner = inner;
+  const uint64_t timeout_ns = (uint64_t)std::max(1, env_mb("TTV_B200_EXCHANGE_TIMEOUT_MS", 10000)) * 1000000ull;
+  char* sc = static_cast<char*>(scratch);
+  CUDA_TRY(launch_exchange(dtype, v, a, b, peer_ws, peer_flags, world, rank, blk, (int)vec, c_block, n_block, token, sc, sc + 8,
+                           accumulate, timeout_ns, max_ctas, st->sm_count, stream), "exchange launch");
+  if (!(opts && (opts->flags & TTV_B200_FLAG_ASYNC))) {
+    CUDA_TRY(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+    uint32_t err = 0;
+    CUDA_TRY(cudaMemcpy(&err, sc + 8, sizeof err, cudaMemcpyDeviceToHost), "cudaMemcpy");
+    if (err) return fail(TTV_B200_ERR_CUDA, "ttv_b200_view_exchange: timed out waiting for the other GPUs (did every rank launch round %u?)", token);
+  }
+  return TTV_B200_OK;
+}
+
 int ttv_b200_reduce_slots(int dtype, const void* ws, void* c, uint64_t n, uint64_t blk, uint32_t slots, const ttv_b200_opts* opts)
 {
   if (dtype_size(dtype) == 0) return fail(TTV_B200_ERR_DTYPE);

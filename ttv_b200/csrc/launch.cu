@@ -23,6 +23,7 @@ namespace ttvb {
 using tile_fn_t   = cudaError_t (*)(const TileParams&, const Launch&, cudaStream_t);
 using reduce_fn_t = cudaError_t (*)(const void*, void*, uint64_t, uint32_t, bool, uint64_t, int, cudaStream_t);
 using scatter_fn_t = cudaError_t (*)(const ScatterParams&, int, uint64_t, uint64_t, cudaStream_t);
+using exchange_fn_t = cudaError_t (*)(const ExchangeParams&, int, uint32_t, int, uint64_t, cudaStream_t);
 using fill_fn_t   = cudaError_t (*)(void*, uint64_t, uint64_t, uint64_t, int, cudaStream_t);
 using stream_fn_t = cudaError_t (*)(const StreamParams&, const Launch&, cudaStream_t);
 using dotf_fn_t   = cudaError_t (*)(const DotfParams&, const Launch&, cudaStream_t);
@@ -33,6 +34,7 @@ using colt_fn_t   = cudaError_t (*)(const CUtensorMap&, const ColtParams&, const
   cudaError_t tile_dtype_##k(const TileParams&, const Launch&, cudaStream_t);                                    \
   cudaError_t reduce_dtype_##k(const void*, void*, uint64_t, uint32_t, bool, uint64_t, int, cudaStream_t);       \
   cudaError_t scatter_dtype_##k(const ScatterParams&, int, uint64_t, uint64_t, cudaStream_t);                    \
+  cudaError_t exchange_dtype_##k(const ExchangeParams&, int, uint32_t, int, uint64_t, cudaStream_t);             \
   cudaError_t fill_dtype_##k(void*, uint64_t, uint64_t, uint64_t, int, cudaStream_t);                            \
   cudaError_t stream_dtype_##k(const StreamParams&, const Launch&, cudaStream_t);                               \
   cudaError_t dotf_dtype_##k(const DotfParams&, const Launch&, cudaStream_t);                                   \
@@ -55,6 +57,7 @@ static const fill_fn_t   k_fill[]   = {fill_dtype_0, fill_dtype_1, fill_dtype_2,
 static const stream_fn_t k_stream[] = {stream_dtype_0, stream_dtype_1, stream_dtype_2, stream_dtype_3, stream_dtype_4, stream_dtype_5};
 static const dotf_fn_t   k_dotf[]   = {dotf_dtype_0, dotf_dtype_1, dotf_dtype_2, dotf_dtype_3, dotf_dtype_4, dotf_dtype_5};
 static const scatter_fn_t k_scatter[] = {scatter_dtype_0, scatter_dtype_1, scatter_dtype_2, scatter_dtype_3, scatter_dtype_4, scatter_dtype_5};
+static const exchange_fn_t k_exchange[] = {exchange_dtype_0, exchange_dtype_1, exchange_dtype_2, exchange_dtype_3, exchange_dtype_4, exchange_dtype_5};
 static const strided_fn_t k_strided[] = {strided_dtype_0, strided_dtype_1, strided_dtype_2, strided_dtype_3, strided_dtype_4, strided_dtype_5};
 static const colt_fn_t   k_colt[]   = {colt_dtype_0, colt_dtype_1, colt_dtype_2, colt_dtype_3, colt_dtype_4, colt_dtype_5};
 
@@ -184,6 +187,36 @@ cudaError_t launch_scatter(int dtype, const View& v, const void* a, const void* 
   S.stream = s >= 16 ? 1u : 0u;
   const uint64_t ctas = std::max<uint64_t>(1, std::min<uint64_t>(S.tiles, (uint64_t)sm_count * 64));
   return k_scatter[dtype](S, vec, ctas, (uint64_t)S.kb * s, stream);
+}
+
+cudaError_t launch_exchange(int dtype, const View& v, const void* a, const void* b, void* const* peers, void* const* flags,
+                            uint32_t world, uint32_t rank, uint64_t blk, int vec, void* c_block, uint64_t n_block, uint32_t token,
+                            void* counter, void* error, bool accumulate, uint64_t timeout_ns, uint32_t max_ctas, int sm_count,
+                            cudaStream_t stream)
+{
+  if (dtype < 0 || dtype >= TTV_B200_DTYPE_COUNT || world == 0 || world > (uint32_t)kMaxPeers || rank >= world) return cudaErrorInvalidValue;
+  ExchangeParams E;
+  ScatterParams& S = E.S;
+  S.a = a; S.b = b;
+  for (uint32_t j = 0; j < (uint32_t)kMaxPeers; ++j) {
+    S.peer[j] = j < world ? peers[j] : nullptr;
+    E.flags_peer[j] = j < world ? static_cast<uint32_t*>(flags[j]) : nullptr;
+  }
+  S.outer = v.outer; S.nq = v.nq; S.inner = v.inner;
+  S.blk = blk;
+  S.itiles = (v.inner / (uint64_t)vec + 255) / 256;
+  S.tiles = S.itiles * v.outer;
+  S.world = world; S.rank = rank;
+  const uint64_t s = (uint64_t)dtype_size(dtype);
+  S.kb = (uint32_t)std::min<uint64_t>(v.nq, 16384 / s);
+  S.stream = s >= 16 ? 1u : 0u;
+  E.c = c_block; E.n_block = n_block;
+  E.counter = static_cast<unsigned long long*>(counter);
+  E.error = static_cast<uint32_t*>(error);
+  E.timeout_ns = timeout_ns;
+  E.token = token;
+  E.accumulate = accumulate ? 1u : 0u;
+  return k_exchange[dtype](E, vec, max_ctas, sm_count, (uint64_t)S.kb * s, stream);
 }
 
 cudaError_t launch_reduce_slots(int dtype, const void* ws, void* c, uint64_t n, uint64_t stride, uint32_t slots, bool accumulate,
@@ -412,6 +445,34 @@ cudaError_t TTVB_CAT(scatter_dtype_, TTVB_DTYPE)(const ScatterParams& S, int vec
   if (vec == 4) return launch_scatter_vec<4>(S, ctas, smem, stream);
   if (vec == 2) return launch_scatter_vec<2>(S, ctas, smem, stream);
   if (vec == 1) return launch_scatter_vec<1>(S, ctas, smem, stream);
+  return cudaErrorInvalidValue;
+}
+
+template<int V>
+static cudaError_t launch_exchange_vec(const ExchangeParams& E, uint32_t max_ctas, int sm_count, uint64_t smem, cudaStream_t stream)
+{
+  if constexpr (V <= kVmax) {
+    auto kern = ttv_col_exchange_kernel<elem_t, V>;
+    // every CTA spins on the other GPUs' flags, so the whole grid has to be resident at once
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, (size_t)smem);
+    if (e != cudaSuccess) return e;
+    uint64_t ctas = (uint64_t)std::max(1, per_sm) * (uint64_t)sm_count;
+    if (max_ctas) ctas = std::min<uint64_t>(ctas, max_ctas);
+    ctas = std::max<uint64_t>(1, std::min<uint64_t>(ctas, std::max<uint64_t>(E.S.tiles, 1)));
+    kern<<<(unsigned)ctas, 256, smem, stream>>>(E);
+    count_launch();
+    return cudaGetLastError();
+  } else {
+    return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t TTVB_CAT(exchange_dtype_, TTVB_DTYPE)(const ExchangeParams& E, int vec, uint32_t max_ctas, int sm_count, uint64_t smem, cudaStream_t stream)
+{
+  if (vec == 4) return launch_exchange_vec<4>(E, max_ctas, sm_count, smem, stream);
+  if (vec == 2) return launch_exchange_vec<2>(E, max_ctas, sm_count, smem, stream);
+  if (vec == 1) return launch_exchange_vec<1>(E, max_ctas, sm_count, smem, stream);
   return cudaErrorInvalidValue;
 }
 

@@ -31,14 +31,11 @@ struct ScatterParams {
   uint32_t stream;
 };
 
+// the product + scatter part shared by both kernels below: every tile's partial sums leave as 16-byte stores into the owner's slot
 template<class T, int V>
-__global__ void __launch_bounds__(256, 3)
-ttv_col_scatter_kernel(const ScatterParams P)
+__device__ __forceinline__ void scatter_tiles(const ScatterParams& P, T* sb)
 {
   constexpr int KU = 8;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* sb = reinterpret_cast<T*>(smem_raw);            // [kb]
-
   const T* __restrict__ A = static_cast<const T*>(P.a);
   const T* __restrict__ B = static_cast<const T*>(P.b);
   const uint32_t tid = threadIdx.x;
@@ -87,6 +84,139 @@ ttv_col_scatter_kernel(const ScatterParams P)
       for (int e = 0; e < V; ++e) val.e[e] = acc[0][e];
       *reinterpret_cast<Vec<T, V>*>(dst) = val;
     }
+  }
+}
+
+template<class T, int V>
+__global__ void __launch_bounds__(256, 3)
+ttv_col_scatter_kernel(const ScatterParams P)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  scatter_tiles<T, V>(P, reinterpret_cast<T*>(smem_raw));            // [kb]
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// The WHOLE exchange in one kernel: product + scatter (above), a barrier across the GPUs, and the sum of the received slots.
+//
+//   1  every CTA computes its tiles and stores the partial sums into the owners' slots over NVLink (scatter_tiles);
+//   2  it fences to system scope and counts itself in; the LAST CTA of this GPU to do so publishes "GPU `rank` has
+//      delivered round `token`" by writing the token into flag[rank] of EVERY GPU's flag array (peer stores);
+//   3  every CTA waits until all `world` flags of its OWN array show the token (ld.acquire.sys): all partials for this
+//      GPU's block have landed;
+//   4  the CTAs sum the `world` slots of this GPU's workspace in rank order into its block of C (deterministic).
+//
+// Step 3 spins, so every CTA of the grid must be resident at once: the launcher sizes the grid from the occupancy of this
+// kernel (persistent CTAs striding over the tiles).  Tokens only grow, the two workspace halves alternate (see
+// sharded.PeerExchange), so nothing is ever reset across GPUs; the local arrival counter is reset by the CTA that closes it.
+// A spin that lasts longer than `timeout_ns` sets *error and gives up (a peer that never launched must not hang the GPU).
+// This replaces scatter kernel + library barrier kernel + reduce kernel by one launch (SURVEY 8e "one ncclReduce").
+// ------------------------------------------------------------------------------------------------------------------
+struct ExchangeParams {
+  ScatterParams S;
+  void*     c;                          // this GPU's block of C, n_block elements
+  uint64_t  n_block;
+  uint32_t* flags_peer[kMaxPeers];      // GPU j's flag array [kMaxPeers], addressable from this GPU
+  unsigned long long* counter;          // local: CTAs of this launch that have delivered
+  uint32_t* error;                      // local: set to 1 when a wait timed out
+  unsigned long long timeout_ns;
+  uint32_t  token;                      // round number, grows by one per exchange of the group
+  uint32_t  accumulate;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v)
+{
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// coherent load that bypasses L1 (ld.global.cg): the slots are written by OTHER GPUs while this kernel runs, so the
+// read-only path (ld.global.nc) is not allowed for them
+template<class T, int V>
+__device__ __forceinline__ Vec<T, V> load_cg(const T* p)
+{
+  Vec<T, V> v;
+  constexpr int BYTES = (int)sizeof(T) * V;
+  if constexpr (BYTES == 16) {
+    uint32_t x, y, z, w;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "l"(p) : "memory");
+    uint32_t* d = reinterpret_cast<uint32_t*>(&v); d[0] = x; d[1] = y; d[2] = z; d[3] = w;
+  } else if constexpr (BYTES == 8) {
+    uint32_t x, y;
+    asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(x), "=r"(y) : "l"(p) : "memory");
+    uint32_t* d = reinterpret_cast<uint32_t*>(&v); d[0] = x; d[1] = y;
+  } else {
+    static_assert(BYTES == 4, "vector width");
+    uint32_t x;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(x) : "l"(p) : "memory");
+    *reinterpret_cast<uint32_t*>(&v) = x;
+  }
+  return v;
+}
+
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template<class T, int V>
+__global__ void __launch_bounds__(256, 3)
+ttv_col_exchange_kernel(const ExchangeParams E)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const ScatterParams& P = E.S;
+  scatter_tiles<T, V>(P, reinterpret_cast<T*>(smem_raw));
+
+  // 2: deliver.  Every thread orders its own peer stores before the CTA's arrival; the closing CTA orders all arrivals
+  // before the flags (fence - atomic ... atomic - fence).
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long arrived = atomicAdd(E.counter, 1ull) + 1ull;
+    if (arrived == (unsigned long long)gridDim.x) {
+      *E.counter = 0ull;                                               // ready for the next launch on this stream
+      __threadfence_system();
+      for (uint32_t j = 0; j < P.world; ++j) st_release_sys(E.flags_peer[j] + P.rank, E.token);
+    }
+  }
+  // 3: wait for every GPU's delivery into OUR workspace
+  if (threadIdx.x < P.world) {
+    const uint32_t* mine = E.flags_peer[P.rank] + threadIdx.x;
+    const unsigned long long t0 = global_timer_ns();
+    while ((int32_t)(ld_acquire_sys(mine) - E.token) < 0) {
+      if (global_timer_ns() - t0 > E.timeout_ns) { *E.error = 1u; break; }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+
+  // 4: sum the slots of our block in rank order
+  const T* ws = static_cast<const T*>(P.peer[P.rank]);
+  T* __restrict__ C = static_cast<T*>(E.c);
+  const uint64_t nvec = E.n_block / V;                                 // (n_block is a multiple of V except for the tail below)
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nvec; j += (uint64_t)gridDim.x * blockDim.x) {
+    Vec<T, V> sum;
+    if (E.accumulate) sum = *reinterpret_cast<const Vec<T, V>*>(C + j * V);
+    else {
+#pragma unroll
+      for (int e = 0; e < V; ++e) sum.e[e] = Num<T>::zero();
+    }
+    for (uint32_t r = 0; r < P.world; ++r) {
+      const Vec<T, V> x = load_cg<T, V>(ws + (uint64_t)r * P.blk + j * V);          // coherent, L1 bypassed: the data came in over NVLink
+#pragma unroll
+      for (int e = 0; e < V; ++e) sum.e[e] = Num<T>::add(sum.e[e], x.e[e]);
+    }
+    *reinterpret_cast<Vec<T, V>*>(C + j * V) = sum;
+  }
+  for (uint64_t j = nvec * V + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < E.n_block; j += (uint64_t)gridDim.x * blockDim.x) {
+    T sum = E.accumulate ? C[j] : Num<T>::zero();
+    for (uint32_t r = 0; r < P.world; ++r) sum = Num<T>::add(sum, load_cg<T, 1>(ws + (uint64_t)r * P.blk + j).e[0]);
+    C[j] = sum;
   }
 }
 

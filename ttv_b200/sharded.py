@@ -84,7 +84,7 @@ class PeerExchange:
     orders the reuse of a half behind the barrier of the round in between) of [world][blk_cap] elements, all mapped into
     every process of the group (torch.distributed._symmetric_memory: peer pointers over NVLink)."""
 
-    def __init__(self, max_c_elems: int, dtype, device, group=None):
+    def __init__(self, max_c_elems: int, dtype, device, group=None, single_kernel: bool = True):
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
@@ -97,15 +97,29 @@ class PeerExchange:
         self.buf = symm_mem.empty(2 * self.world * self.blk_cap, dtype=dtype, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, self.group.group_name)
         self.round = 0
+        # single-kernel form (ttv_b200_view_exchange): one flag word per rank on every GPU, mapped into every process, plus
+        # 16 bytes of local scratch (arrival counter + error flag).  Tokens = round numbers, they only grow.
+        self.single_kernel = single_kernel
+        self.flags = symm_mem.empty(64, dtype=torch.int32, device=device)
+        self.flags.zero_()
+        self.flags_hdl = symm_mem.rendezvous(self.flags, self.group.group_name)
+        self.scratch = torch.zeros(4, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        self.flags_hdl.barrier(channel=0)                    # every rank's flags are zero before anybody writes a token
 
     @staticmethod
     def block(n: int, world: int) -> int:
         """elements of C's flat index space per rank: equal blocks, rounded up to 256 elements (whole 16-byte vectors)"""
         return -(-(-(-n // world)) // 256) * 256
 
+    def timed_out(self) -> bool:
+        """True when a single-kernel exchange gave up waiting for a peer (reads the error word: synchronises)"""
+        return bool(int(self.scratch[2].item()))
+
     def exchange(self, outer: int, nq: int, inner: int, a_local, b_local):
         """partial product of this rank -> peers' slots -> barrier -> sum of the received slots.  Returns (c_block, first,
-        count): this rank's block [first, first + count) of the flat C."""
+        count): this rank's block [first, first + count) of the flat C.  single_kernel (default): all of it is ONE kernel
+        launch per GPU (in-kernel flag barrier over NVLink); otherwise scatter kernel + symmetric-memory barrier + reduce kernel."""
         import torch
         from . import api
         n = outer * inner
@@ -115,10 +129,17 @@ class PeerExchange:
         half = (self.round % 2) * self.world * self.blk_cap
         self.round += 1
         peers = [int(p) + half * self.itemsize for p in self.hdl.buffer_ptrs]
-        api.ttv_view_scatter(outer, nq, inner, a_local, b_local, peers, self.rank, blk)
-        self.hdl.barrier(channel=0)                      # every rank's partials have landed in every owner's slots
         first = min(n, self.rank * blk)
         count = max(0, min(blk, n - first))
+        if self.single_kernel:
+            # ONE launch: the kernel scatters its partials, tells every GPU that it has delivered round `self.round`, waits for
+            # all deliveries into its own workspace and sums them
+            c_block = torch.empty(count, dtype=self.dtype, device=a_local.device)
+            api.ttv_view_exchange(outer, nq, inner, a_local, b_local, peers, [int(p) for p in self.flags_hdl.buffer_ptrs], self.rank, blk,
+                                  c_block if count else None, self.round, self.scratch)
+            return c_block, first, count
+        api.ttv_view_scatter(outer, nq, inner, a_local, b_local, peers, self.rank, blk)
+        self.hdl.barrier(channel=0)                      # every rank's partials have landed in every owner's slots
         c_block = torch.empty(count, dtype=self.dtype, device=a_local.device)
         if count:
             api.reduce_slots(self.buf[half: half + self.world * blk], c_block, count, blk, self.world)
