@@ -58,7 +58,7 @@ def algo_bytes(na, q, elem=ELEM):
 
 
 def workload_name(n, nccl_reduce=False):
-    how = "n_q split + NCCL reduce" if nccl_reduce else "n_q split, exchange fused into the kernel's stores over NVLink peer memory"
+    how = "n_q split + NCCL reduce" if nccl_reduce else "n_q split, the whole exchange in the product's kernel: stores over NVLink peer memory, in-kernel barrier, slot sum"
     return (f"cfg2 symmetric sweep: order-4 fp32 n=(256,256,256,{EXT * n}) first-order, one step = q=1..4; "
             f"{'single GPU' if n == 1 else f'sharded along mode 4 over {n} GPUs (q=1..3 free split, q=4 {how})'}")
 
@@ -542,7 +542,7 @@ def cfg5_leg(torch, dist, ttv_b200, rank, world, dev, args):
             exchange = None
     out = {"workload": f"BASELINE configs[4]: order-3 fp64 n=(2048,2048,2048) first-order, strong scaling over {world} GPU(s), sharded along mode 3",
            "scaling": "strong", "per_gpu_tensor_bytes": sh.a_count * 8,
-           "exchange": None if world == 1 else ("fused into the kernel's stores over NVLink peer memory" if exchange is not None else "ncclReduce")}
+           "exchange": None if world == 1 else ("one kernel per GPU: stores over NVLink peer memory, in-kernel flag barrier, slot sum" if exchange is not None else "ncclReduce")}
     reps = max(5, min(args.steps, 20))
     rng = np.random.default_rng(55 + rank)
     for q in (1, 2, 3):
@@ -583,7 +583,9 @@ def cfg5_leg(torch, dist, ttv_b200, rank, world, dev, args):
                         "ms": round(ms, 4), "gbs": round(byt / ms / 1e6, 1), "gbs_per_gpu": round(byt / ms / 1e6 / world, 1),
                         "frac_of_nominal_8000_per_gpu": round(byt / ms / 1e6 / world / 8000.0, 4),
                         "rank_ms_min": round(min(ms_all), 4), "rank_ms_max": round(max(ms_all), 4),
-                        "kernel": ("ttv_col_scatter_kernel + barrier + ttv_reduce_kernel" if (s.kind == "nq-scattered") else kernel_label(pl)),
+                        "kernel": (("ttv_col_exchange_kernel (product + scatter over NVLink + in-kernel barrier + slot sum, one launch)"
+                                    if exchange.single_kernel else "ttv_col_scatter_kernel + symmetric-memory barrier + ttv_reduce_kernel")
+                                   if (s.kind == "nq-scattered") else kernel_label(pl)),
                         "samples_checked": nchk, "parity_failures": bad}
     del a, cs
     torch.cuda.empty_cache()

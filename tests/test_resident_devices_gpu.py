@@ -87,6 +87,7 @@ def test_one_host_tensor_over_several_devices(oracle, dtype, monkeypatch):
     import torch
     n_dev = torch.cuda.device_count()
     monkeypatch.setenv("TTV_B200_MULTI_MIN_MB", "0")                # these tensors are tiny: split them anyway
+    monkeypatch.setenv("TTV_B200_MULTI_PAGEABLE_NQ", "1")           # ... also the n_q split of these PAGEABLE arrays (kept on one device by default)
     rng = np.random.default_rng(8)
     for devices in ([0, 0], list(range(n_dev)) if n_dev > 1 else [0, 0, 0], [0] * 5, [0]):
         for chunk_mb in ("128", "1"):

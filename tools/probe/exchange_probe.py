@@ -13,8 +13,26 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
-METRICS = ("gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,nvltx__bytes.sum,nvlrx__bytes.sum,"
-           "lts__t_sectors_srcunit_tex_aperture_peer.sum,lts__t_sectors_srcunit_tex_aperture_peer_op_write.sum")
+METRICS = "gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,nvltx__bytes_data_user.sum,nvlrx__bytes_data_user.sum"
+
+
+def nvlink_kib(index):
+    """(tx, rx) KiB of user data this GPU has moved over all its NVLink links since the driver loaded (NVML field values
+    NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX / _RX, scope = all links), or None when the platform does not expose them"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        vals = pynvml.nvmlDeviceGetFieldValues(h, [(pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, 0xFFFFFFFF),
+                                                   (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xFFFFFFFF)])
+        out = []
+        for v in vals:
+            if v.nvmlReturn != 0:
+                return None
+            out.append(int(v.value.ullVal))
+        return tuple(out)
+    except Exception:
+        return None
 
 
 def main():
@@ -47,16 +65,21 @@ def main():
     if not args.ncu_rank0:
         forms["ONE kernel, in-kernel barrier"] = PeerExchange(sh.c_count, torch.float64, dev)
     byt = 8 * (2048 ** 3 + 2048 + 2048 ** 2)
-    results = {}
+    results, nvl = {}, {}
     for name, ex in forms.items():
         for _ in range(3):
             ttv_sharded(q, a, na, pia, b, rank=rank, world=world, c_local=c, reduce_to=0, exchange=ex, asynchronous=True)
         dist.barrier(); torch.cuda.synchronize()
+        nv0 = nvlink_kib(local)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.reps):
             out, s = ttv_sharded(q, a, na, pia, b, rank=rank, world=world, c_local=c, reduce_to=0, exchange=ex, asynchronous=True)
         e1.record(); torch.cuda.synchronize()
+        dist.barrier()
+        nv1 = nvlink_kib(local)
+        if nv0 is not None and nv1 is not None:
+            nvl[name] = ((nv1[0] - nv0[0]) / args.reps / 1024.0, (nv1[1] - nv0[1]) / args.reps / 1024.0)      # MiB per exchange
         t = torch.tensor([e0.elapsed_time(e1) / args.reps], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         results[name] = float(t.item())
@@ -66,7 +89,8 @@ def main():
         print(f"cfg5 q=3 over {world} GPUs (per GPU: {sh.a_count * 8 / 1e9:.2f} GB of A, partial C {sh.c_count * 8 / 2 ** 20:.0f} MiB, "
               f"algorithmic NVLink bytes out per GPU {sh.c_count * 8 * (world - 1) / world / 2 ** 20:.1f} MiB)")
         for name, ms in results.items():
-            print(f"  {name:52s} {ms:8.4f} ms   {byt / ms / 1e6:9.1f} GB/s aggregate   {byt / ms / 1e6 / world:8.1f} GB/s per GPU", flush=True)
+            link = f"   NVLink user data of rank 0 per exchange (NVML): tx {nvl[name][0]:.1f} MiB, rx {nvl[name][1]:.1f} MiB" if name in nvl else ""
+            print(f"  {name:52s} {ms:8.4f} ms   {byt / ms / 1e6:9.1f} GB/s aggregate   {byt / ms / 1e6 / world:8.1f} GB/s per GPU{link}", flush=True)
     dist.destroy_process_group()
 
 

@@ -1263,7 +1263,10 @@ int ttv_b200_run_devices(int dtype, uint64_t q, uint64_t p,
   const bool nq_split = v.outer == 1 || (v.outer % slow) != 0;
   const bool divisible = !v.strided && slow >= 2 && (!nq_split || (v.outer == 1 && v.nq == slow));
   const uint64_t min_bytes = (uint64_t)env_mb("TTV_B200_MULTI_MIN_MB", 64) << 20;
-  if (n_devices == 1 || !divisible || total * s < min_bytes) {
+  // Pageable memory reaches the GPUs through the copy threads' memcpy into pinned buffers, which ONE link already matches
+  // (measured on 2 GPUs, 4 GiB: free split 48 -> 58 GB/s, n_q split 49 -> 30 GB/s): a pageable n_q split stays on one device.
+  const bool pageable_nq = nq_split && !is_pinned_host(a) && env_mb("TTV_B200_MULTI_PAGEABLE_NQ", 0) == 0;
+  if (n_devices == 1 || !divisible || total * s < min_bytes || pageable_nq) {
     base.device = devices[0];
     return run_view_host(dtype, v, a, b, c, &base);
   }
