@@ -182,3 +182,25 @@ def test_native_chain_async_on_a_stream_and_errors():
     assert e.value.status == 41
     ttv_b200._lib.load().ttv_b200_release()                # waits, frees staging / workspaces, trims the pool
     assert np.array_equal(tp.ttvs(3, A, bs), want)         # and everything comes back on demand
+
+
+def test_mixed_operand_types_are_promoted_not_truncated():
+    """the reference binds array_t<double> and converts every operand (wrapped_ttv.cpp:205-206): an integer A with a fractional
+    b, or a real A with a complex b, must not be cast down to A's type (round-1 advisor finding)"""
+    rng = np.random.default_rng(11)
+    A = rng.integers(-4, 5, (3, 2, 4))
+    b = np.array([0.5, 0.25, -1.5])
+    got = tp.ttv(1, A, b)
+    assert got.dtype == np.float64 and np.allclose(got, np.einsum("ijk,i->jk", A, b))
+    assert np.array_equal(tp.ttv(1, A, [1, 2, 3]), np.einsum("ijk,i->jk", A, [1, 2, 3]))          # integers stay exact
+    Af = rng.uniform(-1, 1, (3, 2, 4)).astype(np.float32)
+    bc = (rng.uniform(-1, 1, 2) + 1j * rng.uniform(-1, 1, 2)).astype(np.complex64)
+    got = tp.ttv(2, Af, bc)
+    assert got.dtype == np.complex64 and np.allclose(got, np.einsum("ijk,j->ik", Af, bc), atol=1e-6)
+    bs = [np.array([0.5, 1.5]), np.array([1, 2, 3, 4])]                                          # float64 and int vectors, int tensor
+    got = tp.ttvs(1, A, bs, "optimal")
+    assert got.dtype == np.float64 and np.allclose(got, np.einsum("ijk,j,k->i", A, *bs))
+    import torch
+    tA = torch.from_numpy(A).cuda()                                                               # int64 device tensor, float vector
+    got = tp.ttv(1, tA, torch.from_numpy(b).cuda())
+    assert got.dtype == torch.float64 and np.allclose(got.cpu().numpy(), np.einsum("ijk,i->jk", A, b))
