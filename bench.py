@@ -579,6 +579,32 @@ def cfg5_leg(torch, dist, ttv_b200, rank, world, dev, args):
         byt = 8 * (2048 ** 3 + 2048 + 2048 ** 2)
         pl = ttv_b200.plan(q, list(shards[q].na_local), pia, dtype=dt) if shards[q].count else {}
         from ttv_b200.measure import kernel_label
+        forms = None
+        if q == 3 and world > 1 and exchange is not None:
+            # the same product with the two other exchange forms, timed the same way (none of them is the headline)
+            forms = {}
+            others = {"plain kernel + ncclReduce": None}
+            try:
+                others["scatter kernel + symmetric-memory barrier + reduce kernel"] = PeerExchange(shards[3].c_count, torch.float64, dev, single_kernel=False)
+            except Exception:
+                pass
+            for fname, ex2 in others.items():
+                for _ in range(3):
+                    ttv_sharded(q, a, na, pia, bs[q], rank=rank, world=world, c_local=cs[q], reduce_to=0, exchange=ex2, asynchronous=True)
+                dist.barrier()
+                torch.cuda.synchronize()
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                for _ in range(reps):
+                    ttv_sharded(q, a, na, pia, bs[q], rank=rank, world=world, c_local=cs[q], reduce_to=0, exchange=ex2, asynchronous=True)
+                f1.record()
+                torch.cuda.synchronize()
+                t = torch.tensor([f0.elapsed_time(f1) / reps], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                forms[fname] = round(float(t.item()), 4)
+            forms["one kernel: scatter over NVLink + in-kernel barrier + slot sum"] = round(ms, 4)
+            if exchange.timed_out():
+                raise SystemExit(f"bench.py: rank {rank}: the single-kernel exchange timed out")
         out[f"q{q}"] = {"split": "free (no communication)" if shards[q].kind == "free" else "n_q split",
                         "ms": round(ms, 4), "gbs": round(byt / ms / 1e6, 1), "gbs_per_gpu": round(byt / ms / 1e6 / world, 1),
                         "frac_of_nominal_8000_per_gpu": round(byt / ms / 1e6 / world / 8000.0, 4),
@@ -587,6 +613,8 @@ def cfg5_leg(torch, dist, ttv_b200, rank, world, dev, args):
                                     if exchange.single_kernel else "ttv_col_scatter_kernel + symmetric-memory barrier + ttv_reduce_kernel")
                                    if (s.kind == "nq-scattered") else kernel_label(pl)),
                         "samples_checked": nchk, "parity_failures": bad}
+        if forms:
+            out[f"q{q}"]["exchange_forms_ms"] = forms
     del a, cs
     torch.cuda.empty_cache()
     return out

@@ -69,8 +69,9 @@ def main():
     for name, ex in forms.items():
         for _ in range(3):
             ttv_sharded(q, a, na, pia, b, rank=rank, world=world, c_local=c, reduce_to=0, exchange=ex, asynchronous=True)
-        dist.barrier(); torch.cuda.synchronize()
-        nv0 = nvlink_kib(local)
+        torch.cuda.synchronize()
+        nv0 = nvlink_kib(local)               # (NVML can take tens of ms: read it BEFORE the barrier, or the other ranks' timed
+        dist.barrier(); torch.cuda.synchronize()   #  windows would include this rank's delay through the exchange itself)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.reps):
@@ -91,6 +92,9 @@ def main():
         for name, ms in results.items():
             link = f"   NVLink user data of rank 0 per exchange (NVML): tx {nvl[name][0]:.1f} MiB, rx {nvl[name][1]:.1f} MiB" if name in nvl else ""
             print(f"  {name:52s} {ms:8.4f} ms   {byt / ms / 1e6:9.1f} GB/s aggregate   {byt / ms / 1e6 / world:8.1f} GB/s per GPU{link}", flush=True)
+    del forms, results
+    torch.cuda.synchronize()
+    dist.barrier()
     dist.destroy_process_group()
 
 
