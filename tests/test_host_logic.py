@@ -298,7 +298,8 @@ def test_chooser_only_picks_instantiated_kernels():
                 assert (key in {(1, 8), (2, 4), (4, 2)} and wide or key == (8, 2) and size[dt] == 4) and size[dt] < 16, (dt, outer, nq, inner, pl)
                 assert inner * size[dt] >= 2048 and inner % (16 // size[dt]) != 0
                 if -(-nq // (16 // size[dt])) < 48:      # short contraction: warp-autonomous form, no shared memory
-                    assert (pl["tx"], pl["ty"], pl["smem_bytes"]) == (32, 1, 0) and pl["ku"] % pl["vec"] == 0 and pl["vec"] == 2
+                    # (complex<float> takes the realigned form COLR, whose outputs leave through a warp-private shared-memory strip)
+                    assert (pl["tx"], pl["ty"]) == (32, 1) and (pl["smem_bytes"] == 0 or dt == "c64") and pl["ku"] % pl["vec"] == 0 and pl["vec"] == 2
                 else:
                     assert pl["ty"] == 16 // size[dt] and pl["tx"] * pl["ty"] <= 256 and pl["smem_bytes"] <= 100 * 1024
                 continue

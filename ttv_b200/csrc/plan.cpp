@@ -300,7 +300,7 @@ static int env_int(const char* name, int fallback)
 
 // COLX launch shape.  TY = V lanes along n_q (one per phase), TX lanes along inner; a tile owns W output columns and
 // loads W/V + 1 vectors per row; W is chosen so that the tiles of a row are of (nearly) equal width.
-static int choose_colx(uint64_t s, const View& v, const ttv_b200_opts* opts, uint64_t sms, Launch* out)
+static int choose_colx(uint64_t s, bool is_complex, const View& v, const ttv_b200_opts* opts, uint64_t sms, Launch* out)
 {
   Launch l;
   const uint64_t V = vmax_of(s), NT = 256;
@@ -326,8 +326,11 @@ static int choose_colx(uint64_t s, const View& v, const ttv_b200_opts* opts, uin
     // Measured (23^7 q=4,7 fp32; 21^7 q=7 fp64): the realigned form (80 registers, 3 CTAs per SM, whole-sector stores)
     // is no faster than the phase-class form (115 registers, 2 CTAs): 6.48-6.53 against 6.46-6.55 TB/s in fp32, 6.33
     // against 6.57 in fp64 -- neither residency nor the partial-sector stores bound these shapes -- so COLW stays the
-    // default and COLR is kept selectable (profiles/r01_colr_probe.txt).
-    l.warp = warp_mode == 2 ? 2 : 1; l.tx = 32; l.ty = 1;
+    // default and COLR is kept selectable (profiles/r01_colr_probe.txt).  EXCEPT complex<float> (round 2, 25^6 in three
+    // layouts, profiles/r02_variants_weak_shapes.txt): COLW keeps V x V complex accumulators per unit there and runs
+    // 5 863-6 388 GB/s where COLR runs 6 394-6 661 ([15625, 25, 625]: 5 863 -> 6 394), so complex<float> takes COLR.
+    const bool colr = warp_mode == 2 || (warp_mode == -1 && is_complex && s == 8 && env_int("TTV_B200_COLR_C64", 1) != 0);
+    l.warp = colr ? 2 : 1; l.tx = 32; l.ty = 1;
     uint64_t Vw = V, loads = 8;
     uint64_t ku = V;
     if (l.warp == 1) {
@@ -472,7 +475,14 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
     // (1 CTA of up to 1024 threads x 3 stages per SM, ~100-150 KB in flight): 23 x 529 floats (48.7 KB) run at 6.7-6.8
     // TB/s this way, 4.9 with the warp form of COLX, whose units of 62 columns tile a row of 529 badly; 21 x 441 doubles
     // (74 KB) 6.5 against 5.9.
-    const uint64_t small_payload = (uint64_t)env_int("TTV_B200_STAGE_KB", 36) * 1024 - 128;
+    // Stage size of the shared (small-slab) form, measured per shape family in round 2 (profiles/r02_stream_stage_sweep.txt;
+    // the landscape is not monotonic): 36 KB x 3 stages x 2 CTAs per SM for 4-byte elements and for n_q = 2, 3; FIBERS of
+    // 8-byte elements do better with one CTA per SM and up to 56 KB per stage (21 doubles 6 516 -> 6 939, 73 doubles
+    // 6 387 -> 7 045, 25 complex<float> 6 146 -> 6 767 GB/s), slabs of 8-byte elements of up to 4 KB with 24 KB stages
+    // (21 x 21 doubles 6 408 -> 6 874).
+    int stage_kb = 36;
+    if (s == 8 && v.nq >= 8) stage_kb = v.inner == 1 ? 56 : (slab_bytes <= 4096 ? 24 : 36);
+    const uint64_t small_payload = (uint64_t)env_int("TTV_B200_STAGE_KB", stage_kb) * 1024 - 128;
     const uint64_t big_slab_max = (uint64_t)env_int("TTV_B200_STREAM_SLAB_KB", 75) * 1024;
     const bool big_slab = slab_bytes > small_payload;
     const uint64_t big_stage = (slab_bytes + 32 + 127) / 128 * 128, b_bytes16 = (v.nq * s + 15) / 16 * 16;
@@ -572,7 +582,7 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
                     : mode == 1 ? eligible
                     : mode == 0 ? false
                     : (eligible && odd && v.inner * s >= 2048);
-    if (pick) return choose_colx(s, v, opts, sms, out);
+    if (pick) return choose_colx(s, dtype_is_complex(dtype) != 0, v, opts, sms, out);
   }
 
   l.threads = (uint32_t)env_int("TTV_B200_THREADS", 256);

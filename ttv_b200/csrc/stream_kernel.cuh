@@ -140,6 +140,11 @@ __device__ __forceinline__ void stream_fibers_skewed(const T* slab0, const T* sb
 // MAXT: 256 threads, 2 CTAs per SM for the shared stages of small slabs; up to 1024 threads, 1 CTA per SM when a big
 // slab is alone in its stage (the 8 warps of a 256-thread CTA cannot hide the shared-memory latency of 500+ outputs:
 // 23 x 529 floats ran at 4.5 TB/s with 30 % of the issue slots busy and 6.5 cycles between two instructions of a warp)
+// partial sums per output on the one-output-per-thread path (stages that hold fewer outputs than UO rounds of the CTA)
+#ifndef TTVB_STREAM_KR
+#define TTVB_STREAM_KR(MAXT) ((MAXT) > 256 ? 4 : 1)
+#endif
+
 template<class T, int NS, int UO, bool SKEW = false, int MAXT = 256>
 __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 2 : 1)
 ttv_stream_kernel(const StreamParams P)
@@ -223,7 +228,7 @@ ttv_stream_kernel(const StreamParams P)
         // outputs u0, u0 + NT, ... of this thread; a full set of UO shares every b[k], stragglers go one by one
         if (u0 + (UO - 1) * blockDim.x < outs) stream_outputs<T, UO, (UO == 1 ? 4 : 1)>(slab0, sb, C + o0 * inner, u0, blockDim.x, nq, inner, M, P.accumulate);
         else
-          for (uint32_t u = u0; u < outs; u += blockDim.x) stream_outputs<T, 1, (MAXT > 256 ? 4 : 1)>(slab0, sb, C + o0 * inner, u, blockDim.x, nq, inner, M, P.accumulate);
+          for (uint32_t u = u0; u < outs; u += blockDim.x) stream_outputs<T, 1, TTVB_STREAM_KR(MAXT)>(slab0, sb, C + o0 * inner, u, blockDim.x, nq, inner, M, P.accumulate);
       }
     }
 
