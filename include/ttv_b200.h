@@ -244,8 +244,9 @@ int ttv_b200_reduce_slots(int dtype, const void* ws, void* c, uint64_t n, uint64
  *   peer_flags[j]  GPU j's flag array (>= 16 x uint32, zero before the first round), mapped like peer_ws
  *   token          round number of the group: 1, 2, 3, ... (every GPU passes the same value; flags only grow)
  *   scratch        16 bytes of LOCAL device memory, zeroed once: arrival counter (8) + error flag (4)
- *   max_ctas       cap of the persistent grid; 0 = every CTA the device can hold at once (all CTAs must be resident:
- *                  they spin on the flags).  Peer workspaces must alternate between two halves from round to round.
+ *   max_ctas       how many of the LAST CTAs to finish stay for the barrier and the slot sum; 0 = one per SM.  Only they
+ *                  wait, so the grid is the usual oversubscribed one.  Peer workspaces must alternate between two halves
+ *                  from round to round.
  * Asynchronous with TTV_B200_FLAG_ASYNC; a wait longer than 10 s (TTV_B200_EXCHANGE_TIMEOUT_MS) sets the error flag, which
  * synchronous calls report as TTV_B200_ERR_CUDA. */
 int ttv_b200_view_exchange(int dtype, uint64_t outer, uint64_t nq, uint64_t inner, const void* a, const void* b,

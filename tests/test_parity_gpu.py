@@ -902,10 +902,10 @@ def test_colt_kernel_tma_tensor_tiles(dtype, oracle, monkeypatch):
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.complex64, np.complex128])
 def test_single_kernel_exchange_emulated_on_one_gpu(dtype, oracle, monkeypatch):
     """ttv_b200_view_exchange: product + scatter + in-kernel flag barrier + sum of the slots in ONE kernel per rank.  The
-    `world` ranks are `world` kernels on separate streams of one device, each capped at a few CTAs so that all of them are
-    resident together (every CTA spins until all ranks have delivered).  Several rounds: tokens grow, the two workspace
-    halves alternate, the arrival counter resets itself.  The timeout is short so that a protocol bug fails instead of
-    hanging the device."""
+    `world` ranks are `world` kernels on separate streams of one device; only the last few CTAs of each kernel to finish stay
+    for the barrier (max_ctas caps them, so that the waiting CTAs of all emulated ranks fit on the device together with the
+    CTAs still computing).  Several rounds: tokens grow, the two workspace halves alternate, the arrival counter resets
+    itself.  The timeout is short so that a protocol bug fails instead of hanging the device."""
     import torch
     from ttv_b200.sharded import PeerExchange, split_range
     monkeypatch.setenv("TTV_B200_EXCHANGE_TIMEOUT_MS", "3000")

@@ -453,14 +453,12 @@ static cudaError_t launch_exchange_vec(const ExchangeParams& E, uint32_t max_cta
 {
   if constexpr (V <= kVmax) {
     auto kern = ttv_col_exchange_kernel<elem_t, V>;
-    // every CTA spins on the other GPUs' flags, so the whole grid has to be resident at once
-    int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, (size_t)smem);
-    if (e != cudaSuccess) return e;
-    uint64_t ctas = (uint64_t)std::max(1, per_sm) * (uint64_t)sm_count;
-    if (max_ctas) ctas = std::min<uint64_t>(ctas, max_ctas);
-    ctas = std::max<uint64_t>(1, std::min<uint64_t>(ctas, std::max<uint64_t>(E.S.tiles, 1)));
-    kern<<<(unsigned)ctas, 256, smem, stream>>>(E);
+    // the grid of the plain kernels (CTAs stride over the tiles); only the last `reducers` CTAs to arrive wait for the other
+    // GPUs, one per SM unless capped -- far fewer than the device holds at once, so the rest always finds room
+    ExchangeParams E2 = E;
+    E2.reducers = max_ctas ? max_ctas : (uint32_t)sm_count;
+    const uint64_t ctas = std::max<uint64_t>(1, std::min<uint64_t>(std::max<uint64_t>(E.S.tiles, 1), (uint64_t)sm_count * 64));
+    kern<<<(unsigned)ctas, 256, smem, stream>>>(E2);
     count_launch();
     return cudaGetLastError();
   } else {

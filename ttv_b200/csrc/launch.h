@@ -19,7 +19,7 @@ cudaError_t launch_scatter(int dtype, const View& v, const void* a, const void* 
                            uint64_t blk, int vec, int sm_count, cudaStream_t stream);
 // The whole exchange in ONE kernel (ttv_col_exchange_kernel): product + scatter, cross-GPU flag barrier, sum of the slots into
 // this GPU's block of C.  flags[j]: GPU j's flag array; counter / error: 8 + 4 bytes of local device memory (zero at first use).
-// max_ctas caps the persistent grid (0 = every CTA the device can hold at once).
+// max_ctas caps the CTAs that stay for the barrier and the slot sum (0 = one per SM).
 cudaError_t launch_exchange(int dtype, const View& v, const void* a, const void* b, void* const* peers, void* const* flags,
                             uint32_t world, uint32_t rank, uint64_t blk, int vec, void* c_block, uint64_t n_block, uint32_t token,
                             void* counter, void* error, bool accumulate, uint64_t timeout_ns, uint32_t max_ctas, int sm_count,

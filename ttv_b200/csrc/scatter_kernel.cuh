@@ -99,17 +99,21 @@ ttv_col_scatter_kernel(const ScatterParams P)
 // The WHOLE exchange in one kernel: product + scatter (above), a barrier across the GPUs, and the sum of the received slots.
 //
 //   1  every CTA computes its tiles and stores the partial sums into the owners' slots over NVLink (scatter_tiles);
-//   2  it fences to system scope and counts itself in; the LAST CTA of this GPU to do so publishes "GPU `rank` has
-//      delivered round `token`" by writing the token into flag[rank] of EVERY GPU's flag array (peer stores);
-//   3  every CTA waits until all `world` flags of its OWN array show the token (ld.acquire.sys): all partials for this
-//      GPU's block have landed;
-//   4  the CTAs sum the `world` slots of this GPU's workspace in rank order into its block of C (deterministic).
+//   2  it fences to system scope and counts itself in.  All but the LAST `reducers` CTAs to arrive are done and exit -- the
+//      grid is the same oversubscribed one the plain kernels use (64 CTAs per SM queued), nothing has to be co-resident.
+//      The very last arrival publishes "GPU `rank` has delivered round `token`" by writing the token into flag[rank] of
+//      EVERY GPU's flag array (peer stores), its own included;
+//   3  the last `reducers` arrivals (one per SM by default) wait until all `world` flags of their OWN array show the token
+//      (ld.acquire.sys): all partials for this GPU's block have landed.  They hold at most a third of the CTA slots, so the
+//      CTAs that still have to arrive always find room: no deadlock;
+//   4  they sum the `world` slots of this GPU's workspace in rank order into its block of C (deterministic).
 //
-// Step 3 spins, so every CTA of the grid must be resident at once: the launcher sizes the grid from the occupancy of this
-// kernel (persistent CTAs striding over the tiles).  Tokens only grow, the two workspace halves alternate (see
-// sharded.PeerExchange), so nothing is ever reset across GPUs; the local arrival counter is reset by the CTA that closes it.
-// A spin that lasts longer than `timeout_ns` sets *error and gives up (a peer that never launched must not hang the GPU).
+// Tokens only grow, the two workspace halves alternate (see sharded.PeerExchange), so nothing is ever reset across GPUs; the
+// local arrival counter is reset by the CTA that closes it.  A wait that lasts longer than `timeout_ns` sets *error and gives
+// up (a peer that never launched must not hang the GPU).
 // This replaces scatter kernel + library barrier kernel + reduce kernel by one launch (SURVEY 8e "one ncclReduce").
+// (A first version ran a persistent grid of resident CTAs that all waited: 3 % slower on 2 GPUs than the three-launch form,
+// the 8 192 tiles of a 34 GB slab over 444 CTAs leave the last wave half empty.)
 // ------------------------------------------------------------------------------------------------------------------
 struct ExchangeParams {
   ScatterParams S;
@@ -121,6 +125,7 @@ struct ExchangeParams {
   unsigned long long timeout_ns;
   uint32_t  token;                      // round number, grows by one per exchange of the group
   uint32_t  accumulate;
+  uint32_t  reducers;                   // how many of the last CTAs to arrive stay for the barrier and the slot sum
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
@@ -174,15 +179,19 @@ ttv_col_exchange_kernel(const ExchangeParams E)
 
   // 2: deliver.  Every thread orders its own peer stores before the CTA's arrival; the closing CTA orders all arrivals
   // before the flags (fence - atomic ... atomic - fence).
+  __shared__ unsigned long long s_arrival;
   __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned long long arrived = atomicAdd(E.counter, 1ull) + 1ull;
-    if (arrived == (unsigned long long)gridDim.x) {
-      *E.counter = 0ull;                                               // ready for the next launch on this stream
-      __threadfence_system();
-      for (uint32_t j = 0; j < P.world; ++j) st_release_sys(E.flags_peer[j] + P.rank, E.token);
-    }
+  if (threadIdx.x == 0) s_arrival = atomicAdd(E.counter, 1ull);
+  __syncthreads();
+  const unsigned long long arrival = s_arrival;                        // 0 .. gridDim.x - 1
+  const unsigned long long R = min((unsigned long long)max(E.reducers, 1u), (unsigned long long)gridDim.x);
+  if (arrival + R < (unsigned long long)gridDim.x) return;             // not among the last R: done
+  const uint64_t me = arrival - ((unsigned long long)gridDim.x - R);   // reducer index 0 .. R-1
+  if (arrival + 1 == (unsigned long long)gridDim.x && threadIdx.x == 0) {
+    *E.counter = 0ull;                                                 // ready for the next launch on this stream
+    __threadfence_system();
+    for (uint32_t j = 0; j < P.world; ++j) st_release_sys(E.flags_peer[j] + P.rank, E.token);
   }
   // 3: wait for every GPU's delivery into OUR workspace
   if (threadIdx.x < P.world) {
@@ -199,7 +208,7 @@ ttv_col_exchange_kernel(const ExchangeParams E)
   const T* ws = static_cast<const T*>(P.peer[P.rank]);
   T* __restrict__ C = static_cast<T*>(E.c);
   const uint64_t nvec = E.n_block / V;                                 // (n_block is a multiple of V except for the tail below)
-  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nvec; j += (uint64_t)gridDim.x * blockDim.x) {
+  for (uint64_t j = me * blockDim.x + threadIdx.x; j < nvec; j += R * blockDim.x) {
     Vec<T, V> sum;
     if (E.accumulate) sum = *reinterpret_cast<const Vec<T, V>*>(C + j * V);
     else {
@@ -213,7 +222,7 @@ ttv_col_exchange_kernel(const ExchangeParams E)
     }
     *reinterpret_cast<Vec<T, V>*>(C + j * V) = sum;
   }
-  for (uint64_t j = nvec * V + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < E.n_block; j += (uint64_t)gridDim.x * blockDim.x) {
+  for (uint64_t j = nvec * V + me * blockDim.x + threadIdx.x; j < E.n_block; j += R * blockDim.x) {
     T sum = E.accumulate ? C[j] : Num<T>::zero();
     for (uint32_t r = 0; r < P.world; ++r) sum = Num<T>::add(sum, load_cg<T, 1>(ws + (uint64_t)r * P.blk + j).e[0]);
     C[j] = sum;
