@@ -74,3 +74,15 @@ def test_library_staleness_is_decided_by_content_of_every_source():
     assert stamp == build.source_hash() and len(stamp) == 64
     os.utime(os.path.join(ROOT, "ttv_b200", "csrc", "plan.cpp"))   # ... and a fresh mtime (a snapshot copied elsewhere) changes nothing
     assert not build.stale()
+
+
+def test_roofline_traffic_file_names_the_kernel_the_chooser_launches():
+    """bench.py reports `roofline.traffic` only while profiles/roofline_traffic.json was captured for the kernel this tree
+    launches on the bench workload (the number must not go stale silently when the chooser changes)"""
+    import json
+    rec = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+    for q in (2, 3, 4):
+        pl = ttv_b200.plan(q, [256] * 4, [1, 2, 3, 4], dtype="f32")
+        assert pl["kernel"] == 2 and rec["kernel"] == f"ttv_col_kernel<float,{pl['vec']},{pl['nu']},{pl['ku']}>"
+    assert rec["algorithmic_bytes_per_launch"] == 4 * (256 ** 4 + 256 + 256 ** 3)
+    assert 0.99 < rec["col_kernel_dram_bytes_per_launch"] / rec["algorithmic_bytes_per_launch"] < 1.02

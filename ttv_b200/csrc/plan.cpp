@@ -524,7 +524,7 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
       // a big slab is alone in its stage and the CTA alone on its SM; more than three stages (TTV_B200_STREAM_STAGES, up
       // to 5 when they fit) measured no better: 23 x 529 floats 6.80 TB/s with 3 stages, 6.66 with 4
       l.stages = 3;
-      if (big_slab) l.stages = (uint32_t)std::max<uint64_t>(3, std::min<uint64_t>((uint64_t)env_int("TTV_B200_STREAM_STAGES", 3), (227 * 1024 - b_bytes16 - 64) / l.stage_bytes));
+      l.stages = (uint32_t)std::max<uint64_t>(3, std::min<uint64_t>(std::min<uint64_t>(5, (uint64_t)env_int("TTV_B200_STREAM_STAGES", 3)), (227 * 1024 - b_bytes16 - 64) / l.stage_bytes));
       l.smem_bytes = (uint64_t)l.stages * l.stage_bytes + b_bytes16 + (uint64_t)l.stages * 8;
       if (l.smem_bytes > 227 * 1024) return TTV_B200_ERR_OPTS;                          // (excluded by `eligible`)
       const uint64_t per_sm = l.smem_bytes + 1024 <= (227 * 1024) / 2 ? 2 : 1;        // CTAs of this size an SM can hold
