@@ -177,12 +177,14 @@ ttv_col_exchange_kernel(const ExchangeParams E)
   const ScatterParams& P = E.S;
   scatter_tiles<T, V>(P, reinterpret_cast<T*>(smem_raw));
 
-  // 2: deliver.  Every thread orders its own peer stores before the CTA's arrival; the closing CTA orders all arrivals
-  // before the flags (fence - atomic ... atomic - fence).
+  // 2: deliver.  The CTA orders its peer stores before its arrival; the closing CTA orders all arrivals before the flags
+  // (fence - atomic ... atomic - fence).
   __shared__ unsigned long long s_arrival;
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) s_arrival = atomicAdd(E.counter, 1ull);
+  __syncthreads();                                                     // every thread's peer stores are issued ...
+  if (threadIdx.x == 0) {
+    __threadfence_system();                                            // ... and ordered, cumulatively, before the arrival (the
+    s_arrival = atomicAdd(E.counter, 1ull);                            // pattern of a grid-wide barrier: bar.sync, fence, atomic)
+  }
   __syncthreads();
   const unsigned long long arrival = s_arrival;                        // 0 .. gridDim.x - 1
   const unsigned long long R = min((unsigned long long)max(E.reducers, 1u), (unsigned long long)gridDim.x);
