@@ -158,3 +158,34 @@ print("binding ok")
 '''
     r = subprocess.run([sys.executable, "-c", check], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "binding ok" in r.stdout, r.stdout + r.stderr[-3000:]
+
+
+def test_residency_snippet_of_section_1a_compiles_and_runs(tmp_path):
+    """INTEGRATION.md section 1a: tensor::keep_on_device and device_tensor behind the two high-level interfaces -- the
+    program in the document, compiled against this repo's include/ and run (on a GPU box it must print the known answer
+    of example/interface1.cpp, without one the shim's 'no CPU fallback' error)"""
+    import ttv_b200
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    section = doc[doc.index("### 1a."):doc.index("## 2.")]
+    code = re.search(r"```cpp\n(.*?)```", section, flags=re.S).group(1)
+    assert "keep_on_device" in code and "device_tensor" in code
+    src = tmp_path / "residency.cpp"
+    src.write_text(code)
+    exe = tmp_path / "residency"
+    libdir = os.path.join(ROOT, "ttv_b200")
+    env = dict(os.environ); env.pop("CC", None); env.pop("CXX", None)
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", f"-I{os.path.join(ROOT, 'include')}", str(src), "-o", str(exe),
+                        f"-L{libdir}", "-lttv_b200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr[-4000:]
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    if ttv_b200.device_count() > 0:
+        assert "C1: 15 18 21 24 51 54 57 60" in r.stdout and "C2[0] 15 C3[0] 6 C4[0] 6" in r.stdout, r.stdout
+    else:
+        assert "EXC: Error in ttv_b200: CUDA failure (no CPU fallback exists)." in r.stdout, r.stdout
+
+
+@pytest.mark.gpu
+def test_residency_snippet_of_section_1a_on_the_gpu(tmp_path):
+    """the same program on a B200: it must print example/interface1.cpp's known answer through all four routes"""
+    test_residency_snippet_of_section_1a_compiles_and_runs(tmp_path)

@@ -105,6 +105,7 @@ template<class T, int V, int IM, int NU, int KU>
 __global__ void __launch_bounds__(256, 3)
 ttv_colr_kernel(const TileParams P)
 {
+  pdl_prologue();
   static_assert(V > 1 && V <= 4 && (V & (V - 1)) == 0 && KU % V == 0, "COLR walks whole phase periods");
   const T* __restrict__ A = static_cast<const T*>(P.a);
   const T* __restrict__ B = static_cast<const T*>(P.b);

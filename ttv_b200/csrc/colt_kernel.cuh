@@ -55,6 +55,7 @@ template<class T, int V>
 __global__ void __launch_bounds__(kColtThreads, 1)
 ttv_colt_kernel(const __grid_constant__ CUtensorMap map, const ColtParams P)
 {
+  pdl_prologue();
   static_assert(sizeof(T) * V == 16, "a consumer lane owns 16 bytes of a row");
   extern __shared__ __align__(128) unsigned char colt_smem[];
   const uint32_t stage_bytes = P.wt * P.kt * 4u;

@@ -55,6 +55,7 @@ template<class T, int V, int NU, int KU>
 __global__ void __launch_bounds__(256, min_ctas<NU, KU>())
 ttv_colx_kernel(const TileParams P)
 {
+  pdl_prologue();
   static_assert(V > 1 && (V & (V - 1)) == 0, "COLX is for vector loads");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sb  = reinterpret_cast<T*>(smem_raw);          // [kb]
@@ -181,6 +182,7 @@ template<class T, int V, int NU, int KU>
 __global__ void __launch_bounds__(256, TTVB_COLW_CTAS)
 ttv_colw_kernel(const TileParams P)
 {
+  pdl_prologue();
   static_assert(V > 1 && (V & (V - 1)) == 0 && KU % V == 0, "COLW walks whole phase periods");
   const T* __restrict__ A = static_cast<const T*>(P.a);
   const T* __restrict__ B = static_cast<const T*>(P.b);

@@ -36,6 +36,7 @@ template<class T, int V>
 __global__ void __launch_bounds__(256, 3)
 ttv_dotf_kernel(const DotfParams P)
 {
+  pdl_prologue();
   constexpr int KU = 8;                                  // vector loads in flight per lane; 32 * KU vectors per chunk
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sbv  = reinterpret_cast<T*>(smem_raw);              // [nq]: b

@@ -136,6 +136,7 @@ template<class T, int V, int NU, int KU, bool BG = false>
 __global__ void __launch_bounds__(256, col_min_ctas<T, V, NU, KU>())
 ttv_col_kernel(const TileParams P)
 {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sb  = reinterpret_cast<T*>(smem_raw);          // [kb]   (nothing when b is read directly)
   T* red = sb + (BG ? 0u : P.kb);                   // [threads][NU*V]
@@ -383,6 +384,7 @@ template<class T, int V, int NU, int KU, bool BG = false>
 __global__ void __launch_bounds__(256, col_min_ctas<T, V, NU, KU>())
 ttv_dot_kernel(const TileParams P)
 {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sb  = reinterpret_cast<T*>(smem_raw);          // [kb]   (nothing when b is read directly)
   T* red = sb + (BG ? 0u : P.kb);                   // [threads][NU]
@@ -463,6 +465,7 @@ template<class T, int V, int NU, int KU>
 __global__ void __launch_bounds__(256, min_ctas<NU, KU>())
 ttv_dot_peel_kernel(const TileParams P)
 {
+  pdl_prologue();
   static_assert(V > 1, "peeling needs a vector");
   constexpr int HT = 2;                              // head/tail rounds: HT * ty lanes must cover 2V-2 elements
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -557,6 +560,7 @@ template<class T>
 __global__ void __launch_bounds__(256)
 ttv_reduce_kernel(const T* __restrict__ ws, T* __restrict__ c, uint64_t n, uint32_t ksplit, uint32_t accumulate, uint64_t stride)
 {
+  pdl_prologue();
   // ws is [ksplit][stride], the first n entries of every row are summed (stride == n for the split-n_q workspace)
   for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (uint64_t)gridDim.x * blockDim.x) {
     T s = accumulate ? c[j] : Num<T>::zero();
@@ -580,6 +584,7 @@ template<class T>
 __global__ void __launch_bounds__(256)
 ttv_fill_kernel(T* __restrict__ x, uint64_t first, uint64_t count, uint64_t seed)
 {
+  pdl_prologue();
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
     x[i] = synth<T>(seed, first + i);
 }

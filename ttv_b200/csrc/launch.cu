@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <atomic>
+#include <utility>
 
 namespace ttvb {
 
@@ -44,6 +45,34 @@ TTVB_DECLARE(0) TTVB_DECLARE(1) TTVB_DECLARE(2) TTVB_DECLARE(3) TTVB_DECLARE(4) 
 #undef TTVB_DECLARE
 
 void count_launch();
+
+// Every kernel goes out through cudaLaunchKernelEx.  With TTV_B200_PDL (default on) the launch carries the
+// programmatic-stream-serialization attribute: the kernel may start placing CTAs while the tail of the previous kernel of
+// the stream is still running and waits inside (pdl_prologue, numeric.cuh) until that kernel has completed -- stream
+// semantics unchanged, launch latency and ramp hidden (an 80 us product on a 512 MiB tensor: ~4 % of its time).
+static inline bool pdl_enabled()
+{
+  const char* e = std::getenv("TTV_B200_PDL");
+  return (e && *e) ? std::atoi(e) != 0 : true;
+}
+
+template<class... KArgs, class... Args>
+static inline cudaError_t launch_k(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, Args&&... args)
+{
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1u : 0u;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+  count_launch();
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
 
 #ifndef TTVB_DTYPE
 // ===================================================================================================================
@@ -262,9 +291,7 @@ static cudaError_t launch_tile(Kernel kern, const TileParams& P, const Launch& l
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes);
     if (e != cudaSuccess) return e;
   }
-  kern<<<(unsigned)l.ctas, l.threads, l.smem_bytes, stream>>>(P);
-  count_launch();
-  return cudaGetLastError();
+  return launch_k(kern, (unsigned)l.ctas, l.threads, l.smem_bytes, stream, P);
 }
 
 // (nu, ku) pairs that are instantiated: nu*ku = 8 loads in flight with 16-byte vectors, 16 with narrower ones
@@ -390,10 +417,8 @@ cudaError_t TTVB_CAT(reduce_dtype_, TTVB_DTYPE)(const void* ws, void* c, uint64_
                                                  uint64_t stride, int sm_count, cudaStream_t stream)
 {
   const uint64_t blocks = std::min<uint64_t>((n + 255) / 256, (uint64_t)sm_count * 32);
-  ttv_reduce_kernel<elem_t><<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const elem_t*>(ws), static_cast<elem_t*>(c), n,
-                                                                  ksplit, accumulate ? 1u : 0u, stride);
-  count_launch();
-  return cudaGetLastError();
+  return launch_k(ttv_reduce_kernel<elem_t>, (unsigned)blocks, 256u, 0, stream, static_cast<const elem_t*>(ws), static_cast<elem_t*>(c), n,
+                  ksplit, accumulate ? 1u : 0u, stride);
 }
 
 cudaError_t TTVB_CAT(stream_dtype_, TTVB_DTYPE)(const StreamParams& S, const Launch& l, cudaStream_t stream)
@@ -411,9 +436,7 @@ cudaError_t TTVB_CAT(stream_dtype_, TTVB_DTYPE)(const StreamParams& S, const Lau
   else if (l.stages != 3) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes);
   if (e != cudaSuccess) return e;
-  kern<<<(unsigned)l.ctas, l.threads, l.smem_bytes, stream>>>(S);
-  count_launch();
-  return cudaGetLastError();
+  return launch_k(kern, (unsigned)l.ctas, l.threads, l.smem_bytes, stream, S);
 }
 
 cudaError_t TTVB_CAT(dotf_dtype_, TTVB_DTYPE)(const DotfParams& D, const Launch& l, cudaStream_t stream)
@@ -423,18 +446,14 @@ cudaError_t TTVB_CAT(dotf_dtype_, TTVB_DTYPE)(const DotfParams& D, const Launch&
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes);
     if (e != cudaSuccess) return e;
   }
-  kern<<<(unsigned)l.ctas, l.threads, l.smem_bytes, stream>>>(D);
-  count_launch();
-  return cudaGetLastError();
+  return launch_k(kern, (unsigned)l.ctas, l.threads, l.smem_bytes, stream, D);
 }
 
 template<int V>
 static cudaError_t launch_scatter_vec(const ScatterParams& S, uint64_t ctas, uint64_t smem, cudaStream_t stream)
 {
   if constexpr (V <= kVmax) {
-    ttv_col_scatter_kernel<elem_t, V><<<(unsigned)ctas, 256, smem, stream>>>(S);
-    count_launch();
-    return cudaGetLastError();
+    return launch_k(ttv_col_scatter_kernel<elem_t, V>, (unsigned)ctas, 256u, smem, stream, S);
   } else {
     return cudaErrorInvalidValue;
   }
@@ -457,10 +476,14 @@ static cudaError_t launch_exchange_vec(const ExchangeParams& E, uint32_t max_cta
     // GPUs, one per SM unless capped -- far fewer than the device holds at once, so the rest always finds room
     ExchangeParams E2 = E;
     E2.reducers = max_ctas ? max_ctas : (uint32_t)sm_count;
-    const uint64_t ctas = std::max<uint64_t>(1, std::min<uint64_t>(std::max<uint64_t>(E.S.tiles, 1), (uint64_t)sm_count * 64));
-    kern<<<(unsigned)ctas, 256, smem, stream>>>(E2);
-    count_launch();
-    return cudaGetLastError();
+    // Every CTA ends with a system-scope fence that waits for its peer stores to be acknowledged over NVLink (a few
+    // microseconds): with one tile per CTA (the 64-per-SM grid of the plain kernels) that is 3-5 % of a CTA's life
+    // (measured on 8 GPUs: 1.245 ms against 1.188 for the three-launch form).  Twelve CTAs per SM -- four rounds of the
+    // three resident ones, several tiles each -- pay the fence once per several tiles and still end as evenly.
+    const char* gm = std::getenv("TTV_B200_EXCHANGE_GRID_MULT");
+    const uint64_t mult = (gm && *gm) ? (uint64_t)std::max(1, std::atoi(gm)) : 12;
+    const uint64_t ctas = std::max<uint64_t>(1, std::min<uint64_t>(std::max<uint64_t>(E.S.tiles, 1), (uint64_t)sm_count * mult));
+    return launch_k(kern, (unsigned)ctas, 256u, smem, stream, E2);
   } else {
     return cudaErrorInvalidValue;
   }
@@ -489,9 +512,7 @@ static cudaError_t launch_strided_vec(StridedParams S, int sm_count, cudaStream_
     S.n0p = (S.n[0] / (uint64_t)V + 31) / 32 * 32;      // whole warps per row
     const uint64_t lanes = (S.total / S.n[0]) * S.n0p;
     const uint64_t blocks = std::max<uint64_t>(1, std::min<uint64_t>((lanes + 255) / 256, (uint64_t)sm_count * 32));
-    ttv_strided_vec_kernel<elem_t, V><<<(unsigned)blocks, 256, 0, stream>>>(S);
-    count_launch();
-    return cudaGetLastError();
+    return launch_k(ttv_strided_vec_kernel<elem_t, V>, (unsigned)blocks, 256u, 0, stream, S);
   } else {
     return cudaErrorInvalidValue;
   }
@@ -506,9 +527,7 @@ static cudaError_t launch_strided_dot(const StridedParams& S, int sm_count, cuda
   while (G < 32 && (uint64_t)G * strided_dot_ku<elem_t, V>() < kv) G *= 2;
   const uint64_t fibers_per_cta = 256 / G;
   const uint64_t blocks = std::max<uint64_t>(1, std::min<uint64_t>((S.total + fibers_per_cta - 1) / fibers_per_cta, (uint64_t)sm_count * 32));
-  ttv_strided_dot_kernel<elem_t, V><<<(unsigned)blocks, 256, 0, stream>>>(S, G);
-  count_launch();
-  return cudaGetLastError();
+  return launch_k(ttv_strided_dot_kernel<elem_t, V>, (unsigned)blocks, 256u, 0, stream, S, G);
 }
 
 cudaError_t TTVB_CAT(strided_dtype_, TTVB_DTYPE)(const StridedParams& S, int sm_count, cudaStream_t stream)
@@ -540,9 +559,7 @@ cudaError_t TTVB_CAT(strided_dtype_, TTVB_DTYPE)(const StridedParams& S, int sm_
     if (forced == 2 && kVmax >= 4 && align % 2 == 0) return launch_strided_vec<2>(S, sm_count, stream);
   }
   const uint64_t blocks = std::max<uint64_t>(1, std::min<uint64_t>((S.total + 255) / 256, (uint64_t)sm_count * 32));
-  ttv_strided_kernel<elem_t><<<(unsigned)blocks, 256, 0, stream>>>(S);
-  count_launch();
-  return cudaGetLastError();
+  return launch_k(ttv_strided_kernel<elem_t>, (unsigned)blocks, 256u, 0, stream, S);
 }
 
 cudaError_t TTVB_CAT(colt_dtype_, TTVB_DTYPE)(const CUtensorMap& map, const ColtParams& P, const Launch& l, cudaStream_t stream)
@@ -551,17 +568,13 @@ cudaError_t TTVB_CAT(colt_dtype_, TTVB_DTYPE)(const CUtensorMap& map, const Colt
   auto kern = ttv_colt_kernel<elem_t, V>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes);
   if (e != cudaSuccess) return e;
-  kern<<<(unsigned)l.ctas, kColtThreads, l.smem_bytes, stream>>>(map, P);
-  count_launch();
-  return cudaGetLastError();
+  return launch_k(kern, (unsigned)l.ctas, (unsigned)kColtThreads, l.smem_bytes, stream, map, P);
 }
 
 cudaError_t TTVB_CAT(fill_dtype_, TTVB_DTYPE)(void* x, uint64_t first, uint64_t count, uint64_t seed, int sm_count, cudaStream_t stream)
 {
   const unsigned blocks = (unsigned)std::min<uint64_t>((count + 255) / 256, (uint64_t)sm_count * 32);
-  ttv_fill_kernel<elem_t><<<blocks, 256, 0, stream>>>(static_cast<elem_t*>(x), first, count, seed);
-  count_launch();
-  return cudaGetLastError();
+  return launch_k(ttv_fill_kernel<elem_t>, blocks, 256u, 0, stream, static_cast<elem_t*>(x), first, count, seed);
 }
 #endif
 

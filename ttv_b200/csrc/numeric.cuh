@@ -100,6 +100,19 @@ __device__ __forceinline__ Vec<T, V> load_stream(const T* p) {
   return v;
 }
 
+// ---- programmatic dependent launch (sm_90+) -------------------------------------------------------------------------
+// Every kernel of this library starts with pdl_prologue(): it lets the NEXT kernel of the stream start placing its CTAs as
+// soon as all CTAs of this one have started (griddepcontrol.launch_dependents), and it waits until the PREVIOUS kernel of
+// the stream has completed and flushed its memory before touching anything (griddepcontrol.wait) -- so the semantics of a
+// stream are unchanged (a product may read what the product before it wrote, as in a ttvs chain), but the launch latency
+// and the CTA ramp of a kernel overlap the tail of the one before it.  Both instructions are no-ops for kernels launched
+// without the programmatic-serialization attribute (launch.cu, TTV_B200_PDL).
+__device__ __forceinline__ void pdl_prologue()
+{
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ---- synthetic data: identical to oracle/ttv_oracle.c ttv_oracle_fill -------------------------------
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   uint64_t z = x + 0x9E3779B97F4A7C15ull;

@@ -91,6 +91,7 @@ template<class T, int V>
 __global__ void __launch_bounds__(256, 3)
 ttv_col_scatter_kernel(const ScatterParams P)
 {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   scatter_tiles<T, V>(P, reinterpret_cast<T*>(smem_raw));            // [kb]
 }
@@ -173,6 +174,7 @@ template<class T, int V>
 __global__ void __launch_bounds__(256, 3)
 ttv_col_exchange_kernel(const ExchangeParams E)
 {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const ScatterParams& P = E.S;
   scatter_tiles<T, V>(P, reinterpret_cast<T*>(smem_raw));

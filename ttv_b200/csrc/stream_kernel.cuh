@@ -149,6 +149,7 @@ template<class T, int NS, int UO, bool SKEW = false, int MAXT = 256>
 __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 2 : 1)
 ttv_stream_kernel(const StreamParams P)
 {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];   // the runtime places dynamic shared memory at a 1024-byte aligned offset when it is the only shared allocation
   unsigned char* stages = smem_raw;                                                  // [NS][stage_bytes]
   T*        sb   = reinterpret_cast<T*>(smem_raw + (size_t)NS * P.stage_bytes);      // [nq]

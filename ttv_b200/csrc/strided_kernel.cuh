@@ -59,6 +59,7 @@ template<class T>
 __global__ void __launch_bounds__(256)
 ttv_strided_kernel(const StridedParams P)
 {
+  pdl_prologue();
   const T* __restrict__ A = static_cast<const T*>(P.a);
   const T* __restrict__ B = static_cast<const T*>(P.b);
   T* __restrict__       C = static_cast<T*>(P.c);
@@ -101,6 +102,7 @@ template<class T, int V>
 __global__ void __launch_bounds__(256)
 ttv_strided_vec_kernel(const StridedParams P)
 {
+  pdl_prologue();
   const T* __restrict__ A = static_cast<const T*>(P.a);
   const T* __restrict__ B = static_cast<const T*>(P.b);
   T* __restrict__       C = static_cast<T*>(P.c);
@@ -177,6 +179,7 @@ template<class T, int V>
 __global__ void __launch_bounds__(256)
 ttv_strided_dot_kernel(const StridedParams P, const uint32_t G)
 {
+  pdl_prologue();
   const T* __restrict__ A = static_cast<const T*>(P.a);
   const T* __restrict__ B = static_cast<const T*>(P.b);
   T* __restrict__       C = static_cast<T*>(P.c);
