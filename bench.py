@@ -437,7 +437,9 @@ def run_own_arm(args):
         cfg5 = cfg5_leg(torch, dist, ttv_b200, rank, world, dev, args)
     sweep = None
     if world == 1 and not args.no_sweep:
-        sweep = sweep_leg(torch, ttv_b200, args)
+        with ClockSampler(local) as sweep_clocks:
+            sweep = sweep_leg(torch, ttv_b200, args)
+        sweep["clocks"] = sweep_clocks.summary()
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
