@@ -672,39 +672,19 @@ def local_product(ttv_b200, q, a, shard, pia, b, c):
                           ttv_b200.generate_strides(nc, pic), pic, flags=2)
 
 
-def synth_f32(seed: int, idx):
-    """the synthetic generator of the fill kernel (csrc/numeric.cuh: splitmix64 of seed ^ j, top 53 bits mapped to
-    [-1, 1)), restated in numpy for the sampled self-check below -- no code under oracle/ runs on this arm outside the
-    cpu_baseline leg"""
-    with np.errstate(over="ignore"):
-        z = (np.asarray(idx, dtype=np.uint64) ^ np.uint64(seed)) + np.uint64(0x9E3779B97F4A7C15)
-        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-        z = z ^ (z >> np.uint64(31))
-    return ((z >> np.uint64(11)).astype(np.float64) * (2.0 / 9007199254740992.0) - 1.0).astype(np.float32)
-
-
 def verify_sample(torch, cs, shards, na_global, bs, rank, world):
-    """64 sampled outputs per product against a host long-double dot on regenerated data"""
+    """sampled outputs of every product against a host long-double dot on regenerated fibers (ttv_b200/selfcheck.py: the
+    fill generator restated in numpy -- no code under oracle/ runs on this arm outside the cpu_baseline leg)"""
+    from ttv_b200 import selfcheck
     rng = np.random.default_rng(1234 + rank)
     for q in range(1, ORDER + 1):
         sh = shards[q]
         if (sh.kind == "nq" and (world > 1 and rank != 0)) or sh.c_count == 0:
             continue
-        c = cs[q]
-        inner = int(np.prod(na_global[: q - 1], dtype=object)) if q > 1 else 1
-        nq = na_global[q - 1]
-        bh = bs[q].cpu().numpy().astype(np.longdouble)
-        for j in rng.integers(0, sh.c_count, 64):
-            jg = int(j) + sh.c_offset                       # index into the global C
-            o, i = divmod(jg, inner)
-            idx = (o * nq + np.arange(nq)) * inner + i      # global element indices of the fiber
-            fiber = synth_f32(SEED_A, idx).astype(np.longdouble)
-            want = float(np.dot(fiber, bh))
-            tol = 2 * nq * (np.finfo(np.float32).eps / 2) * float(np.dot(np.abs(fiber), np.abs(bh))) + 1e-30
-            got = float(c[int(j)].item())
-            if not abs(got - want) <= tol:
-                raise SystemExit(f"bench.py: parity check failed for q={q}, output {jg}: got {got}, want {want}, tol {tol}")
+        n, bad, worst = selfcheck.check_product(cs[q], DTYPE, na_global, [1, 2, 3, 4], q, SEED_A, bs[q], samples=64, rng=rng, c_first=sh.c_offset)
+        if bad:
+            raise SystemExit(f"bench.py: parity check failed for q={q} on rank {rank}: {bad} of {n} sampled outputs outside the tolerance "
+                             f"(worst |err| / tol = {worst:.3g})")
 
 
 def measure_e2e(torch, dist, ttv_b200, args, a, bs, cs, shards, na_global, pia, rank, world, dev, total_bytes, exchange=None):
