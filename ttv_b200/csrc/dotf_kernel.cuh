@@ -32,8 +32,11 @@ struct DotfParams {
   uint32_t lpf;             // lanes per fiber in the summation (power of two, lpf * min(fw, 32) <= 32)
 };
 
-template<class T, int V>
-__global__ void __launch_bounds__(256, 3)
+// BREG: the KU vectors of b a lane needs are the same in every chunk (see above), so they can live in registers instead of
+// being fetched from shared memory for every chunk -- 32 more registers (two CTAs per SM instead of three) against a fifth
+// fewer shared-memory wavefronts in a kernel whose load/store pipe is the busiest unit (ncu: l1tex 93 % on complex<double>).
+template<class T, int V, bool BREG = false>
+__global__ void __launch_bounds__(256, BREG ? 2 : 3)
 ttv_dotf_kernel(const DotfParams P)
 {
   pdl_prologue();
@@ -66,6 +69,12 @@ ttv_dotf_kernel(const DotfParams P)
     }
   }
 
+  Vec<T, V> breg[BREG ? KU : 1];
+  if constexpr (BREG) {
+#pragma unroll
+    for (int s = 0; s < KU; ++s) breg[s] = *reinterpret_cast<const Vec<T, V>*>(sbv + pos[s] * V);
+  }
+
   const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
   uint64_t chunk = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
 
@@ -90,7 +99,9 @@ ttv_dotf_kernel(const DotfParams P)
     // one partial per vector
 #pragma unroll
     for (int s = 0; s < KU; ++s) {
-      const Vec<T, V> bv = *reinterpret_cast<const Vec<T, V>*>(sbv + pos[s] * V);
+      Vec<T, V> bv;
+      if constexpr (BREG) bv = breg[s];
+      else bv = *reinterpret_cast<const Vec<T, V>*>(sbv + pos[s] * V);
       T p = Num<T>::zero();
 #pragma unroll
       for (int e = 0; e < V; ++e) p = Num<T>::madd(v[s].e[e], bv.e[e], p);

@@ -441,7 +441,12 @@ cudaError_t TTVB_CAT(stream_dtype_, TTVB_DTYPE)(const StreamParams& S, const Lau
 
 cudaError_t TTVB_CAT(dotf_dtype_, TTVB_DTYPE)(const DotfParams& D, const Launch& l, cudaStream_t stream)
 {
-  auto kern = ttv_dotf_kernel<elem_t, kVmax>;
+  // b in registers (2 CTAs per SM) instead of shared memory (3 CTAs): measured on every DOTF shape of the named set
+  // (profiles/r02_dotf_breg.txt): +5 % on fibers of 25 complex<double> (6 292 -> 6 618 GB/s, the slowest DOTF shape),
+  // +2 % on 48, -1..-3 % on 24 / 40 and on the 8-byte types, +-0.5 % on 4-byte elements.  Rule: 16-byte elements, odd length.
+  const char* br = std::getenv("TTV_B200_DOTF_BREG");
+  const bool breg = (br && *br) ? std::atoi(br) != 0 : (sizeof(elem_t) == 16 && (D.nv & 1u));
+  auto kern = breg ? ttv_dotf_kernel<elem_t, kVmax, true> : ttv_dotf_kernel<elem_t, kVmax, false>;
   if (l.smem_bytes > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes);
     if (e != cudaSuccess) return e;
