@@ -144,3 +144,37 @@ def test_copy_and_memory_helpers_round_trip():
     assert lib.ttv_b200_copy(back.ctypes.data_as(C.c_void_p), dev2, n, None) == 0
     assert np.array_equal(back, src)
     assert lib.ttv_b200_device_free(dev) == 0 and lib.ttv_b200_device_free(dev2) == 0
+
+
+def test_resident_and_devices_with_padded_strides(oracle, monkeypatch):
+    """a tensor with padded leading dimensions (TTV_B200_FLAG_HONOR_STRIDES) through the resident twin and through a device
+    list: the whole span is what lives on the device / what a single device gets (strided views are not cut)"""
+    monkeypatch.setenv("TTV_B200_MULTI_MIN_MB", "0")
+    rng = np.random.default_rng(12)
+    na, pia = (10, 7, 9), (1, 2, 3)
+    wa = [1, 12, 12 * 8]                                             # rows padded 10 -> 12, slabs 7 -> 8 rows
+    span = 1 + sum((n - 1) * w for n, w in zip(na, wa))
+    buf = np.full(span, 77, np.float64)
+    x = rng.integers(-8, 9, na).astype(np.float64)
+    idx = np.add.outer(np.add.outer(np.arange(10) * wa[0], np.arange(7) * wa[1]), np.arange(9) * wa[2])
+    buf[idx] = x
+    packed = np.ascontiguousarray(x.transpose(2, 1, 0)).reshape(-1)   # the same tensor, packed first-order
+    res = ttv_b200.Resident()
+    for q in (1, 2, 3):
+        b = rng.integers(-8, 9, na[q - 1]).astype(np.float64)
+        want = oracle.ttv(q, packed, na, pia, b)
+        nc = ttv_b200.generate_output_shape(na, q); pic = ttv_b200.generate_output_layout(pia, q)
+        for call in (lambda *a, **k: res.ttv_lowlevel(*a, **k), lambda *a, **k: ttv_b200.ttv_lowlevel_devices([0, 0], *a, **k)):
+            c = np.full(want.size, 5, np.float64)
+            call(q, 3, buf, list(na), wa, list(pia), b, [len(b)], c, nc, ttv_b200.generate_strides(nc, pic), pic, flags=8)
+            assert np.array_equal(c, want), (q, call)
+    assert res.valid
+
+
+def test_copy_between_host_buffers_uses_the_copy_threads():
+    lib = ttv_b200._lib.load()
+    n = (40 << 20) + 7
+    src = np.random.default_rng(2).integers(0, 255, n).astype(np.uint8)
+    dst = np.zeros(n, np.uint8)
+    assert lib.ttv_b200_copy(dst.ctypes.data_as(C.c_void_p), src.ctypes.data_as(C.c_void_p), n, None) == 0
+    assert np.array_equal(dst, src)
