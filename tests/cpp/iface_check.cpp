@@ -5,9 +5,10 @@
 // (tensor::keep_on_device, device_tensor).  Test infrastructure: reads one case written by tests/test_cpp_interfaces_gpu.py
 // (element type, order, q, shape, layout, A, b), writes every result back; the Python side compares with the oracle.
 //
-//   iface_check <case.bin> <out.bin>
-// case.bin: int64 dtype, p, q, shape[p], layout[p]; then A (N elements), b (n_q elements), raw.
-// out.bin : 6 result arrays of N / n_q elements each, in the order of run() below.
+//   iface_check <cases.bin> <out.bin>
+// cases.bin: any number of cases back to back; a case = int64 dtype, p, q, shape[p], layout[p]; then A (N elements),
+//            b (n_q elements), raw.
+// out.bin  : per case 6 result arrays of N / n_q elements each, in the order of run() below.
 #include <tlib/ttv.h>
 
 #include <complex>
@@ -71,21 +72,25 @@ int main(int argc, char** argv)
     std::FILE* in = std::fopen(argv[1], "rb");
     std::FILE* out = std::fopen(argv[2], "wb");
     if (!in || !out) throw std::runtime_error("cannot open files");
-    std::int64_t head[3];
-    read_exact(in, head, sizeof head);
-    std::size_t const p = static_cast<std::size_t>(head[1]), q = static_cast<std::size_t>(head[2]);
-    std::vector<std::int64_t> raw(2 * p);
-    read_exact(in, raw.data(), raw.size() * sizeof(std::int64_t));
-    std::vector<std::size_t> n(raw.begin(), raw.begin() + p), pi(raw.begin() + p, raw.end());
-    int rc = 1;
-    switch (head[0]) {
-      case 0: rc = run<float>(in, out, p, q, n, pi); break;
-      case 1: rc = run<double>(in, out, p, q, n, pi); break;
-      case 2: rc = run<std::complex<float>>(in, out, p, q, n, pi); break;
-      case 3: rc = run<std::complex<double>>(in, out, p, q, n, pi); break;
-      case 4: rc = run<std::int32_t>(in, out, p, q, n, pi); break;
-      case 5: rc = run<std::int64_t>(in, out, p, q, n, pi); break;
-      default: throw std::runtime_error("unknown element type");
+    int rc = 0;
+    for (;;) {
+      std::int64_t head[3];
+      std::size_t const got = std::fread(head, 1, sizeof head, in);
+      if (got == 0) break;                                           // end of the cases
+      if (got != sizeof head) throw std::runtime_error("short read");
+      std::size_t const p = static_cast<std::size_t>(head[1]), q = static_cast<std::size_t>(head[2]);
+      std::vector<std::int64_t> raw(2 * p);
+      read_exact(in, raw.data(), raw.size() * sizeof(std::int64_t));
+      std::vector<std::size_t> n(raw.begin(), raw.begin() + p), pi(raw.begin() + p, raw.end());
+      switch (head[0]) {
+        case 0: rc |= run<float>(in, out, p, q, n, pi); break;
+        case 1: rc |= run<double>(in, out, p, q, n, pi); break;
+        case 2: rc |= run<std::complex<float>>(in, out, p, q, n, pi); break;
+        case 3: rc |= run<std::complex<double>>(in, out, p, q, n, pi); break;
+        case 4: rc |= run<std::int32_t>(in, out, p, q, n, pi); break;
+        case 5: rc |= run<std::int64_t>(in, out, p, q, n, pi); break;
+        default: throw std::runtime_error("unknown element type");
+      }
     }
     std::fclose(in);
     std::fclose(out);

@@ -51,19 +51,30 @@ def test_reference_examples_run_unmodified_on_the_gpu(which):
         assert values == [15, 18, 21, 24, 51, 54, 57, 60], line
 
 
-def run_iface(tmp_path, q, a, na, pia, b):
-    """-> the six results of tests/cpp/iface_check.cpp for this case"""
-    case, out = tmp_path / "case.bin", tmp_path / "out.bin"
+def run_iface_many(tmp_path, cases):
+    """cases: [(q, a, na, pia, b), ...] -> per case the six results of tests/cpp/iface_check.cpp (ONE process for all of them:
+    a CUDA context per case would dominate the test time)"""
+    case, out = tmp_path / "cases.bin", tmp_path / "out.bin"
     with open(case, "wb") as f:
-        np.array([CODES[a.dtype], len(na), q] + list(na) + list(pia), dtype=np.int64).tofile(f)
-        np.ascontiguousarray(a).tofile(f)
-        np.ascontiguousarray(b).tofile(f)
-    r = subprocess.run([_binary("iface_check", False), str(case), str(out)], capture_output=True, text=True, timeout=300)
+        for q, a, na, pia, b in cases:
+            np.array([CODES[a.dtype], len(na), q] + list(na) + list(pia), dtype=np.int64).tofile(f)
+            np.ascontiguousarray(a).tofile(f)
+            np.ascontiguousarray(b).tofile(f)
+    r = subprocess.run([_binary("iface_check", False), str(case), str(out)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    n_out = a.size // na[q - 1]
-    res = np.fromfile(out, dtype=a.dtype)
-    assert res.size == 6 * n_out
-    return res.reshape(6, n_out)
+    raw = open(out, "rb").read()
+    results, off = [], 0
+    for q, a, na, pia, b in cases:
+        n_out = a.size // na[q - 1]
+        nbytes = 6 * n_out * a.dtype.itemsize
+        results.append(np.frombuffer(raw, dtype=a.dtype, count=6 * n_out, offset=off).reshape(6, n_out))
+        off += nbytes
+    assert off == len(raw)
+    return results
+
+
+def run_iface(tmp_path, q, a, na, pia, b):
+    return run_iface_many(tmp_path, [(q, a, na, pia, b)])[0]
 
 
 CASES = [((7, 5, 6, 4), (2, 4, 1, 3)), ((6, 9, 5), (3, 1, 2)), ((4, 3, 5, 2, 6), (5, 2, 4, 1, 3)), ((8, 11, 7, 5), (4, 3, 2, 1)),
@@ -73,27 +84,31 @@ CASES = [((7, 5, 6, 4), (2, 4, 1, 3)), ((6, 9, 5), (3, 1, 2)), ((4, 3, 5, 2, 6),
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.complex128, np.int32])
 def test_operator_and_tensor_level_interfaces_match_the_oracle(oracle, tmp_path, dtype):
     rng = np.random.default_rng(2026)
+    cases = []
     for na, pia in CASES:
         for q in range(1, len(na) + 1):
             a, b = random_case(rng, na, q, dtype)
-            want = oracle.ttv(q, a, na, pia, b)
-            got = run_iface(tmp_path, q, a, na, pia, b)
-            for i in range(5):
-                assert np.array_equal(got[i], want), (na, pia, q, dtype, "variant", i)
-            a2 = a.copy(); a2[0] += 1                               # what iface_check did through A.begin()
-            assert np.array_equal(got[5], oracle.ttv(q, a2, na, pia, b)), (na, pia, q, dtype, "after mutation")
+            cases.append((q, a, na, pia, b))
+    for (q, a, na, pia, b), got in zip(cases, run_iface_many(tmp_path, cases)):
+        want = oracle.ttv(q, a, na, pia, b)
+        for i in range(5):
+            assert np.array_equal(got[i], want), (na, pia, q, dtype, "variant", i)
+        a2 = a.copy(); a2[0] += 1                                   # what iface_check did through A.begin()
+        assert np.array_equal(got[5], oracle.ttv(q, a2, na, pia, b)), (na, pia, q, dtype, "after mutation")
 
 
 def test_interfaces_on_real_valued_data_within_the_stated_tolerance(oracle, tmp_path):
     rng = np.random.default_rng(7)
+    cases = []
     for dtype in (np.float32, np.complex128):
         for na, pia in CASES[:3]:
             for q in range(1, len(na) + 1):
                 a, b = real_case(rng, na, q, dtype)
-                ref, mag = oracle.naive(q, a, na, pia, b, want_abs=True)
-                got = run_iface(tmp_path, q, a, na, pia, b)
-                for i in range(5):
-                    assert_close(got[i], ref, mag, na[q - 1], dtype, what=f"{na} {pia} q={q} variant {i}")
+                cases.append((q, a, na, pia, b))
+    for (q, a, na, pia, b), got in zip(cases, run_iface_many(tmp_path, cases)):
+        ref, mag = oracle.naive(q, a, na, pia, b, want_abs=True)
+        for i in range(5):
+            assert_close(got[i], ref, mag, na[q - 1], a.dtype, what=f"{na} {pia} q={q} variant {i}")
 
 
 def test_interfaces_reproduce_the_reference_fixtures(oracle, tmp_path):
@@ -101,12 +116,13 @@ def test_interfaces_reproduce_the_reference_fixtures(oracle, tmp_path):
     g = np.load(GOLDEN, allow_pickle=False)
     n_cases = int(g["count"])
     done = 0
+    picked = []
     for i in range(0, n_cases, 6):                                   # every sixth case: all dtypes and orders come by
         na = [int(x) for x in g[f"na_{i}"]]; pia = [int(x) for x in g[f"pia_{i}"]]; q = int(g[f"q_{i}"])
-        a, b, c = g[f"a_{i}"], g[f"b_{i}"], g[f"c_{i}"]
-        if len(na) < 2:
-            continue
-        got = run_iface(tmp_path, q, a, na, pia, b)
+        if len(na) >= 2:
+            picked.append((i, q, g[f"a_{i}"], na, pia, g[f"b_{i}"]))
+    for (i, q, a, na, pia, b), got in zip(picked, run_iface_many(tmp_path, [x[1:] for x in picked])):
+        c = g[f"c_{i}"]
         for v in range(5):
             if bool(g[f"exact_{i}"]):
                 assert np.array_equal(got[v], c), (i, na, pia, q, a.dtype, v)
