@@ -2,7 +2,7 @@
 big-slab STREAM form, n_q split + direct b, 128-thread CTAs, the (1,16) deep batch, COLX / COLW, DOTF on 16-byte elements,
 the peeled DOT, fibers cut into pieces, ...).  Small shapes reach those kernel FAMILIES when forced, but not these exact
 plans; here every one of them runs on its BASELINE-sized tensor and sampled outputs are compared with a host long-double dot
-on regenerated fibers (ttv_b200/selfcheck.py; int32 bit-exact).  bench.py's sweep leg does the same for all 210 named
+on regenerated fibers (ttv_b200/selfcheck.py; int32 bit-exact).  bench.py's sweep leg does the same for all 236 named
 products; this is the subset that pins one product per chooser branch in the test suite.
 
 The reference's own grid only reaches extents {2,4,8}^p (test/src/gtest_tlib_ttv.cpp:192-425)."""
