@@ -324,6 +324,8 @@ def run_own_arm(args):
         barrier()
         launches = ttv_b200.launch_count() - launches0
         ms = e0.elapsed_time(e1)
+        if exchange is not None and exchange.single_kernel and exchange.timed_out():
+            raise SystemExit(f"bench.py: rank {rank}: the one-kernel exchange gave up waiting for another GPU inside the timed region")
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -946,3 +946,18 @@ def test_single_kernel_exchange_emulated_on_one_gpu(dtype, oracle, monkeypatch):
             torch.cuda.synchronize()
             assert all(int(s[2].item()) == 0 for s in scratch), "an emulated rank timed out waiting for the others"
             assert np.array_equal(got.cpu().numpy(), want), ((outer, nq, inner), world, dtype, rnd)
+
+
+@pytest.mark.parametrize("dtype", ALL_DTYPES)
+def test_split_nq_with_many_partitions_and_few_outputs(dtype, oracle):
+    """the second pass of the split-n_q variant has two forms: a thread per output (many outputs) and a CTA per output with a
+    shared-memory tree (ttv_reduce_wide_kernel: 64+ partitions, <= 8192 outputs -- what [1, 2^26, 4] of the asymmetric family
+    takes at full size).  Forced partition counts on both sides of the switch, accumulate, odd output counts."""
+    rng = np.random.default_rng(31)
+    for na, pia, q in [((4, 50000), (1, 2), 2), ((3, 40000, 5), (1, 2, 3), 2), ((7, 30011), (1, 2), 2), ((30011, 9), (2, 1), 1), ((1, 70000, 2), (1, 2, 3), 2)]:
+        a, b = random_case(rng, na, q, dtype)
+        want = oracle.ttv(q, a, na, pia, b)
+        for ks in (63, 64, 100, 777):
+            assert np.array_equal(run_lowlevel(q, a, na, pia, b, ksplit=ks), want), (na, pia, q, dtype, ks)
+        c0 = np.full(want.size, 3, dtype)
+        assert np.array_equal(run_lowlevel(q, a, na, pia, b, c0=c0, ksplit=200, flags=1), want + 3), (na, pia, q, dtype, "accumulate")

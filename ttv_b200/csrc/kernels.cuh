@@ -569,6 +569,30 @@ ttv_reduce_kernel(const T* __restrict__ ws, T* __restrict__ c, uint64_t n, uint3
   }
 }
 
+// The same pass when there are FEW outputs and MANY partitions (n_q in the hundreds of millions with a tiny inner extent:
+// [1, 2^26, 4] has four outputs and 1 184 partitions): one thread per output would walk its partitions alone, ~1 000
+// dependent steps, tens of microseconds next to a 150 us product.  Here a CTA owns an output, its threads take the partitions
+// p = t, t + 256, ... and a shared-memory tree adds the 256 partial sums -- a fixed order again, so still deterministic.
+template<class T>
+__global__ void __launch_bounds__(256)
+ttv_reduce_wide_kernel(const T* __restrict__ ws, T* __restrict__ c, uint64_t n, uint32_t ksplit, uint32_t accumulate, uint64_t stride)
+{
+  pdl_prologue();
+  __shared__ T part[256];
+  for (uint64_t j = blockIdx.x; j < n; j += gridDim.x) {
+    T s = Num<T>::zero();
+    for (uint32_t p = threadIdx.x; p < ksplit; p += 256) s = Num<T>::add(s, ws[(uint64_t)p * stride + j]);
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (uint32_t h = 128; h > 0; h >>= 1) {
+      if (threadIdx.x < h) part[threadIdx.x] = Num<T>::add(part[threadIdx.x], part[threadIdx.x + h]);
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) c[j] = accumulate ? Num<T>::add(c[j], part[0]) : part[0];
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // synthetic data on the device (same generator as oracle/ttv_oracle.c:ttv_oracle_fill)
 // ------------------------------------------------------------------------------------------------------------------

@@ -416,6 +416,11 @@ cudaError_t TTVB_CAT(tile_dtype_, TTVB_DTYPE)(const TileParams& P, const Launch&
 cudaError_t TTVB_CAT(reduce_dtype_, TTVB_DTYPE)(const void* ws, void* c, uint64_t n, uint32_t ksplit, bool accumulate,
                                                  uint64_t stride, int sm_count, cudaStream_t stream)
 {
+  if (ksplit >= 64 && n <= 8192) {       // few outputs, many partitions: a CTA per output (kernels.cuh)
+    const uint64_t wide_blocks = std::min<uint64_t>(n, (uint64_t)sm_count * 8);
+    return launch_k(ttv_reduce_wide_kernel<elem_t>, (unsigned)wide_blocks, 256u, 0, stream, static_cast<const elem_t*>(ws),
+                    static_cast<elem_t*>(c), n, ksplit, accumulate ? 1u : 0u, stride);
+  }
   const uint64_t blocks = std::min<uint64_t>((n + 255) / 256, (uint64_t)sm_count * 32);
   return launch_k(ttv_reduce_kernel<elem_t>, (unsigned)blocks, 256u, 0, stream, static_cast<const elem_t*>(ws), static_cast<elem_t*>(c), n,
                   ksplit, accumulate ? 1u : 0u, stride);
