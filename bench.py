@@ -225,10 +225,13 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": round(m["gbs"], 2), "unit": "GB/s", "n_gpus": args.gpus,
             "steps": m["steps_done"], "warmup": args.warmup, "ms_per_step": round(m["seconds_per_step"] * 1e3, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
-            "config": {"workload": workload_name(args.gpus), "timed_on": "host CPU cores",
+            "config": {"workload": workload_name(args.gpus), "layout": "first-order", "per_gpu_tensor_bytes": EXT ** 4 * ELEM,
+                       "timed_on": "host CPU cores",
                        # what this arm actually times: a rate (GB/s) on a bounded sample of the PER-GPU tensor, not the N x tensor
                        "sampled_shape": [EXT, EXT, EXT, last], "sampled_bytes_per_step": m["bytes_per_step"],
-                       "sample_is": "the whole per-GPU 256^4 tensor" if last == EXT else "a slab of the per-GPU 256^4 tensor along mode 4"},
+                       "sample_is": "the whole per-GPU 256^4 tensor" if last == EXT else "a slab of the per-GPU 256^4 tensor along mode 4",
+                       "l2": "inputs are larger than the CPU's caches; no flush needed",
+                       "timing": "wall clock around every step (q = 1..4), mean over the steps"},
             "cpu_baseline": {"value": round(m["gbs"], 2), "unit": "GB/s", "cores": m["cores"], "kind": m["kind"], "sample": sample},
             "e2e": {"value": round(m["gbs"], 2), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gflops": round(2 * EXT ** 3 * last * 4 / m["seconds_per_step"] / 1e9, 2)}
@@ -447,6 +450,8 @@ def run_own_arm(args):
                 "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
                 "config": {"workload": workload_name(world, args.nccl_reduce), "layout": "first-order", "per_gpu_tensor_bytes": sh.a_count * ELEM,
+                           "timed_on": f"{world} x B200", "sampled_shape": list(sh.na_local), "sampled_bytes_per_step": total_bytes // world,
+                           "sample_is": "the whole per-GPU 256^4 tensor",
                            "l2": "inputs (16 GiB per GPU) are larger than L2; no flush needed",
                            "timing": "CUDA events on the launching stream, max over ranks"},
                 "gflops": round(total_flops / (ms_per_step * 1e-3) / 1e9, 1),
