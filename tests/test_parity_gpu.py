@@ -899,6 +899,99 @@ def test_colt_kernel_tma_tensor_tiles(dtype, oracle, monkeypatch):
         ttv_b200.plan(2, (64 * vec + 1, 9), (1, 2), dtype=name, kernel="colt") if vec > 1 else ttv_b200.plan(1, (9, 64), (1, 2), dtype=name, kernel="colt")
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.int32, np.int64])
+def test_dotp_kernel_fibers_of_two_elements(dtype, oracle, monkeypatch):
+    """kernel="dotp": n_q = 2 with q the contiguous mode (dotp_kernel.cuh).  Even and odd numbers of fibers (the half vector
+    at the end), fewer fibers than one vector / one tile / several tiles, both batch depths, accumulate; 4-byte types take it
+    on their own, 16-byte elements are refused."""
+    rng = np.random.default_rng(31)
+    dt = np.dtype(dtype)
+    name = {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64", np.dtype(np.complex64): "c64", np.dtype(np.int32): "i32", np.dtype(np.int64): "i64"}[dt]
+    cases = [((2, 1), (1, 2), 1), ((2, 2), (1, 2), 1), ((2, 3), (1, 2), 1), ((2, 1001), (1, 2), 1), ((2, 4096), (1, 2), 1), ((2, 2048 * 3 + 5), (1, 2), 1),
+             ((7, 2, 11), (2, 1, 3), 2), ((5, 3, 2, 9), (3, 2, 1, 4), 3), ((2, 70001), (1, 2), 1), ((33, 2), (2, 1), 2)]
+    for ku, warp in (("8", "0"), ("4", "0"), ("8", "1")):
+        monkeypatch.setenv("TTV_B200_DOTP_KU", ku)
+        monkeypatch.setenv("TTV_B200_DOTP_WARP", warp)
+        for na, pia, q in cases:
+            a, b = random_case(rng, na, q, dtype)
+            want = oracle.ttv(q, a, na, pia, b)
+            assert ttv_b200.plan(q, na, pia, dtype=name, kernel="dotp")["kernel"] == 9
+            assert (ttv_b200.plan(q, na, pia, dtype=name)["kernel"] == 9) == (dt.itemsize == 4)
+            assert np.array_equal(run_lowlevel(q, a, na, pia, b, kernel="dotp"), want), (na, pia, q, dtype, ku)
+            assert np.array_equal(run_lowlevel(q, a, na, pia, b), want), (na, pia, q, dtype, ku)
+            c0 = np.full(want.size, 3, dtype)
+            assert np.array_equal(run_lowlevel(q, a, na, pia, b, c0=c0, kernel="dotp", flags=1), want + 3)
+    with pytest.raises(ttv_b200.TTVError):
+        ttv_b200.plan(1, (2, 64), (1, 2), dtype="c128", kernel="dotp")
+    with pytest.raises(ttv_b200.TTVError):                          # three elements per fiber
+        ttv_b200.plan(1, (3, 64), (1, 2), dtype=name, kernel="dotp")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.int32, np.int64])
+def test_colf_kernel_rows_that_are_not_whole_vectors(dtype, oracle, monkeypatch):
+    """kernel="colf": rows narrower than / not a multiple of a 16-byte vector, streamed flat as super-rows of V / gcd(inner, V)
+    rows (colf_kernel.cuh).  Every gcd class (super-rows of 2 and 4 rows), one to 64 vectors per super-row, contractions
+    shorter than a super-row / a batch / several batches, rows past the last whole super-row (single slab only), several
+    slabs, n_q split across CTAs (chosen and forced), accumulate; taken on its own from 64 KB per slab."""
+    rng = np.random.default_rng(37)
+    dt = np.dtype(dtype)
+    name = {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64", np.dtype(np.complex64): "c64", np.dtype(np.int32): "i32", np.dtype(np.int64): "i64"}[dt]
+    vec = 16 // dt.itemsize
+    inners = [3, 5, 7, 9, 15, 63] + ([2, 6, 10, 14, 126] if vec == 4 else [])
+    cases = []
+    for i, inner in enumerate(inners):
+        rows = vec // np.gcd(inner, vec)
+        cases += [((inner, rows * (1000 + 7 * i), 3), (1, 2, 3), 2), ((inner, rows * 3), (1, 2), 2), ((inner, 1, rows * 2501), (1, 3, 2), 3),
+                  ((inner, 4001 + i), (1, 2), 2), ((inner, rows - 1), (1, 2), 2), ((2, rows * 700, inner), (3, 2, 1), 2)]
+    for na, pia, q in cases:
+        a, b = random_case(rng, na, q, dtype)
+        want = oracle.ttv(q, a, na, pia, b)
+        assert ttv_b200.plan(q, na, pia, dtype=name, kernel="colf")["kernel"] == 10
+        for ks in (0, 1, 3):
+            assert np.array_equal(run_lowlevel(q, a, na, pia, b, kernel="colf", ksplit=ks), want), (na, pia, q, dtype, ks)
+        c0 = np.full(want.size, 3, dtype)
+        assert np.array_equal(run_lowlevel(q, a, na, pia, b, c0=c0, kernel="colf", flags=1), want + 3)
+    na = (3, 4 * 6000, 2)                                           # 72 000 elements per slab: above 64 KB for every type
+    assert ttv_b200.plan(2, na, (1, 2, 3), dtype=name)["kernel"] == 10
+    a, b = random_case(rng, na, 2, dtype)
+    assert np.array_equal(run_lowlevel(2, a, na, (1, 2, 3), b), oracle.ttv(2, a, na, (1, 2, 3), b))
+    with pytest.raises(ttv_b200.TTVError):                          # rows of whole vectors
+        ttv_b200.plan(2, (2 * vec, 5000), (1, 2), dtype=name, kernel="colf")
+    with pytest.raises(ttv_b200.TTVError):                          # several slabs that do not start on a vector boundary
+        ttv_b200.plan(2, (3, 4001, 2), (1, 2, 3), dtype=name, kernel="colf")
+
+
+@pytest.mark.parametrize("dtype", ALL_DTYPES)
+def test_streamk_kernel_tiny_inner_long_contraction(dtype, oracle, monkeypatch):
+    """kernel="streamk": rows of a few elements under a long contraction, staged through shared memory by bulk copies with the
+    threads along n_q (streamk_kernel.cuh).  Rows of 2 .. 64 bytes, contractions that are not a multiple of a stage, tensors
+    and vectors whose last bytes no 16-byte bulk copy covers (plain-load tail), several slabs, n_q split across CTAs (forced and
+    chosen), one and many stages per partition, accumulate."""
+    rng = np.random.default_rng(29)
+    dt = np.dtype(dtype)
+    name = {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64", np.dtype(np.complex64): "c64",
+            np.dtype(np.complex128): "c128", np.dtype(np.int32): "i32", np.dtype(np.int64): "i64"}[dt]
+    imax = 64 // dt.itemsize
+    inners = sorted({2, 3, min(5, imax), min(7, imax), imax})
+    cases = []
+    for i, inner in enumerate(inners):
+        cases += [((inner, 4099 + 2 * i, 3), (1, 2, 3), 2), ((inner, 4096, 1), (1, 2, 3), 2), ((2, 9001, inner), (3, 2, 1), 2), ((inner, 1, 20011), (1, 3, 2), 3)]
+    for stage_kb in ("32", "1", "6"):
+        monkeypatch.setenv("TTV_B200_STREAMK_STAGE_KB", stage_kb)
+        for na, pia, q in cases:
+            a, b = random_case(rng, na, q, dtype)
+            want = oracle.ttv(q, a, na, pia, b)
+            assert ttv_b200.plan(q, na, pia, dtype=name, kernel="streamk")["kernel"] == 8
+            for ks in (0, 1, 3):
+                assert np.array_equal(run_lowlevel(q, a, na, pia, b, kernel="streamk", ksplit=ks), want), (na, pia, q, dtype, stage_kb, ks)
+            c0 = np.full(want.size, 3, dtype)
+            assert np.array_equal(run_lowlevel(q, a, na, pia, b, c0=c0, kernel="streamk", flags=1), want + 3)
+    with pytest.raises(ttv_b200.TTVError):                          # rows wider than 64 bytes
+        ttv_b200.plan(2, (imax + 1, 5000), (1, 2), dtype=name, kernel="streamk")
+    with pytest.raises(ttv_b200.TTVError):                          # a short contraction
+        ttv_b200.plan(2, (3, 100), (1, 2), dtype=name, kernel="streamk")
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.complex64, np.complex128])
 def test_single_kernel_exchange_emulated_on_one_gpu(dtype, oracle, monkeypatch):
     """ttv_b200_view_exchange: product + scatter + in-kernel flag barrier + sum of the slots in ONE kernel per rank.  The

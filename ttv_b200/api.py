@@ -29,7 +29,7 @@ EXECUTION = {"seq": 0, "seq_blas": 1, "par": 2, "par_loop": 3, "par_taskloop": 4
              "par_blas_loop": 7}
 SLICING = {"slice": 0, "subtensor": 1}
 FUSION = {"none": 0, "outer": 1, "all": 2}
-KERNELS = {"auto": 0, "dot": 1, "col": 2, "stream": 3, "colx": 4, "dotf": 5, "colt": 7}
+KERNELS = {"auto": 0, "dot": 1, "col": 2, "stream": 3, "colx": 4, "dotf": 5, "colt": 7, "streamk": 8, "dotp": 9, "colf": 10}
 
 FLAG_ACCUMULATE, FLAG_ASYNC, FLAG_NO_VEC = 1, 2, 4
 

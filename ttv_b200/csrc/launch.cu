@@ -12,6 +12,9 @@
 #include "strided_kernel.cuh"
 #include "scatter_kernel.cuh"
 #include "colt_kernel.cuh"
+#include "streamk_kernel.cuh"
+#include "dotp_kernel.cuh"
+#include "colf_kernel.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -29,6 +32,9 @@ using fill_fn_t   = cudaError_t (*)(void*, uint64_t, uint64_t, uint64_t, int, cu
 using stream_fn_t = cudaError_t (*)(const StreamParams&, const Launch&, cudaStream_t);
 using dotf_fn_t   = cudaError_t (*)(const DotfParams&, const Launch&, cudaStream_t);
 using strided_fn_t = cudaError_t (*)(const StridedParams&, int, cudaStream_t);
+using streamk_fn_t = cudaError_t (*)(const StreamkParams&, const Launch&, cudaStream_t);
+using dotp_fn_t   = cudaError_t (*)(const DotpParams&, const Launch&, cudaStream_t);
+using colf_fn_t   = cudaError_t (*)(const ColfParams&, const Launch&, cudaStream_t);
 using colt_fn_t   = cudaError_t (*)(const CUtensorMap&, const ColtParams&, const Launch&, cudaStream_t);
 
 #define TTVB_DECLARE(k)                                                                                          \
@@ -40,7 +46,10 @@ using colt_fn_t   = cudaError_t (*)(const CUtensorMap&, const ColtParams&, const
   cudaError_t stream_dtype_##k(const StreamParams&, const Launch&, cudaStream_t);                               \
   cudaError_t dotf_dtype_##k(const DotfParams&, const Launch&, cudaStream_t);                                   \
   cudaError_t strided_dtype_##k(const StridedParams&, int, cudaStream_t);                                         \
-  cudaError_t colt_dtype_##k(const CUtensorMap&, const ColtParams&, const Launch&, cudaStream_t);
+  cudaError_t colt_dtype_##k(const CUtensorMap&, const ColtParams&, const Launch&, cudaStream_t);                \
+  cudaError_t streamk_dtype_##k(const StreamkParams&, const Launch&, cudaStream_t);                             \
+  cudaError_t dotp_dtype_##k(const DotpParams&, const Launch&, cudaStream_t);                                   \
+  cudaError_t colf_dtype_##k(const ColfParams&, const Launch&, cudaStream_t);
 TTVB_DECLARE(0) TTVB_DECLARE(1) TTVB_DECLARE(2) TTVB_DECLARE(3) TTVB_DECLARE(4) TTVB_DECLARE(5)
 #undef TTVB_DECLARE
 
@@ -88,6 +97,9 @@ static const dotf_fn_t   k_dotf[]   = {dotf_dtype_0, dotf_dtype_1, dotf_dtype_2,
 static const scatter_fn_t k_scatter[] = {scatter_dtype_0, scatter_dtype_1, scatter_dtype_2, scatter_dtype_3, scatter_dtype_4, scatter_dtype_5};
 static const exchange_fn_t k_exchange[] = {exchange_dtype_0, exchange_dtype_1, exchange_dtype_2, exchange_dtype_3, exchange_dtype_4, exchange_dtype_5};
 static const strided_fn_t k_strided[] = {strided_dtype_0, strided_dtype_1, strided_dtype_2, strided_dtype_3, strided_dtype_4, strided_dtype_5};
+static const streamk_fn_t k_streamk[] = {streamk_dtype_0, streamk_dtype_1, streamk_dtype_2, streamk_dtype_3, streamk_dtype_4, streamk_dtype_5};
+static const dotp_fn_t   k_dotp[]   = {dotp_dtype_0, dotp_dtype_1, dotp_dtype_2, dotp_dtype_3, dotp_dtype_4, dotp_dtype_5};
+static const colf_fn_t   k_colf[]   = {colf_dtype_0, colf_dtype_1, colf_dtype_2, colf_dtype_3, colf_dtype_4, colf_dtype_5};
 static const colt_fn_t   k_colt[]   = {colt_dtype_0, colt_dtype_1, colt_dtype_2, colt_dtype_3, colt_dtype_4, colt_dtype_5};
 
 // cuTensorMapEncodeTiled lives in the driver library; the runtime hands out its address, so nothing links against libcuda
@@ -164,10 +176,42 @@ cudaError_t launch_view(int dtype, const View& v, const Launch& l, const void* a
     S.accumulate = accumulate ? 1u : 0u;
     return k_stream[dtype](S, l, stream);
   }
+  if (l.kernel == TTV_B200_KERNEL_STREAMK) {
+    StreamkParams K;
+    const uint64_t es = (uint64_t)dtype_size(dtype);
+    K.a = a; K.b = b; K.c = l.ksplit > 1 ? workspace : c;
+    K.outer = v.outer; K.nq = v.nq; K.inner = v.inner;
+    K.kchunk = l.kchunk;
+    K.total_bytes_a = v.outer * v.nq * v.inner * es; K.total_bytes_b = v.nq * es;
+    K.ksplit = l.ksplit; K.rows_per_stage = (uint32_t)l.slabs_per_chunk;
+    K.a_stage_bytes = l.stage_bytes; K.b_stage_bytes = l.b_stage_bytes;
+    K.accumulate = (accumulate && l.ksplit == 1) ? 1u : 0u;
+    cudaError_t e = k_streamk[dtype](K, l, stream);
+    if (e != cudaSuccess || l.ksplit <= 1) return e;
+    return k_reduce[dtype](workspace, c, v.outer * v.inner, l.ksplit, accumulate, v.outer * v.inner, sm_count, stream);
+  }
   if (l.kernel == TTV_B200_KERNEL_COLT) {
     cudaError_t e = launch_colt(dtype, v, l, a, b, c, workspace, accumulate, stream);
     if (e != cudaSuccess || l.ksplit <= 1) return e;
     return k_reduce[dtype](workspace, c, v.outer * v.inner, l.ksplit, accumulate, v.outer * v.inner, sm_count, stream);
+  }
+  if (l.kernel == TTV_B200_KERNEL_COLF) {
+    ColfParams F;
+    F.a = a; F.b = b; F.c = l.ksplit > 1 ? workspace : c;
+    F.outer = v.outer; F.nq = v.nq; F.inner = v.inner;
+    F.srchunk = l.kchunk / l.to;                                     // l.to carries R, the rows of a super-row
+    F.ksplit = l.ksplit; F.L = l.tx; F.TY = l.ty;
+    F.accumulate = (accumulate && l.ksplit == 1) ? 1u : 0u;
+    cudaError_t e = k_colf[dtype](F, l, stream);
+    if (e != cudaSuccess || l.ksplit <= 1) return e;
+    return k_reduce[dtype](workspace, c, v.outer * v.inner, l.ksplit, accumulate, v.outer * v.inner, sm_count, stream);
+  }
+  if (l.kernel == TTV_B200_KERNEL_DOTP) {
+    DotpParams D;
+    D.a = a; D.b = b; D.c = c;
+    D.outer = v.outer; D.nvec = v.outer * 2 * (uint64_t)dtype_size(dtype) / 16; D.tiles = l.tiles;
+    D.accumulate = accumulate ? 1u : 0u;
+    return k_dotp[dtype](D, l, stream);
   }
   if (l.kernel == TTV_B200_KERNEL_DOTF) {
     DotfParams D;
@@ -570,6 +614,42 @@ cudaError_t TTVB_CAT(strided_dtype_, TTVB_DTYPE)(const StridedParams& S, int sm_
   }
   const uint64_t blocks = std::max<uint64_t>(1, std::min<uint64_t>((S.total + 255) / 256, (uint64_t)sm_count * 32));
   return launch_k(ttv_strided_kernel<elem_t>, (unsigned)blocks, 256u, 0, stream, S);
+}
+
+cudaError_t TTVB_CAT(streamk_dtype_, TTVB_DTYPE)(const StreamkParams& K, const Launch& l, cudaStream_t stream)
+{
+  constexpr int kImaxAll = 64 / (int)sizeof(elem_t);                 // the widest row STREAMK takes: 64 bytes
+  auto kern = ttv_streamk_kernel<elem_t, 3, kImaxAll>;
+  if constexpr (kImaxAll >= 8) if (K.inner <= 4) kern = ttv_streamk_kernel<elem_t, 3, 4>;
+  if constexpr (kImaxAll >= 16) if (K.inner > 4 && K.inner <= 8) kern = ttv_streamk_kernel<elem_t, 3, 8>;
+  if ((int)K.inner > kImaxAll) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes);
+  if (e != cudaSuccess) return e;
+  return launch_k(kern, (unsigned)l.ctas, 256u, l.smem_bytes, stream, K);
+}
+
+cudaError_t TTVB_CAT(colf_dtype_, TTVB_DTYPE)(const ColfParams& F, const Launch& l, cudaStream_t stream)
+{
+  if constexpr (sizeof(elem_t) == 4) {
+    if (l.to == 4) return launch_k(ttv_colf_kernel<elem_t, 4, 8>, (unsigned)l.ctas, 256u, l.smem_bytes, stream, F);
+    if (l.to == 2) return launch_k(ttv_colf_kernel<elem_t, 2, 8>, (unsigned)l.ctas, 256u, l.smem_bytes, stream, F);
+  } else if constexpr (sizeof(elem_t) == 8) {
+    if (l.to == 2) return launch_k(ttv_colf_kernel<elem_t, 2, 8>, (unsigned)l.ctas, 256u, l.smem_bytes, stream, F);
+  }
+  (void)F; (void)stream;
+  return cudaErrorInvalidValue;                                      // 16-byte elements: every row is whole vectors
+}
+
+cudaError_t TTVB_CAT(dotp_dtype_, TTVB_DTYPE)(const DotpParams& D, const Launch& l, cudaStream_t stream)
+{
+  if constexpr (sizeof(elem_t) <= 8) {
+    if (l.nu == 2) return launch_k(ttv_dotp_kernel<elem_t, 8, true>, (unsigned)l.ctas, 256u, 0, stream, D);   // warp-contiguous, 16-byte stores
+    if (l.ku == 4) return launch_k(ttv_dotp_kernel<elem_t, 4, false>, (unsigned)l.ctas, 256u, 0, stream, D);
+    return launch_k(ttv_dotp_kernel<elem_t, 8, false>, (unsigned)l.ctas, 256u, 0, stream, D);
+  } else {
+    (void)D; (void)l; (void)stream;
+    return cudaErrorInvalidValue;                                    // a fiber of two 16-byte elements is two vectors: DOTF
+  }
 }
 
 cudaError_t TTVB_CAT(colt_dtype_, TTVB_DTYPE)(const CUtensorMap& map, const ColtParams& P, const Launch& l, cudaStream_t stream)

@@ -467,6 +467,34 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
       return TTV_B200_OK;
     }
   }
+  // DOTP: fibers of two elements of 4 or 8 bytes (dotp_kernel.cuh): whole fibers per 16-byte vector, b in registers, one
+  // 8-byte store per vector, nothing shared.  STREAM took the 4-byte shapes before ([1610612736, 2, 1]: 6 311-6 389 GB/s).
+  {
+    const bool eligible = v.inner == 1 && v.nq == 2 && s <= 8 && (align_a % 16) == 0 && (align_c % 8) == 0 && (!opts || opts->ksplit <= 1) &&
+                          !(flags & TTV_B200_FLAG_NO_VEC);
+    if (forced == TTV_B200_KERNEL_DOTP && !eligible) return TTV_B200_ERR_OPTS;
+    const int mode = env_int("TTV_B200_USE_DOTP", -1);                                 // -1 auto, 0 never, 1 whenever eligible
+    const bool pick = forced == TTV_B200_KERNEL_DOTP ? true
+                    : forced != 0 ? false
+                    : mode == 1 ? eligible
+                    : mode == 0 ? false
+                    : (eligible && s == 4);
+    if (pick) {
+      l.kernel = TTV_B200_KERNEL_DOTP;
+      l.threads = 256;
+      l.vec = (int)(16 / s); l.tx = 1; l.ty = 1; l.to = 256; l.nu = 1; l.stream = 1; l.udir = 0; l.ksplit = 1;
+      l.ku = env_int("TTV_B200_DOTP_KU", 8) == 4 ? 4 : 8;
+      if (env_int("TTV_B200_DOTP_WARP", 0) == 1 && (align_c % 16) == 0) { l.nu = 2; l.ku = 8; }             // warp-contiguous form with 16-byte stores
+      const uint64_t nvec = v.outer * 2 * s / 16;
+      l.tiles = std::max<uint64_t>(1, ceil_div(nvec, 256ull * (uint64_t)l.ku));
+      l.ctas = std::min<uint64_t>(l.tiles, sms * (uint64_t)std::max(1, env_int("TTV_B200_DOTP_CTAS", 64)));
+      l.kchunk = v.nq; l.kb = 2;
+      l.smem_bytes = 0;
+      l.workspace_bytes = 0;
+      *out = l;
+      return TTV_B200_OK;
+    }
+  }
   // STREAM: small slabs staged through shared memory by TMA bulk copies (stream_kernel.cuh).  Eligible when a slab and
   // b are small, A is 16-byte aligned and n_q is not split.
   {
@@ -535,6 +563,97 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
       return TTV_B200_OK;
     }
     if (forced == TTV_B200_KERNEL_STREAM) forced = 0;
+  }
+
+  // COLF: rows that are not whole 16-byte vectors under a long contraction, streamed flat as super-rows of
+  // R = V / gcd(inner, V) rows = L = inner / gcd whole vectors (colf_kernel.cuh).  Slabs must start on a vector boundary
+  // (n_q a multiple of R, or one slab whose last rows the kernel takes with plain loads).
+  {
+    const uint64_t Vf = vmax_of(s);
+    uint64_t g = Vf, t = v.inner % Vf;
+    while (t) { const uint64_t r = g % t; g = t; t = r; }             // gcd(inner, V)
+    const uint64_t R = Vf / g, L = v.inner / g;
+    const bool eligible = Vf > 1 && v.inner > 1 && R > 1 && L <= 64 && (v.nq % R == 0 || v.outer == 1) && (align_a % 16) == 0 &&
+                          (align_b % 16) == 0 && !(flags & TTV_B200_FLAG_NO_VEC);
+    if (forced == TTV_B200_KERNEL_COLF && !eligible) return TTV_B200_ERR_OPTS;
+    const int mode = env_int("TTV_B200_USE_COLF", -1);                                 // -1 auto, 0 never, 1 whenever eligible
+    const bool pick = forced == TTV_B200_KERNEL_COLF ? true
+                    : forced != 0 ? false
+                    : mode == 1 ? eligible
+                    : mode == 0 ? false
+                    : (eligible && v.nq * v.inner * s >= (uint64_t)env_int("TTV_B200_COLF_MIN_SLAB_KB", 64) * 1024);
+    if (pick) {
+      constexpr uint64_t KUf = 8;
+      l.kernel = TTV_B200_KERNEL_COLF;
+      l.threads = 256;
+      l.vec = (int)Vf; l.tx = (uint32_t)L; l.ty = (uint32_t)(256 / L); l.to = (uint32_t)R; l.nu = 1; l.ku = (int)KUf; l.stream = 1; l.udir = 0;
+      const uint64_t nsr = v.nq / R, batch = (uint64_t)l.ty * KUf;   // super-rows of a slab / of one batch of the CTA
+      int want = opts ? opts->ksplit : 0;
+      if (want < 0) return TTV_B200_ERR_OPTS;
+      if (want == 0) want = env_int("TTV_B200_KSPLIT", 0);
+      // enough work items for several waves of three CTAs per SM, at least four batches per partition
+      uint64_t ksplit = want > 0 ? (uint64_t)want : ceil_div(sms * (uint64_t)env_int("TTV_B200_COLF_ITEMS_PER_SM", 12), v.outer);
+      if (want <= 0) ksplit = std::min(ksplit, std::max<uint64_t>(1, nsr / (batch * 4)));
+      ksplit = std::max<uint64_t>(1, std::min(ksplit, std::max<uint64_t>(1, nsr)));
+      uint64_t srchunk = ceil_div(std::max<uint64_t>(1, ceil_div(nsr, ksplit)), batch) * batch;
+      ksplit = std::max<uint64_t>(1, ceil_div(nsr, srchunk));
+      l.ksplit = (uint32_t)ksplit; l.kchunk = srchunk * R;
+      l.itiles = 1; l.otiles = v.outer;
+      l.tiles = v.outer * ksplit;
+      l.ctas = std::min<uint64_t>(l.tiles, sms * 64);
+      l.kb = 0;
+      l.smem_bytes = 256 * 16;
+      l.workspace_bytes = ksplit > 1 ? ksplit * v.outer * v.inner * s : 0;
+      *out = l;
+      return TTV_B200_OK;
+    }
+  }
+
+  // STREAMK: a tiny inner extent that no 16-byte vector tiles (3, 5, 6, 7, 9 ... elements) under a long contraction
+  // (streamk_kernel.cuh).  The column kernel runs such rows with 4- / 8-byte loads and its lanes along n_q: measured
+  // [64, 2^20, 3] fp32 4.3, [262144, 256, 3] 2.9, [48, 2^19, 5] fp64 5.9 TB/s (tools/probe/tiny_inner.py).
+  {
+    const uint64_t Vk = vmax_of(s);
+    const bool eligible = v.inner > 1 && v.inner <= 16 && v.inner * s <= 64 && v.nq >= 4096 && (align_a % 16) == 0 && (align_b % 16) == 0 &&
+                          !(flags & TTV_B200_FLAG_NO_VEC);
+    if (forced == TTV_B200_KERNEL_STREAMK && !eligible) return TTV_B200_ERR_OPTS;
+    const int mode = env_int("TTV_B200_USE_STREAMK", -1);
+    const bool misaligned = (v.inner % Vk) != 0;
+    const bool pick = forced == TTV_B200_KERNEL_STREAMK ? true
+                    : forced != 0 ? false
+                    : mode == 1 ? eligible
+                    : mode == 0 ? false
+                    : (eligible && misaligned && v.outer * v.nq * v.inner * s >= (64ull << 20));
+    if (pick) {
+      l.kernel = TTV_B200_KERNEL_STREAMK;
+      l.threads = 256;
+      l.vec = 1; l.tx = 1; l.ty = 256; l.to = 1; l.nu = 1; l.ku = 1; l.stream = 1; l.udir = 0;
+      const uint64_t budget = (uint64_t)env_int("TTV_B200_STREAMK_STAGE_KB", 32) * 1024;
+      uint64_t rows = std::max<uint64_t>(256, budget / ((v.inner + 1) * s) / 256 * 256);
+      rows = std::min<uint64_t>(rows, ceil_div(v.nq, 256) * 256);
+      l.slabs_per_chunk = rows;
+      l.stage_bytes = (uint32_t)((rows * v.inner * s + 32 + 127) / 128 * 128);
+      l.b_stage_bytes = (uint32_t)((rows * s + 32 + 127) / 128 * 128);
+      l.stages = 3;
+      int want = opts ? opts->ksplit : 0;
+      if (want < 0) return TTV_B200_ERR_OPTS;
+      if (want == 0) want = env_int("TTV_B200_KSPLIT", 0);
+      uint64_t ksplit = want > 0 ? (uint64_t)want : std::max<uint64_t>(1, ceil_div(sms * 8, v.outer));
+      ksplit = std::max<uint64_t>(1, std::min(ksplit, std::max<uint64_t>(1, v.nq / (rows * 4))));     // four stages per partition at least
+      if (want > 0) ksplit = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)want, ceil_div(v.nq, rows)));
+      uint64_t kchunk = ceil_div(ceil_div(v.nq, ksplit), rows) * rows;
+      ksplit = ceil_div(v.nq, kchunk);
+      l.ksplit = (uint32_t)ksplit; l.kchunk = kchunk;
+      l.itiles = 1; l.otiles = v.outer;
+      l.tiles = v.outer * ksplit;
+      l.ctas = std::min<uint64_t>(l.tiles, sms * 2);
+      l.kb = (uint32_t)rows;
+      l.smem_bytes = 3ull * (l.stage_bytes + l.b_stage_bytes) + ((256 * v.inner * s + 15) / 16 * 16) + 3 * 8 + 64;
+      if (l.smem_bytes > 113 * 1024) return TTV_B200_ERR_OPTS;
+      l.workspace_bytes = ksplit > 1 ? ksplit * v.outer * v.inner * s : 0;
+      *out = l;
+      return TTV_B200_OK;
+    }
   }
 
   // DOTF: short contiguous fibers read as one flat stream (dotf_kernel.cuh).  Measured against the lane-group DOT kernel:

@@ -10,7 +10,7 @@ from . import api, selfcheck
 from .workloads import SEED_A, SEED_B, SIZE, algo_bytes
 
 L2_BYTES = 126 * 2 ** 20
-KERNEL_NAMES = {0: "auto", 1: "dot", 2: "col", 3: "stream", 4: "colx", 5: "dotf", 6: "strided", 7: "colt"}
+KERNEL_NAMES = {0: "auto", 1: "dot", 2: "col", 3: "stream", 4: "colx", 5: "dotf", 6: "strided", 7: "colt", 8: "streamk", 9: "dotp", 10: "colf"}
 
 
 def _torch_dtype(dt):
