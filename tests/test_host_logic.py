@@ -297,20 +297,18 @@ def test_chooser_only_picks_instantiated_kernels():
                 continue
             if pl["kernel"] == 9:       # DOTP: fibers of two 4-byte elements, vectors of whole fibers, nothing shared
                 assert inner == 1 and nq == 2 and size[dt] == 4 and pl["vec"] == 4 and pl["ku"] in (4, 8) and pl["smem_bytes"] == 0 and pl["ksplit"] == 1
-                assert pl["ctas"] == min(148 * 64, max(1, -(-(outer // 2) // (256 * pl["ku"]))))
+                assert pl["ctas"] == max(1, -(-(outer // 2) // (256 * pl["ku"])))                        # one tile per CTA
                 continue
-            if pl["kernel"] == 10:      # COLF: narrow / odd rows under a long contraction as a flat stream of super-rows
-                import math
+            if pl["kernel"] == 10:      # COLF: narrow / odd rows as a flat stream of super-rows, a warp per slab (partition)
                 vec = 16 // size[dt]
                 g = math.gcd(inner, vec)
-                assert inner > 1 and g < vec and (nq % (vec // g) == 0 or outer == 1) and nq * inner * size[dt] >= 64 * 1024
-                assert (pl["tx"], pl["ty"], pl["to"]) == (inner // g, 256 // (inner // g), vec // g) and pl["smem_bytes"] == 4096
-                assert pl["ksplit"] >= 1 and pl["ctas"] == min(outer * pl["ksplit"], 148 * 64) and pl["workspace_bytes"] == (pl["ksplit"] > 1) * pl["ksplit"] * outer * inner * size[dt]
+                assert inner > 1 and g < vec and inner // g <= 32 and (nq % (vec // g) == 0 or outer == 1) and nq * inner * size[dt] >= 1024
+                assert (pl["tx"], pl["ty"], pl["to"]) == (inner // g, 32 // (inner // g), vec // g) and pl["smem_bytes"] == 4096
+                assert pl["ksplit"] >= 1 and pl["ctas"] == -(-outer * pl["ksplit"] // 8) and pl["workspace_bytes"] == (pl["ksplit"] > 1) * pl["ksplit"] * outer * inner * size[dt]
                 continue
             if pl["kernel"] == 8:       # STREAMK: rows of a few elements under a long contraction, staged through shared memory
                 assert 1 < inner <= 16 and inner * size[dt] <= 64 and inner % (16 // size[dt]) != 0 and nq >= 4096
-                # what COLF leaves: slabs off the vector grid, slabs under 64 KB
-                assert (outer > 1 and nq % ((16 // size[dt]) // math.gcd(inner, 16 // size[dt])) != 0) or nq * inner * size[dt] < 64 * 1024
+                assert outer > 1 and nq % ((16 // size[dt]) // math.gcd(inner, 16 // size[dt])) != 0      # what COLF cannot take
                 assert pl["smem_bytes"] <= 113 * 1024 and pl["ctas"] <= 148 * 2 and pl["ksplit"] >= 1 and pl["threads"] == 256
                 continue
             if pl["kernel"] == 4:       # COLX: odd wide rows, 16-byte loads at any phase

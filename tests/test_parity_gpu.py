@@ -930,14 +930,15 @@ def test_dotp_kernel_fibers_of_two_elements(dtype, oracle, monkeypatch):
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.int32, np.int64])
 def test_colf_kernel_rows_that_are_not_whole_vectors(dtype, oracle, monkeypatch):
     """kernel="colf": rows narrower than / not a multiple of a 16-byte vector, streamed flat as super-rows of V / gcd(inner, V)
-    rows (colf_kernel.cuh).  Every gcd class (super-rows of 2 and 4 rows), one to 64 vectors per super-row, contractions
-    shorter than a super-row / a batch / several batches, rows past the last whole super-row (single slab only), several
-    slabs, n_q split across CTAs (chosen and forced), accumulate; taken on its own from 64 KB per slab."""
+    rows, a warp per slab or slab partition (colf_kernel.cuh).  Every gcd class (super-rows of 2 and 4 rows), one to 31
+    vectors per super-row, contractions shorter than a super-row / a batch / several batches, rows past the last whole
+    super-row (single slab only), several slabs, n_q split across warps (chosen and forced), accumulate; taken on its own
+    from 1 KB per slab."""
     rng = np.random.default_rng(37)
     dt = np.dtype(dtype)
     name = {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64", np.dtype(np.complex64): "c64", np.dtype(np.int32): "i32", np.dtype(np.int64): "i64"}[dt]
     vec = 16 // dt.itemsize
-    inners = [3, 5, 7, 9, 15, 63] + ([2, 6, 10, 14, 126] if vec == 4 else [])
+    inners = [3, 5, 7, 9, 15, 31] + ([2, 6, 10, 14, 62] if vec == 4 else [])
     cases = []
     for i, inner in enumerate(inners):
         rows = vec // np.gcd(inner, vec)
@@ -951,12 +952,14 @@ def test_colf_kernel_rows_that_are_not_whole_vectors(dtype, oracle, monkeypatch)
             assert np.array_equal(run_lowlevel(q, a, na, pia, b, kernel="colf", ksplit=ks), want), (na, pia, q, dtype, ks)
         c0 = np.full(want.size, 3, dtype)
         assert np.array_equal(run_lowlevel(q, a, na, pia, b, c0=c0, kernel="colf", flags=1), want + 3)
-    na = (3, 4 * 6000, 2)                                           # 72 000 elements per slab: above 64 KB for every type
-    assert ttv_b200.plan(2, na, (1, 2, 3), dtype=name)["kernel"] == 10
-    a, b = random_case(rng, na, 2, dtype)
-    assert np.array_equal(run_lowlevel(2, a, na, (1, 2, 3), b), oracle.ttv(2, a, na, (1, 2, 3), b))
+    for na in ((3, 4 * 6000, 2), (3, 4 * 30, 700), (2 if vec == 4 else 3, 256, 3000)):
+        assert ttv_b200.plan(2, na, (1, 2, 3), dtype=name)["kernel"] == 10
+        a, b = random_case(rng, na, 2, dtype)
+        assert np.array_equal(run_lowlevel(2, a, na, (1, 2, 3), b), oracle.ttv(2, a, na, (1, 2, 3), b)), na
     with pytest.raises(ttv_b200.TTVError):                          # rows of whole vectors
         ttv_b200.plan(2, (2 * vec, 5000), (1, 2), dtype=name, kernel="colf")
+    with pytest.raises(ttv_b200.TTVError):                          # more than 32 vectors per super-row
+        ttv_b200.plan(2, (33, 5000), (1, 2), dtype=name, kernel="colf")
     with pytest.raises(ttv_b200.TTVError):                          # several slabs that do not start on a vector boundary
         ttv_b200.plan(2, (3, 4001, 2), (1, 2, 3), dtype=name, kernel="colf")
 

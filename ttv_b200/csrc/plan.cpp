@@ -487,7 +487,8 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
       if (env_int("TTV_B200_DOTP_WARP", 0) == 1 && (align_c % 16) == 0) { l.nu = 2; l.ku = 8; }             // warp-contiguous form with 16-byte stores
       const uint64_t nvec = v.outer * 2 * s / 16;
       l.tiles = std::max<uint64_t>(1, ceil_div(nvec, 256ull * (uint64_t)l.ku));
-      l.ctas = std::min<uint64_t>(l.tiles, sms * (uint64_t)std::max(1, env_int("TTV_B200_DOTP_CTAS", 64)));
+      // one tile per CTA: measured 6 432 (64 CTAs per SM striding over the tiles) -> 7 000 GB/s on [1610612736, 2, 1]
+      l.ctas = std::min<uint64_t>(l.tiles, std::min<uint64_t>(0x7fffffffull, sms * (uint64_t)std::max(1, env_int("TTV_B200_DOTP_CTAS", 1 << 20))));
       l.kchunk = v.nq; l.kb = 2;
       l.smem_bytes = 0;
       l.workspace_bytes = 0;
@@ -565,34 +566,35 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
     if (forced == TTV_B200_KERNEL_STREAM) forced = 0;
   }
 
-  // COLF: rows that are not whole 16-byte vectors under a long contraction, streamed flat as super-rows of
-  // R = V / gcd(inner, V) rows = L = inner / gcd whole vectors (colf_kernel.cuh).  Slabs must start on a vector boundary
-  // (n_q a multiple of R, or one slab whose last rows the kernel takes with plain loads).
+  // COLF: rows that are not whole 16-byte vectors, streamed flat as super-rows of R = V / gcd(inner, V) rows =
+  // L = inner / gcd whole vectors, a warp per slab or slab partition (colf_kernel.cuh).  Slabs must start on a vector
+  // boundary (n_q a multiple of R, or one slab whose last rows the kernel takes with plain loads).
   {
     const uint64_t Vf = vmax_of(s);
     uint64_t g = Vf, t = v.inner % Vf;
     while (t) { const uint64_t r = g % t; g = t; t = r; }             // gcd(inner, V)
     const uint64_t R = Vf / g, L = v.inner / g;
-    const bool eligible = Vf > 1 && v.inner > 1 && R > 1 && L <= 64 && (v.nq % R == 0 || v.outer == 1) && (align_a % 16) == 0 &&
-                          (align_b % 16) == 0 && !(flags & TTV_B200_FLAG_NO_VEC);
+    const bool eligible = Vf > 1 && v.inner > 1 && R > 1 && L <= 32 && (v.nq % R == 0 || v.outer == 1) && (align_a % 16) == 0 &&
+                          !(flags & TTV_B200_FLAG_NO_VEC);
     if (forced == TTV_B200_KERNEL_COLF && !eligible) return TTV_B200_ERR_OPTS;
     const int mode = env_int("TTV_B200_USE_COLF", -1);                                 // -1 auto, 0 never, 1 whenever eligible
     const bool pick = forced == TTV_B200_KERNEL_COLF ? true
                     : forced != 0 ? false
                     : mode == 1 ? eligible
                     : mode == 0 ? false
-                    : (eligible && v.nq * v.inner * s >= (uint64_t)env_int("TTV_B200_COLF_MIN_SLAB_KB", 64) * 1024);
+                    : (eligible && v.nq * v.inner * s >= (uint64_t)env_int("TTV_B200_COLF_MIN_SLAB_B", 1024));
     if (pick) {
       constexpr uint64_t KUf = 8;
       l.kernel = TTV_B200_KERNEL_COLF;
       l.threads = 256;
-      l.vec = (int)Vf; l.tx = (uint32_t)L; l.ty = (uint32_t)(256 / L); l.to = (uint32_t)R; l.nu = 1; l.ku = (int)KUf; l.stream = 1; l.udir = 0;
-      const uint64_t nsr = v.nq / R, batch = (uint64_t)l.ty * KUf;   // super-rows of a slab / of one batch of the CTA
+      l.vec = (int)Vf; l.tx = (uint32_t)L; l.ty = (uint32_t)(32 / L); l.to = (uint32_t)R; l.nu = 1; l.ku = (int)KUf; l.stream = 1; l.udir = 0;
+      const uint64_t nsr = v.nq / R, batch = (uint64_t)l.ty * KUf;   // super-rows of a slab / of one batch of a warp
       int want = opts ? opts->ksplit : 0;
       if (want < 0) return TTV_B200_ERR_OPTS;
       if (want == 0) want = env_int("TTV_B200_KSPLIT", 0);
-      // enough work items for several waves of three CTAs per SM, at least four batches per partition
-      uint64_t ksplit = want > 0 ? (uint64_t)want : ceil_div(sms * (uint64_t)env_int("TTV_B200_COLF_ITEMS_PER_SM", 12), v.outer);
+      // a work item (slab, partition) per warp: enough of them for several rounds of the 24 warps an SM holds, at least
+      // four batches per partition
+      uint64_t ksplit = want > 0 ? (uint64_t)want : ceil_div(sms * (uint64_t)env_int("TTV_B200_COLF_ITEMS_PER_SM", 96), v.outer);
       if (want <= 0) ksplit = std::min(ksplit, std::max<uint64_t>(1, nsr / (batch * 4)));
       ksplit = std::max<uint64_t>(1, std::min(ksplit, std::max<uint64_t>(1, nsr)));
       uint64_t srchunk = ceil_div(std::max<uint64_t>(1, ceil_div(nsr, ksplit)), batch) * batch;
@@ -600,9 +602,9 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
       l.ksplit = (uint32_t)ksplit; l.kchunk = srchunk * R;
       l.itiles = 1; l.otiles = v.outer;
       l.tiles = v.outer * ksplit;
-      l.ctas = std::min<uint64_t>(l.tiles, sms * 64);
+      l.ctas = std::min<uint64_t>(ceil_div(l.tiles, 8), std::min<uint64_t>(0x7fffffffull, sms * (uint64_t)std::max(1, env_int("TTV_B200_COLF_CTAS", 1 << 20))));
       l.kb = 0;
-      l.smem_bytes = 256 * 16;
+      l.smem_bytes = 8 * 32 * 16;                                    // static: a strip of 32 vectors per warp
       l.workspace_bytes = ksplit > 1 ? ksplit * v.outer * v.inner * s : 0;
       *out = l;
       return TTV_B200_OK;
