@@ -173,7 +173,7 @@ def test_fold_and_case_classification(oracle):
                     n = int(np.prod(na))
                     assert pl["algo_bytes"] == 8 * (n + na[q - 1] + n // na[q - 1])
                     assert pl["algo_flops"] == 2 * n
-                    assert pl["kernel"] == (1 if pl["inner"] == 1 else 2)
+                    assert pl["kernel"] in (((9,) if pl["nq"] == 2 else (1,)) if pl["inner"] == 1 else (2, 10))
 
 
 def test_chooser_named_configs():
@@ -295,16 +295,20 @@ def test_chooser_only_picks_instantiated_kernels():
                 assert inner == 1 and nq % vec == 0 and nq // vec <= (128 if size[dt] == 16 else 48) and pl["vec"] == vec and pl["ksplit"] == 1
                 assert pl["smem_bytes"] == (nq + 2048) * size[dt]
                 continue
-            if pl["kernel"] == 9:       # DOTP: fibers of two 4-byte elements, vectors of whole fibers, nothing shared
-                assert inner == 1 and nq == 2 and size[dt] == 4 and pl["vec"] == 4 and pl["ku"] in (4, 8) and pl["smem_bytes"] == 0 and pl["ksplit"] == 1
-                assert pl["ctas"] == max(1, -(-(outer // 2) // (256 * pl["ku"])))                        # one tile per CTA
+            if pl["kernel"] == 9:       # DOTP: fibers of two 4- / 8-byte elements, vectors of whole fibers, nothing shared
+                assert inner == 1 and nq == 2 and size[dt] <= 8 and pl["vec"] == 16 // size[dt] and pl["ku"] in (4, 8) and pl["smem_bytes"] == 0 and pl["ksplit"] == 1
+                assert pl["ctas"] == max(1, -(-(outer * 2 * size[dt] // 16) // (256 * pl["ku"])))          # one tile per CTA
                 continue
-            if pl["kernel"] == 10:      # COLF: narrow / odd rows as a flat stream of super-rows, a warp per slab (partition)
+            if pl["kernel"] == 10:      # COLF: narrow / odd rows as a flat stream of super-rows, a warp per slab (partition) or several short slabs per warp
                 vec = 16 // size[dt]
                 g = math.gcd(inner, vec)
-                assert inner > 1 and g < vec and inner // g <= 32 and (nq % (vec // g) == 0 or outer == 1) and nq * inner * size[dt] >= 1024
-                assert (pl["tx"], pl["ty"], pl["to"]) == (inner // g, 32 // (inner // g), vec // g) and pl["smem_bytes"] == 4096
-                assert pl["ksplit"] >= 1 and pl["ctas"] == -(-outer * pl["ksplit"] // 8) and pl["workspace_bytes"] == (pl["ksplit"] > 1) * pl["ksplit"] * outer * inner * size[dt]
+                L, R = inner // g, vec // g
+                assert inner > 1 and g < vec and L <= 32 and (nq % R == 0 or outer == 1) and nq * inner * size[dt] >= 256
+                assert (pl["tx"], pl["to"]) == (L, R) and 1 <= pl["ty"] <= 32 // L and pl["nu"] * pl["ty"] * L <= 32 and pl["smem_bytes"] == 4096
+                assert pl["nu"] == 1 or (pl["ksplit"] == 1 and pl["ty"] <= max(1, nq // R // 8))         # several slabs per warp: short slabs only
+                groups = -(-outer // pl["nu"])
+                assert pl["ksplit"] >= 1 and pl["ctas"] == min(-(-groups * pl["ksplit"] // 8), 148 * (4 if size[dt] == 8 else 6))
+                assert pl["workspace_bytes"] == (pl["ksplit"] > 1) * pl["ksplit"] * outer * inner * size[dt]
                 continue
             if pl["kernel"] == 8:       # STREAMK: rows of a few elements under a long contraction, staged through shared memory
                 assert 1 < inner <= 16 and inner * size[dt] <= 64 and inner % (16 // size[dt]) != 0 and nq >= 4096

@@ -902,21 +902,20 @@ def test_colt_kernel_tma_tensor_tiles(dtype, oracle, monkeypatch):
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.int32, np.int64])
 def test_dotp_kernel_fibers_of_two_elements(dtype, oracle, monkeypatch):
     """kernel="dotp": n_q = 2 with q the contiguous mode (dotp_kernel.cuh).  Even and odd numbers of fibers (the half vector
-    at the end), fewer fibers than one vector / one tile / several tiles, both batch depths, accumulate; 4-byte types take it
-    on their own, 16-byte elements are refused."""
+    at the end), fewer fibers than one vector / one tile / several tiles, both batch depths, accumulate; 16-byte elements
+    are refused."""
     rng = np.random.default_rng(31)
     dt = np.dtype(dtype)
     name = {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64", np.dtype(np.complex64): "c64", np.dtype(np.int32): "i32", np.dtype(np.int64): "i64"}[dt]
     cases = [((2, 1), (1, 2), 1), ((2, 2), (1, 2), 1), ((2, 3), (1, 2), 1), ((2, 1001), (1, 2), 1), ((2, 4096), (1, 2), 1), ((2, 2048 * 3 + 5), (1, 2), 1),
              ((7, 2, 11), (2, 1, 3), 2), ((5, 3, 2, 9), (3, 2, 1, 4), 3), ((2, 70001), (1, 2), 1), ((33, 2), (2, 1), 2)]
-    for ku, warp in (("8", "0"), ("4", "0"), ("8", "1")):
+    for ku in ("8", "4"):
         monkeypatch.setenv("TTV_B200_DOTP_KU", ku)
-        monkeypatch.setenv("TTV_B200_DOTP_WARP", warp)
         for na, pia, q in cases:
             a, b = random_case(rng, na, q, dtype)
             want = oracle.ttv(q, a, na, pia, b)
             assert ttv_b200.plan(q, na, pia, dtype=name, kernel="dotp")["kernel"] == 9
-            assert (ttv_b200.plan(q, na, pia, dtype=name)["kernel"] == 9) == (dt.itemsize == 4)
+            assert ttv_b200.plan(q, na, pia, dtype=name)["kernel"] == 9
             assert np.array_equal(run_lowlevel(q, a, na, pia, b, kernel="dotp"), want), (na, pia, q, dtype, ku)
             assert np.array_equal(run_lowlevel(q, a, na, pia, b), want), (na, pia, q, dtype, ku)
             c0 = np.full(want.size, 3, dtype)
@@ -932,8 +931,8 @@ def test_colf_kernel_rows_that_are_not_whole_vectors(dtype, oracle, monkeypatch)
     """kernel="colf": rows narrower than / not a multiple of a 16-byte vector, streamed flat as super-rows of V / gcd(inner, V)
     rows, a warp per slab or slab partition (colf_kernel.cuh).  Every gcd class (super-rows of 2 and 4 rows), one to 31
     vectors per super-row, contractions shorter than a super-row / a batch / several batches, rows past the last whole
-    super-row (single slab only), several slabs, n_q split across warps (chosen and forced), accumulate; taken on its own
-    from 1 KB per slab."""
+    super-row (single slab only), several slabs, n_q split across warps (chosen and forced), short slabs side by side in one
+    warp (with a last, partly filled group of slabs), accumulate; taken on its own from 256 bytes per slab."""
     rng = np.random.default_rng(37)
     dt = np.dtype(dtype)
     name = {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64", np.dtype(np.complex64): "c64", np.dtype(np.int32): "i32", np.dtype(np.int64): "i64"}[dt]
@@ -952,7 +951,7 @@ def test_colf_kernel_rows_that_are_not_whole_vectors(dtype, oracle, monkeypatch)
             assert np.array_equal(run_lowlevel(q, a, na, pia, b, kernel="colf", ksplit=ks), want), (na, pia, q, dtype, ks)
         c0 = np.full(want.size, 3, dtype)
         assert np.array_equal(run_lowlevel(q, a, na, pia, b, c0=c0, kernel="colf", flags=1), want + 3)
-    for na in ((3, 4 * 6000, 2), (3, 4 * 30, 700), (2 if vec == 4 else 3, 256, 3000)):
+    for na in ((3, 4 * 6000, 2), (3, 4 * 30, 701), (2 if vec == 4 else 3, 256, 3000), (5, 64, 1001), (3, 32, 777), (2 if vec == 4 else 7, 16, 5003)):
         assert ttv_b200.plan(2, na, (1, 2, 3), dtype=name)["kernel"] == 10
         a, b = random_case(rng, na, 2, dtype)
         assert np.array_equal(run_lowlevel(2, a, na, (1, 2, 3), b), oracle.ttv(2, a, na, (1, 2, 3), b)), na

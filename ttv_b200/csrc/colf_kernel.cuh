@@ -14,6 +14,10 @@
 // j < L hold a partial matrix [R][inner] (flat index V j + e), which goes through a warp-private strip of shared memory to
 // be folded over its R rows.  No CTA-wide synchronisation anywhere.  A contraction cut across warps (ksplit) goes to the
 // workspace [ksplit][outer * inner] and is finished by ttv_reduce_kernel / ttv_reduce_wide_kernel in fixed order.
+// SHORT slabs (a few hundred bytes to a few KB: n = (2, 128, 2^21), (5, 64, 2^20)) would leave a lane with one or two
+// loads and the warp with a shuffle tree per slab; there a warp works on SW slabs side by side, G = TY L lanes each, TY
+// chosen so that a lane still has a batch of loads: the slabs are contiguous, so the warp keeps reading one contiguous
+// run, the tree shrinks to log2(TY) levels, and the SW x inner outputs of the item are one contiguous run of C.
 #pragma once
 
 #include "kernels.cuh"
@@ -27,13 +31,15 @@ struct ColfParams {
   uint64_t outer, nq, inner;
   uint64_t srchunk;         // super-rows per partition
   uint32_t ksplit;
-  uint32_t R, L, TY;        // rows / vectors per super-row, super-rows per step of a warp (TY * L <= 32 lanes work)
+  uint32_t R, L, TY;        // rows / vectors per super-row, super-rows per step of a lane group (G = TY * L lanes per slab)
+  uint32_t SW;              // slabs a warp works on side by side: SW * G <= 32 (SW > 1 only with ksplit == 1)
+  uint32_t stream;          // 1: L1::no_allocate loads (a lane group reads at least a 128-byte line per step)
   uint32_t accumulate;      // only honoured when ksplit == 1
 };
 
 template<class T, int KU, bool PRED>
 __device__ __forceinline__ void colf_batch(T (&acc)[16 / sizeof(T)], const T* ap, const T* blo, const T* bhi, uint64_t astep, uint64_t bstep,
-                                           uint64_t sr, uint64_t step, uint64_t n, uint32_t sp)
+                                           uint64_t sr, uint64_t step, uint64_t n, uint32_t sp, bool stream)
 {
   constexpr int V = 16 / (int)sizeof(T);
   Vec<T, V> x[KU];
@@ -42,11 +48,11 @@ __device__ __forceinline__ void colf_batch(T (&acc)[16 / sizeof(T)], const T* ap
   for (int s = 0; s < KU; ++s) {
     if constexpr (PRED) {
       const bool ok = sr + s * step < n;
-      x[s]  = ok ? load_a<T, V>(ap + s * astep, true) : zero_vec<T, V>();
+      x[s]  = ok ? load_a<T, V>(ap + s * astep, stream) : zero_vec<T, V>();
       lo[s] = ok ? blo[s * bstep] : Num<T>::zero();
       hi[s] = ok ? bhi[s * bstep] : Num<T>::zero();
     } else {
-      x[s]  = load_a<T, V>(ap + s * astep, true);
+      x[s]  = load_a<T, V>(ap + s * astep, stream);
       lo[s] = blo[s * bstep];
       hi[s] = bhi[s * bstep];
     }
@@ -64,7 +70,7 @@ ttv_colf_kernel(const ColfParams P)
 {
   pdl_prologue();
   constexpr int V = 16 / (int)sizeof(T);
-  __shared__ T strips[8][32 * V];                                   // per warp: the partial matrix [R][inner], L * V <= 32 V cells
+  __shared__ T strips[8][32 * V];                                   // per warp: SW partial matrices [R][inner] of L * V cells each
 
   const T* __restrict__ A = static_cast<const T*>(P.a);
   const T* __restrict__ B = static_cast<const T*>(P.b);
@@ -72,41 +78,45 @@ ttv_colf_kernel(const ColfParams P)
 
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t inner = (uint32_t)P.inner;
-  const uint32_t j  = lane % P.L;
-  const uint32_t ty = lane / P.L;
-  const bool live = ty < P.TY;
+  const uint32_t G  = P.TY * P.L;                                   // lanes of one slab
+  const uint32_t g  = lane / G, t = lane % G;                       // slab of the item, lane inside its group
+  const uint32_t j  = t % P.L;
+  const uint32_t ty = t / P.L;
   const uint32_t r0  = (V * j) / inner;                             // row of the vector's first element inside the super-row
   const uint32_t sp  = min((uint32_t)V, (r0 + 1) * inner - V * j);  // elements of the vector that lie in row r0
   const uint32_t rhi = min(r0 + 1, P.R - 1);
+  const bool stream = P.stream != 0;
   T* strip = strips[warp];
 
   const uint64_t nsr   = P.nq / P.R;                                // whole super-rows of a slab
-  const uint64_t astep = (uint64_t)P.TY * P.L * V, bstep = (uint64_t)P.TY * P.R;
-  const uint64_t items = P.outer * P.ksplit;
+  const uint64_t astep = (uint64_t)G * V, bstep = (uint64_t)P.TY * P.R;
+  const uint64_t ogroups = (P.outer + P.SW - 1) / P.SW;
+  const uint64_t items = ogroups * P.ksplit;
   uint32_t span = 1;
   while (span < P.TY) span <<= 1;
 
   for (uint64_t item = (uint64_t)blockIdx.x * 8 + warp; item < items; item += (uint64_t)gridDim.x * 8) {
-    const uint64_t o  = item / P.ksplit;
+    const uint64_t o0 = (item / P.ksplit) * P.SW;                   // first slab of the item
     const uint32_t ks = (uint32_t)(item % P.ksplit);
     const uint64_t srbeg = min((uint64_t)ks * P.srchunk, nsr), srend = min(srbeg + P.srchunk, nsr);
     const uint64_t n = srend - srbeg;
+    const uint64_t o = o0 + g;
 
     T acc[V];
 #pragma unroll
     for (int e = 0; e < V; ++e) acc[e] = Num<T>::zero();
 
-    if (live) {
-      const T* ap  = A + (o * P.nq + srbeg * P.R) * inner + (uint64_t)lane * V;
+    if (g < P.SW && o < P.outer) {
+      const T* ap  = A + (o * P.nq + srbeg * P.R) * inner + (uint64_t)t * V;
       const T* blo = B + (srbeg + ty) * P.R + r0;
       const T* bhi = B + (srbeg + ty) * P.R + rhi;
       uint64_t sr = ty;
       for (; sr + (uint64_t)(KU - 1) * P.TY < n; sr += (uint64_t)KU * P.TY, ap += KU * astep, blo += KU * bstep, bhi += KU * bstep)
-        colf_batch<T, KU, false>(acc, ap, blo, bhi, astep, bstep, sr, P.TY, n, sp);
-      if (sr < n) colf_batch<T, KU, true>(acc, ap, blo, bhi, astep, bstep, sr, P.TY, n, sp);
+        colf_batch<T, KU, false>(acc, ap, blo, bhi, astep, bstep, sr, P.TY, n, sp, stream);
+      if (sr < n) colf_batch<T, KU, true>(acc, ap, blo, bhi, astep, bstep, sr, P.TY, n, sp, stream);
     }
 
-    // lanes of one phase j: rows ty + h are folded onto ty (lanes past the working ones hold zeros and are never a source)
+    // lanes of one phase j of one slab: rows ty + h are folded onto ty (a source lane lies inside the same group)
     for (uint32_t h = span >> 1; h > 0; h >>= 1) {
 #pragma unroll
       for (int e = 0; e < V; ++e) {
@@ -114,18 +124,22 @@ ttv_colf_kernel(const ColfParams P)
         if (ty < h && ty + h < P.TY) acc[e] = Num<T>::add(acc[e], other);
       }
     }
-    if (lane < P.L) {
+    if (g < P.SW && t < P.L) {
 #pragma unroll
-      for (int e = 0; e < V; ++e) strip[V * lane + e] = acc[e];
+      for (int e = 0; e < V; ++e) strip[(g * P.L + t) * V + e] = acc[e];
     }
     __syncwarp();
-    for (uint32_t c = lane; c < inner; c += 32) {
-      T val = strip[c];
-      for (uint32_t r = 1; r < P.R; ++r) val = Num<T>::add(val, strip[c + r * inner]);
+    // the outputs of the item's slabs are one contiguous run of C
+    const uint32_t slabs = (uint32_t)min((uint64_t)P.SW, P.outer - o0);
+    for (uint32_t idx = lane; idx < slabs * inner; idx += 32) {
+      const uint32_t gg = idx / inner, c = idx % inner;
+      const T* m = strip + gg * P.L * V;
+      T val = m[c];
+      for (uint32_t r = 1; r < P.R; ++r) val = Num<T>::add(val, m[c + r * inner]);
       if (ks + 1 == P.ksplit) {                                     // rows past the last whole super-row (only when outer == 1)
-        for (uint64_t r = nsr * P.R; r < P.nq; ++r) val = Num<T>::madd(A[(o * P.nq + r) * inner + c], B[r], val);
+        for (uint64_t r = nsr * P.R; r < P.nq; ++r) val = Num<T>::madd(A[((o0 + gg) * P.nq + r) * inner + c], B[r], val);
       }
-      T* out = C + ((P.ksplit > 1 ? (uint64_t)ks * P.outer : 0) + o) * inner + c;
+      T* out = C + ((P.ksplit > 1 ? (uint64_t)ks * P.outer : 0) + o0) * inner + idx;
       *out = (P.accumulate && P.ksplit == 1) ? Num<T>::add(*out, val) : val;
     }
     __syncwarp();                                                   // the strip is rewritten by the next item

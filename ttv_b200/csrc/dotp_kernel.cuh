@@ -6,8 +6,10 @@
 // 16-byte vector, a third of the traffic is the WRITE of C, and there is nothing to reduce across threads: a 16-byte vector
 // of A holds whole fibers, so a lane loads consecutive vectors (a warp reads 512 contiguous bytes per instruction, KU of them
 // in flight per lane), multiplies by the two elements of b it keeps in registers and stores the 8 bytes of C that belong to
-// its vector (a warp writes 256 contiguous bytes per instruction).  No shared memory, no synchronisation.
-// STREAM ran this shape through shared memory at 6 311-6 430 GB/s.
+// its vector (a warp writes 256 contiguous bytes per instruction).  No shared memory, no synchronisation, ONE tile of
+// 256 x KU vectors per CTA: CTAs striding over the tiles measured 6 432-6 478 GB/s on [1610612736, 2, 1], a CTA per tile
+// 7 002-7 060 (STREAM through shared memory: 6 311-6 539; 8-byte types 6 957-6 970 against DOTF's 6 689-6 738).  Swapping
+// halves between neighbouring lanes for 16-byte stores measured slower (6 692) and is gone.
 #pragma once
 
 #include "numeric.cuh"
@@ -24,10 +26,7 @@ struct DotpParams {
   uint32_t accumulate;
 };
 
-// WARPC: a warp owns KU * 32 CONSECUTIVE vectors of a tile (KU loads of 512 contiguous bytes, 2 KB of C in one run) and
-// neighbouring lanes swap halves, so that every store is 16 bytes wide; otherwise vector j of a thread lies 256 vectors
-// behind vector j - 1 and a lane stores the 8 bytes of each of its vectors.
-template<class T, int KU, bool WARPC>
+template<class T, int KU>
 __global__ void __launch_bounds__(256)
 ttv_dotp_kernel(const DotpParams P)
 {
@@ -58,44 +57,10 @@ ttv_dotp_kernel(const DotpParams P)
     const uint64_t v0 = tile * (uint64_t)(256 * KU) + threadIdx.x;
     VA x[KU];
     if (v0 - threadIdx.x + (uint64_t)(256 * KU) <= P.nvec) {
-      if constexpr (WARPC) {
-        static_assert(KU % 2 == 0, "pairs of vectors");
-        const uint32_t lane = threadIdx.x & 31u;
-        const uint64_t w0 = tile * (uint64_t)(256 * KU) + (uint64_t)(threadIdx.x >> 5) * (32 * KU);      // first vector of the warp
 #pragma unroll
-        for (int j = 0; j < KU; ++j) x[j] = load_stream<T, V>(A + (w0 + (uint64_t)j * 32 + lane) * V);
-        VC y[KU];
+      for (int j = 0; j < KU; ++j) x[j] = load_stream<T, V>(A + (v0 + (uint64_t)j * 256) * V);
 #pragma unroll
-        for (int j = 0; j < KU; ++j)
-#pragma unroll
-          for (int i = 0; i < OV; ++i) y[j].e[i] = Num<T>::madd(x[j].e[2 * i + 1], b1, Num<T>::madd(x[j].e[2 * i], b0, Num<T>::zero()));
-#pragma unroll
-        for (int j = 0; j < KU; j += 2) {
-          // even lanes finish the pair (lane, lane + 1) of block j, odd lanes the pair (lane - 1, lane) of block j + 1
-          const bool odd = lane & 1u;
-          VC give = odd ? y[j] : y[j + 1], got;
-          uint32_t w[2];
-          memcpy(w, &give, 8);
-          w[0] = __shfl_xor_sync(0xffffffffu, w[0], 1);
-          w[1] = __shfl_xor_sync(0xffffffffu, w[1], 1);
-          memcpy(&got, w, 8);
-          Vec<T, 2 * OV> z;
-#pragma unroll
-          for (int i = 0; i < OV; ++i) { z.e[i] = odd ? got.e[i] : y[j].e[i]; z.e[OV + i] = odd ? y[j + 1].e[i] : got.e[i]; }
-          Vec<T, 2 * OV>* out = reinterpret_cast<Vec<T, 2 * OV>*>(C + (w0 + (uint64_t)(odd ? j + 1 : j) * 32 + (lane & ~1u)) * OV);
-          if (P.accumulate) {
-            const Vec<T, 2 * OV> old = *out;
-#pragma unroll
-            for (int i = 0; i < 2 * OV; ++i) z.e[i] = Num<T>::add(old.e[i], z.e[i]);
-          }
-          *out = z;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < KU; ++j) x[j] = load_stream<T, V>(A + (v0 + (uint64_t)j * 256) * V);
-#pragma unroll
-        for (int j = 0; j < KU; ++j) product(x[j], v0 + (uint64_t)j * 256);
-      }
+      for (int j = 0; j < KU; ++j) product(x[j], v0 + (uint64_t)j * 256);
     } else {
 #pragma unroll
       for (int j = 0; j < KU; ++j)

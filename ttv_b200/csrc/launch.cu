@@ -200,7 +200,7 @@ cudaError_t launch_view(int dtype, const View& v, const Launch& l, const void* a
     F.a = a; F.b = b; F.c = l.ksplit > 1 ? workspace : c;
     F.outer = v.outer; F.nq = v.nq; F.inner = v.inner;
     F.srchunk = l.kchunk / l.to;                                     // l.to carries R, the rows of a super-row
-    F.ksplit = l.ksplit; F.R = l.to; F.L = l.tx; F.TY = l.ty;
+    F.ksplit = l.ksplit; F.R = l.to; F.L = l.tx; F.TY = l.ty; F.SW = l.nu; F.stream = l.stream;
     F.accumulate = (accumulate && l.ksplit == 1) ? 1u : 0u;
     cudaError_t e = k_colf[dtype](F, l, stream);
     if (e != cudaSuccess || l.ksplit <= 1) return e;
@@ -641,9 +641,8 @@ cudaError_t TTVB_CAT(colf_dtype_, TTVB_DTYPE)(const ColfParams& F, const Launch&
 cudaError_t TTVB_CAT(dotp_dtype_, TTVB_DTYPE)(const DotpParams& D, const Launch& l, cudaStream_t stream)
 {
   if constexpr (sizeof(elem_t) <= 8) {
-    if (l.nu == 2) return launch_k(ttv_dotp_kernel<elem_t, 8, true>, (unsigned)l.ctas, 256u, 0, stream, D);   // warp-contiguous, 16-byte stores
-    if (l.ku == 4) return launch_k(ttv_dotp_kernel<elem_t, 4, false>, (unsigned)l.ctas, 256u, 0, stream, D);
-    return launch_k(ttv_dotp_kernel<elem_t, 8, false>, (unsigned)l.ctas, 256u, 0, stream, D);
+    if (l.ku == 4) return launch_k(ttv_dotp_kernel<elem_t, 4>, (unsigned)l.ctas, 256u, 0, stream, D);
+    return launch_k(ttv_dotp_kernel<elem_t, 8>, (unsigned)l.ctas, 256u, 0, stream, D);
   } else {
     (void)D; (void)l; (void)stream;
     return cudaErrorInvalidValue;                                    // a fiber of two 16-byte elements is two vectors: DOTF

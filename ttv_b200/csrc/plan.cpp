@@ -468,7 +468,8 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
     }
   }
   // DOTP: fibers of two elements of 4 or 8 bytes (dotp_kernel.cuh): whole fibers per 16-byte vector, b in registers, one
-  // 8-byte store per vector, nothing shared.  STREAM took the 4-byte shapes before ([1610612736, 2, 1]: 6 311-6 389 GB/s).
+  // 8-byte store per vector, nothing shared.  STREAM took the 4-byte shapes before ([1610612736, 2, 1]: 6 311-6 539 GB/s,
+  // now 7 002-7 060), DOTF the 8-byte ones ([536870912, 2, 1] fp64 6 738 -> 6 970) -- tools/probe/tiny_inner.py.
   {
     const bool eligible = v.inner == 1 && v.nq == 2 && s <= 8 && (align_a % 16) == 0 && (align_c % 8) == 0 && (!opts || opts->ksplit <= 1) &&
                           !(flags & TTV_B200_FLAG_NO_VEC);
@@ -478,13 +479,12 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
                     : forced != 0 ? false
                     : mode == 1 ? eligible
                     : mode == 0 ? false
-                    : (eligible && s == 4);
+                    : eligible;
     if (pick) {
       l.kernel = TTV_B200_KERNEL_DOTP;
       l.threads = 256;
       l.vec = (int)(16 / s); l.tx = 1; l.ty = 1; l.to = 256; l.nu = 1; l.stream = 1; l.udir = 0; l.ksplit = 1;
       l.ku = env_int("TTV_B200_DOTP_KU", 8) == 4 ? 4 : 8;
-      if (env_int("TTV_B200_DOTP_WARP", 0) == 1 && (align_c % 16) == 0) { l.nu = 2; l.ku = 8; }             // warp-contiguous form with 16-byte stores
       const uint64_t nvec = v.outer * 2 * s / 16;
       l.tiles = std::max<uint64_t>(1, ceil_div(nvec, 256ull * (uint64_t)l.ku));
       // one tile per CTA: measured 6 432 (64 CTAs per SM striding over the tiles) -> 7 000 GB/s on [1610612736, 2, 1]
@@ -582,27 +582,48 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
                     : forced != 0 ? false
                     : mode == 1 ? eligible
                     : mode == 0 ? false
-                    : (eligible && v.nq * v.inner * s >= (uint64_t)env_int("TTV_B200_COLF_MIN_SLAB_B", 1024));
+                    : (eligible && v.nq * v.inner * s >= (uint64_t)env_int("TTV_B200_COLF_MIN_SLAB_B", 256));
     if (pick) {
       constexpr uint64_t KUf = 8;
       l.kernel = TTV_B200_KERNEL_COLF;
       l.threads = 256;
-      l.vec = (int)Vf; l.tx = (uint32_t)L; l.ty = (uint32_t)(32 / L); l.to = (uint32_t)R; l.nu = 1; l.ku = (int)KUf; l.stream = 1; l.udir = 0;
-      const uint64_t nsr = v.nq / R, batch = (uint64_t)l.ty * KUf;   // super-rows of a slab / of one batch of a warp
+      const uint64_t nsr = v.nq / R, ty_max = 32 / L;                // super-rows of a slab; lanes per phase when a warp has one slab
       int want = opts ? opts->ksplit : 0;
       if (want < 0) return TTV_B200_ERR_OPTS;
       if (want == 0) want = env_int("TTV_B200_KSPLIT", 0);
-      // a work item (slab, partition) per warp: enough of them for several rounds of the 24 warps an SM holds, at least
-      // four batches per partition
-      uint64_t ksplit = want > 0 ? (uint64_t)want : ceil_div(sms * (uint64_t)env_int("TTV_B200_COLF_ITEMS_PER_SM", 96), v.outer);
-      if (want <= 0) ksplit = std::min(ksplit, std::max<uint64_t>(1, nsr / (batch * 4)));
-      ksplit = std::max<uint64_t>(1, std::min(ksplit, std::max<uint64_t>(1, nsr)));
-      uint64_t srchunk = ceil_div(std::max<uint64_t>(1, ceil_div(nsr, ksplit)), batch) * batch;
-      ksplit = std::max<uint64_t>(1, ceil_div(nsr, srchunk));
+      // short slabs: fewer lanes per slab, so that a lane still has a batch of loads, and several slabs side by side in a warp
+      uint64_t ty = want > 1 ? ty_max : std::min(ty_max, std::max<uint64_t>(1, nsr / KUf));
+      const uint64_t sw = ty < ty_max ? 32 / (ty * L) : 1;
+      if (sw == 1) ty = ty_max;
+      l.vec = (int)Vf; l.tx = (uint32_t)L; l.ty = (uint32_t)ty; l.to = (uint32_t)R; l.nu = (int)sw; l.ku = (int)KUf; l.udir = 0;
+      l.stream = ty * L * 16 >= 128 ? 1 : 0;                         // lane groups narrower than a line reuse it from L1
+      const uint64_t batch = ty * KUf;                               // super-rows of one batch of a lane group
+      // persistent warps striding over the items (slab group, partition): twice the CTAs an SM holds
+      const uint64_t resident = s == 8 ? 2 : 3;
+      const uint64_t max_ctas = sms * (uint64_t)std::max(1, env_int("TTV_B200_COLF_CTAS", (int)(2 * resident)));
+      const uint64_t vslots = max_ctas * 8;
+      const uint64_t ogroups = ceil_div(v.outer, sw);
+      // n_q split: ~16 items per warp so that the last, partly filled round costs little, at least four batches per
+      // partition; among the candidates the one whose item count fills its rounds best
+      uint64_t ksplit = 1;
+      auto parts = [&](uint64_t ks) { const uint64_t chunk = ceil_div(std::max<uint64_t>(1, ceil_div(nsr, ks)), batch) * batch; return std::max<uint64_t>(1, ceil_div(nsr, chunk)); };
+      if (want > 0) ksplit = parts(std::min<uint64_t>((uint64_t)want, std::max<uint64_t>(1, nsr)));
+      else if (sw == 1) {
+        const uint64_t hi = std::max<uint64_t>(1, std::min(ceil_div(vslots * (uint64_t)env_int("TTV_B200_COLF_ITEMS_PER_WARP", 8), ogroups), std::max<uint64_t>(1, nsr / (batch * 4))));
+        double best = -1.0;
+        for (uint64_t ks = hi; ks >= std::max<uint64_t>(1, hi / 2); --ks) {
+          const uint64_t k2 = parts(ks);
+          const double x = (double)(ogroups * k2) / (double)vslots, eff = x / (double)ceil_div(ogroups * k2, vslots);
+          if (eff > best + 1e-9) { best = eff; ksplit = k2; }
+          if (ks == 1) break;
+          (void)x;
+        }
+      }
+      const uint64_t srchunk = ceil_div(std::max<uint64_t>(1, ceil_div(nsr, ksplit)), batch) * batch;
       l.ksplit = (uint32_t)ksplit; l.kchunk = srchunk * R;
-      l.itiles = 1; l.otiles = v.outer;
-      l.tiles = v.outer * ksplit;
-      l.ctas = std::min<uint64_t>(ceil_div(l.tiles, 8), std::min<uint64_t>(0x7fffffffull, sms * (uint64_t)std::max(1, env_int("TTV_B200_COLF_CTAS", 1 << 20))));
+      l.itiles = 1; l.otiles = ogroups;
+      l.tiles = ogroups * ksplit;
+      l.ctas = std::min<uint64_t>(ceil_div(l.tiles, 8), max_ctas);
       l.kb = 0;
       l.smem_bytes = 8 * 32 * 16;                                    // static: a strip of 32 vectors per warp
       l.workspace_bytes = ksplit > 1 ? ksplit * v.outer * v.inner * s : 0;
