@@ -951,7 +951,7 @@ def test_colf_kernel_rows_that_are_not_whole_vectors(dtype, oracle, monkeypatch)
             assert np.array_equal(run_lowlevel(q, a, na, pia, b, kernel="colf", ksplit=ks), want), (na, pia, q, dtype, ks)
         c0 = np.full(want.size, 3, dtype)
         assert np.array_equal(run_lowlevel(q, a, na, pia, b, c0=c0, kernel="colf", flags=1), want + 3)
-    for na in ((3, 4 * 6000, 2), (3, 4 * 30, 701), (2 if vec == 4 else 3, 256, 3000), (5, 64, 1001), (3, 32, 777), (2 if vec == 4 else 7, 16, 5003)):
+    for na in ((3, 4 * 6000, 2), (3, 4 * 30, 701), (2 if vec == 4 else 3, 256, 3000), (5, 64, 1001), (3, 32, 777), (2 if vec == 4 else 7, 32, 5003)):
         assert ttv_b200.plan(2, na, (1, 2, 3), dtype=name)["kernel"] == 10
         a, b = random_case(rng, na, 2, dtype)
         assert np.array_equal(run_lowlevel(2, a, na, (1, 2, 3), b), oracle.ttv(2, a, na, (1, 2, 3), b)), na

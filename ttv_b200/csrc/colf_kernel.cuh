@@ -33,13 +33,12 @@ struct ColfParams {
   uint32_t ksplit;
   uint32_t R, L, TY;        // rows / vectors per super-row, super-rows per step of a lane group (G = TY * L lanes per slab)
   uint32_t SW;              // slabs a warp works on side by side: SW * G <= 32 (SW > 1 only with ksplit == 1)
-  uint32_t stream;          // 1: L1::no_allocate loads (a lane group reads at least a 128-byte line per step)
   uint32_t accumulate;      // only honoured when ksplit == 1
 };
 
-template<class T, int KU, bool PRED>
+template<class T, int KU, bool PRED, bool NA>
 __device__ __forceinline__ void colf_batch(T (&acc)[16 / sizeof(T)], const T* ap, const T* blo, const T* bhi, uint64_t astep, uint64_t bstep,
-                                           uint64_t sr, uint64_t step, uint64_t n, uint32_t sp, bool stream)
+                                           uint64_t sr, uint64_t step, uint64_t n, uint32_t sp)
 {
   constexpr int V = 16 / (int)sizeof(T);
   Vec<T, V> x[KU];
@@ -48,11 +47,11 @@ __device__ __forceinline__ void colf_batch(T (&acc)[16 / sizeof(T)], const T* ap
   for (int s = 0; s < KU; ++s) {
     if constexpr (PRED) {
       const bool ok = sr + s * step < n;
-      x[s]  = ok ? load_a<T, V>(ap + s * astep, stream) : zero_vec<T, V>();
+      ld16_if<NA>(&x[s], ap + s * astep, ok);
       lo[s] = ok ? blo[s * bstep] : Num<T>::zero();
       hi[s] = ok ? bhi[s * bstep] : Num<T>::zero();
     } else {
-      x[s]  = load_a<T, V>(ap + s * astep, stream);
+      x[s]  = load_a<T, V>(ap + s * astep, NA);
       lo[s] = blo[s * bstep];
       hi[s] = bhi[s * bstep];
     }
@@ -64,7 +63,8 @@ __device__ __forceinline__ void colf_batch(T (&acc)[16 / sizeof(T)], const T* ap
 }
 
 // (8-byte elements: the KU vectors of A and the 2 KU elements of b of a batch are 64 registers; two CTAs per SM, no spills)
-template<class T, int KU>
+// NA: L1::no_allocate loads -- a lane group reads at least a 128-byte line per step; narrower groups reuse the line from L1.
+template<class T, int KU, bool NA>
 __global__ void __launch_bounds__(256, sizeof(T) == 8 ? 2 : 3)
 ttv_colf_kernel(const ColfParams P)
 {
@@ -85,7 +85,6 @@ ttv_colf_kernel(const ColfParams P)
   const uint32_t r0  = (V * j) / inner;                             // row of the vector's first element inside the super-row
   const uint32_t sp  = min((uint32_t)V, (r0 + 1) * inner - V * j);  // elements of the vector that lie in row r0
   const uint32_t rhi = min(r0 + 1, P.R - 1);
-  const bool stream = P.stream != 0;
   T* strip = strips[warp];
 
   const uint64_t nsr   = P.nq / P.R;                                // whole super-rows of a slab
@@ -112,8 +111,8 @@ ttv_colf_kernel(const ColfParams P)
       const T* bhi = B + (srbeg + ty) * P.R + rhi;
       uint64_t sr = ty;
       for (; sr + (uint64_t)(KU - 1) * P.TY < n; sr += (uint64_t)KU * P.TY, ap += KU * astep, blo += KU * bstep, bhi += KU * bstep)
-        colf_batch<T, KU, false>(acc, ap, blo, bhi, astep, bstep, sr, P.TY, n, sp, stream);
-      if (sr < n) colf_batch<T, KU, true>(acc, ap, blo, bhi, astep, bstep, sr, P.TY, n, sp, stream);
+        colf_batch<T, KU, false, NA>(acc, ap, blo, bhi, astep, bstep, sr, P.TY, n, sp);
+      if (sr < n) colf_batch<T, KU, true, NA>(acc, ap, blo, bhi, astep, bstep, sr, P.TY, n, sp);
     }
 
     // lanes of one phase j of one slab: rows ty + h are folded onto ty (a source lane lies inside the same group)

@@ -200,7 +200,7 @@ cudaError_t launch_view(int dtype, const View& v, const Launch& l, const void* a
     F.a = a; F.b = b; F.c = l.ksplit > 1 ? workspace : c;
     F.outer = v.outer; F.nq = v.nq; F.inner = v.inner;
     F.srchunk = l.kchunk / l.to;                                     // l.to carries R, the rows of a super-row
-    F.ksplit = l.ksplit; F.R = l.to; F.L = l.tx; F.TY = l.ty; F.SW = l.nu; F.stream = l.stream;
+    F.ksplit = l.ksplit; F.R = l.to; F.L = l.tx; F.TY = l.ty; F.SW = l.nu;
     F.accumulate = (accumulate && l.ksplit == 1) ? 1u : 0u;
     cudaError_t e = k_colf[dtype](F, l, stream);
     if (e != cudaSuccess || l.ksplit <= 1) return e;
@@ -631,7 +631,8 @@ cudaError_t TTVB_CAT(streamk_dtype_, TTVB_DTYPE)(const StreamkParams& K, const L
 cudaError_t TTVB_CAT(colf_dtype_, TTVB_DTYPE)(const ColfParams& F, const Launch& l, cudaStream_t stream)
 {
   if constexpr (sizeof(elem_t) <= 8) {
-    return launch_k(ttv_colf_kernel<elem_t, 8>, (unsigned)l.ctas, 256u, 0, stream, F);
+    if (l.stream) return launch_k(ttv_colf_kernel<elem_t, 8, true>, (unsigned)l.ctas, 256u, 0, stream, F);
+    return launch_k(ttv_colf_kernel<elem_t, 8, false>, (unsigned)l.ctas, 256u, 0, stream, F);
   } else {
     (void)F; (void)l; (void)stream;
     return cudaErrorInvalidValue;                                    // 16-byte elements: every row is whole vectors

@@ -93,6 +93,23 @@ template<> struct Ld<32> {
   }
 };
 
+// A 16-byte load under a predicate, zeros otherwise: one predicated instruction, no branch around the asm statement (a
+// batch whose loads are all conditional -- a slab shorter than the batch -- keeps them back to back).  NA: L1::no_allocate.
+template<bool NA>
+__device__ __forceinline__ void ld16_if(void* dst, const void* src, bool ok)
+{
+  uint32_t x, y, z, w;
+  if constexpr (NA)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\tmov.b32 %3, 0;\n\t"
+                 "@p ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
+                 : "=&r"(x), "=&r"(y), "=&r"(z), "=&r"(w) : "l"(src), "r"((uint32_t)ok));
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\tmov.b32 %3, 0;\n\t"
+                 "@p ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
+                 : "=&r"(x), "=&r"(y), "=&r"(z), "=&r"(w) : "l"(src), "r"((uint32_t)ok));
+  uint32_t* d = reinterpret_cast<uint32_t*>(dst); d[0] = x; d[1] = y; d[2] = z; d[3] = w;
+}
+
 template<class T, int V>
 __device__ __forceinline__ Vec<T, V> load_stream(const T* p) {
   Vec<T, V> v;

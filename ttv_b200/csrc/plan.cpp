@@ -603,13 +603,14 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
       const uint64_t max_ctas = sms * (uint64_t)std::max(1, env_int("TTV_B200_COLF_CTAS", (int)(2 * resident)));
       const uint64_t vslots = max_ctas * 8;
       const uint64_t ogroups = ceil_div(v.outer, sw);
-      // n_q split: ~16 items per warp so that the last, partly filled round costs little, at least four batches per
-      // partition; among the candidates the one whose item count fills its rounds best
+      // n_q split: up to four items per warp (more partitions measured slower: [64, 2^19, 7] 216 partitions 6 026, 820
+      // 5 784 GB/s -- the reduce pass is a second launch), at least four batches per partition; among the candidates
+      // the one whose item count fills its rounds best (a last round that is 4 % full costs a whole round)
       uint64_t ksplit = 1;
       auto parts = [&](uint64_t ks) { const uint64_t chunk = ceil_div(std::max<uint64_t>(1, ceil_div(nsr, ks)), batch) * batch; return std::max<uint64_t>(1, ceil_div(nsr, chunk)); };
       if (want > 0) ksplit = parts(std::min<uint64_t>((uint64_t)want, std::max<uint64_t>(1, nsr)));
       else if (sw == 1) {
-        const uint64_t hi = std::max<uint64_t>(1, std::min(ceil_div(vslots * (uint64_t)env_int("TTV_B200_COLF_ITEMS_PER_WARP", 8), ogroups), std::max<uint64_t>(1, nsr / (batch * 4))));
+        const uint64_t hi = std::max<uint64_t>(1, std::min(ceil_div(vslots * (uint64_t)env_int("TTV_B200_COLF_ITEMS_PER_WARP", 4), ogroups), std::max<uint64_t>(1, nsr / (batch * 4))));
         double best = -1.0;
         for (uint64_t ks = hi; ks >= std::max<uint64_t>(1, hi / 2); --ks) {
           const uint64_t k2 = parts(ks);
