@@ -2,7 +2,7 @@
 big-slab STREAM form, n_q split + direct b, 128-thread CTAs, the (1,16) deep batch, COLX / COLW, DOTF on 16-byte elements,
 the peeled DOT, fibers cut into pieces, ...).  Small shapes reach those kernel FAMILIES when forced, but not these exact
 plans; here every one of them runs on its BASELINE-sized tensor and sampled outputs are compared with a host long-double dot
-on regenerated fibers (ttv_b200/selfcheck.py; int32 bit-exact).  bench.py's sweep leg does the same for all 236 named
+on regenerated fibers (ttv_b200/selfcheck.py; int32 bit-exact).  bench.py's sweep leg does the same for all 252 named
 products; this is the subset that pins one product per chooser branch in the test suite.
 
 The reference's own grid only reaches extents {2,4,8}^p (test/src/gtest_tlib_ttv.cpp:192-425)."""
@@ -37,8 +37,12 @@ BRANCHES = [
     ("sym5d", "f64", 3, dict(kernel=4)),                                 # 73^5: COLX warp form below 48 rows per phase lane
     ("sym7d", "f64", 3, dict(kernel=3)),                                 # 21 x 441 doubles: 74 KB slab
     ("asym4", "i32", 2, None),                                           # int32 bit-exact on the asymmetric family
-    ("asym6", "i32", 3, dict(ksplit_gt=1)),                              # n_q = 2^20, inner 6: lanes along n_q, b direct from L2
-    ("asym10", "i32", 1, None),                                          # n_q = 2: half of the traffic is writes
+    ("asym6", "i32", 3, dict(kernel=10, ksplit_gt=1)),                   # n_q = 2^20, rows of 6: COLF, super-rows of two rows, n_q split over warps
+    ("asym7", "f32", 2, dict(kernel=10, ksplit_gt=1)),                   # rows of two floats under n_q = 2^17: COLF
+    ("asym5n", "f32", 2, dict(kernel=10, ksplit=1)),                     # 8 388 608 slabs of 128 x 2 floats: COLF, four slabs per warp
+    ("asym5n", "i32", 2, dict(kernel=10, ksplit=1)),
+    ("asym3n", "f32", 1, dict(kernel=9)),                                # DOTP: fibers of two floats
+    ("asym10", "i32", 1, dict(kernel=9)),                                # n_q = 2: a third of the traffic is writes
     ("asym10", "f32", 10, None),
     ("asym8", "f32", 2, None),
     ("cplx5", "c128", 5, dict(kernel=5)),                                # DOTF on 16-byte elements

@@ -303,7 +303,7 @@ def test_chooser_only_picks_instantiated_kernels():
                 vec = 16 // size[dt]
                 g = math.gcd(inner, vec)
                 L, R = inner // g, vec // g
-                assert inner > 1 and g < vec and L <= 32 and (nq % R == 0 or outer == 1) and nq * inner * size[dt] >= 256
+                assert inner > 1 and g < vec and L <= 32 and (nq % R == 0 or outer == 1) and nq * inner * size[dt] >= 128 and (size[dt] == 4 or L <= 8)
                 assert (pl["tx"], pl["to"]) == (L, R) and 1 <= pl["ty"] <= 32 // L and pl["nu"] * pl["ty"] * L <= 32 and pl["smem_bytes"] == 4096
                 assert pl["nu"] == 1 or (pl["ksplit"] == 1 and pl["ty"] <= max(1, nq // R // 8))         # several slabs per warp: short slabs only
                 groups = -(-outer // pl["nu"])

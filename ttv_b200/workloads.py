@@ -81,6 +81,9 @@ def configs(which: str):
             out += [("asym3", dt, [16, 1 << 12, 1 << 14], first(3), q) for q in (1, 2, 3)]
             out += [("asym7", dt, [2, 1 << 17, 2, 4, 2, 2, 64], first(7), q) for q in (1, 2, 4, 7)]
             out += [("asym9", dt, [2, 2, 1 << 14, 2, 2, 3, 2, 2, 256], first(9), q) for q in (1, 3, 6, 9)]
+            # leading extent 2 (rows of two elements when a later mode is contracted): large / small mode in second place
+            out += [("asym3n", dt, [2, 1 << 20, 512], first(3), q) for q in (1, 2, 3)]
+            out += [("asym5n", dt, [2, 128, 2, 2, 1 << 21], first(5), q) for q in (1, 2, 3, 4, 5)]
     if which in ("complex", "all", "named"):
         out += [("cplx4", "c64", [128] * 4, last(4), q) for q in (1, 2, 4)]
         out += [("cplx4r", "c64", [128] * 4, [3, 1, 4, 2], q) for q in (1, 2, 3, 4)]
