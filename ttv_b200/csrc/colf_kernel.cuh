@@ -42,30 +42,33 @@ __device__ __forceinline__ void colf_batch(T (&acc)[16 / sizeof(T)], const T* ap
 {
   constexpr int V = 16 / (int)sizeof(T);
   Vec<T, V> x[KU];
-  T lo[KU], hi[KU];
 #pragma unroll
   for (int s = 0; s < KU; ++s) {
+    if constexpr (PRED) ld16_if<NA>(&x[s], ap + s * astep, sr + s * step < n);
+    else                x[s] = load_a<T, V>(ap + s * astep, NA);
+  }
+  // the elements of b are L1 hits; they are fetched behind the vectors of A, as early as the register budget allows
+#pragma unroll
+  for (int s = 0; s < KU; ++s) {
+    T lo, hi;
     if constexpr (PRED) {
       const bool ok = sr + s * step < n;
-      ld16_if<NA>(&x[s], ap + s * astep, ok);
-      lo[s] = ok ? blo[s * bstep] : Num<T>::zero();
-      hi[s] = ok ? bhi[s * bstep] : Num<T>::zero();
+      lo = ok ? blo[s * bstep] : Num<T>::zero();
+      hi = ok ? bhi[s * bstep] : Num<T>::zero();
     } else {
-      x[s]  = load_a<T, V>(ap + s * astep, NA);
-      lo[s] = blo[s * bstep];
-      hi[s] = bhi[s * bstep];
+      lo = blo[s * bstep];
+      hi = bhi[s * bstep];
     }
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = Num<T>::madd(x[s].e[e], (uint32_t)e < sp ? lo : hi, acc[e]);
   }
-#pragma unroll
-  for (int s = 0; s < KU; ++s)
-#pragma unroll
-    for (int e = 0; e < V; ++e) acc[e] = Num<T>::madd(x[s].e[e], (uint32_t)e < sp ? lo[s] : hi[s], acc[e]);
 }
 
-// (8-byte elements: the KU vectors of A and the 2 KU elements of b of a batch are 64 registers; two CTAs per SM, no spills)
 // NA: L1::no_allocate loads -- a lane group reads at least a 128-byte line per step; narrower groups reuse the line from L1.
-template<class T, int KU, bool NA>
-__global__ void __launch_bounds__(256, sizeof(T) == 8 ? 2 : 3)
+// MINB: CTAs per SM the register budget is planned for (a warp works through its items one after the other, and between the
+// last load of an item and the first of the next lie the shuffle tree and the strip: more resident warps cover that).
+template<class T, int KU, bool NA, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 ttv_colf_kernel(const ColfParams P)
 {
   pdl_prologue();
