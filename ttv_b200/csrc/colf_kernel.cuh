@@ -42,38 +42,35 @@ __device__ __forceinline__ void colf_batch(T (&acc)[16 / sizeof(T)], const T* ap
 {
   constexpr int V = 16 / (int)sizeof(T);
   Vec<T, V> x[KU];
+  T lo[KU], hi[KU];
 #pragma unroll
   for (int s = 0; s < KU; ++s) {
-    if constexpr (PRED) ld16_if<NA>(&x[s], ap + s * astep, sr + s * step < n);
-    else                x[s] = load_a<T, V>(ap + s * astep, NA);
-  }
-  // the elements of b are L1 hits; they are fetched behind the vectors of A, as early as the register budget allows
-#pragma unroll
-  for (int s = 0; s < KU; ++s) {
-    T lo, hi;
     if constexpr (PRED) {
       const bool ok = sr + s * step < n;
-      lo = ok ? blo[s * bstep] : Num<T>::zero();
-      hi = ok ? bhi[s * bstep] : Num<T>::zero();
+      ld16_if<NA>(&x[s], ap + s * astep, ok);
+      lo[s] = ok ? blo[s * bstep] : Num<T>::zero();
+      hi[s] = ok ? bhi[s * bstep] : Num<T>::zero();
     } else {
-      lo = blo[s * bstep];
-      hi = bhi[s * bstep];
+      x[s]  = load_a<T, V>(ap + s * astep, NA);
+      lo[s] = blo[s * bstep];
+      hi[s] = bhi[s * bstep];
     }
-#pragma unroll
-    for (int e = 0; e < V; ++e) acc[e] = Num<T>::madd(x[s].e[e], (uint32_t)e < sp ? lo : hi, acc[e]);
   }
+#pragma unroll
+  for (int s = 0; s < KU; ++s)
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = Num<T>::madd(x[s].e[e], (uint32_t)e < sp ? lo[s] : hi[s], acc[e]);
 }
 
+// (8-byte elements: the KU vectors of A and the 2 KU elements of b of a batch are 64 registers; two CTAs per SM, no spills)
 // NA: L1::no_allocate loads -- a lane group reads at least a 128-byte line per step; narrower groups reuse the line from L1.
-// MINB: CTAs per SM the register budget is planned for (a warp works through its items one after the other, and between the
-// last load of an item and the first of the next lie the shuffle tree and the strip: more resident warps cover that).
-template<class T, int KU, bool NA, int MINB>
-__global__ void __launch_bounds__(256, MINB)
+template<class T, int KU, bool NA>
+__global__ void __launch_bounds__(256, sizeof(T) == 8 ? 2 : 3)
 ttv_colf_kernel(const ColfParams P)
 {
   pdl_prologue();
   constexpr int V = 16 / (int)sizeof(T);
-  __shared__ T strips[8][32 * V];                                   // per warp: SW partial matrices [R][inner] of L * V cells each
+  __shared__ __align__(16) T strips[8][32 * V];                                   // per warp: SW partial matrices [R][inner] of L * V cells each
 
   const T* __restrict__ A = static_cast<const T*>(P.a);
   const T* __restrict__ B = static_cast<const T*>(P.b);
@@ -97,9 +94,16 @@ ttv_colf_kernel(const ColfParams P)
   uint32_t span = 1;
   while (span < P.TY) span <<= 1;
 
+  // what does not change from item to item: the cell of the strip a lane writes, the output a lane finishes first
+  const bool holds_matrix = g < P.SW && t < P.L;                    // ty == 0: after the tree this lane holds V cells of [R][inner]
+  Vec<T, V>* my_cells = reinterpret_cast<Vec<T, V>*>(strip) + (g * P.L + t);
+  const uint32_t gg0 = lane / inner, c0 = lane % inner;             // output `lane` of an item: slab gg0, column c0
+  const bool single = P.ksplit == 1;                                // no partition index to divide out (every short slab)
+
   for (uint64_t item = (uint64_t)blockIdx.x * 8 + warp; item < items; item += (uint64_t)gridDim.x * 8) {
-    const uint64_t o0 = (item / P.ksplit) * P.SW;                   // first slab of the item
-    const uint32_t ks = (uint32_t)(item % P.ksplit);
+    const uint64_t og = single ? item : item / P.ksplit;
+    const uint32_t ks = single ? 0u : (uint32_t)(item - og * P.ksplit);
+    const uint64_t o0 = og * P.SW;                                  // first slab of the item
     const uint64_t srbeg = min((uint64_t)ks * P.srchunk, nsr), srend = min(srbeg + P.srchunk, nsr);
     const uint64_t n = srend - srbeg;
     const uint64_t o = o0 + g;
@@ -120,29 +124,32 @@ ttv_colf_kernel(const ColfParams P)
 
     // lanes of one phase j of one slab: rows ty + h are folded onto ty (a source lane lies inside the same group)
     for (uint32_t h = span >> 1; h > 0; h >>= 1) {
+      const bool take = ty < h && ty + h < P.TY;
 #pragma unroll
       for (int e = 0; e < V; ++e) {
         const T other = shfl_down_elem(acc[e], (int)(h * P.L));
-        if (ty < h && ty + h < P.TY) acc[e] = Num<T>::add(acc[e], other);
+        if (take) acc[e] = Num<T>::add(acc[e], other);
       }
     }
-    if (g < P.SW && t < P.L) {
+    if (holds_matrix) {
+      Vec<T, V> cells;
 #pragma unroll
-      for (int e = 0; e < V; ++e) strip[(g * P.L + t) * V + e] = acc[e];
+      for (int e = 0; e < V; ++e) cells.e[e] = acc[e];
+      *my_cells = cells;
     }
     __syncwarp();
     // the outputs of the item's slabs are one contiguous run of C
-    const uint32_t slabs = (uint32_t)min((uint64_t)P.SW, P.outer - o0);
-    for (uint32_t idx = lane; idx < slabs * inner; idx += 32) {
-      const uint32_t gg = idx / inner, c = idx % inner;
+    const uint32_t outs = (uint32_t)min((uint64_t)P.SW, P.outer - o0) * inner;
+    T* cout = C + ((single ? 0 : (uint64_t)ks * P.outer) + o0) * inner;
+    for (uint32_t idx = lane; idx < outs; idx += 32) {
+      const uint32_t gg = idx < 32 ? gg0 : idx / inner, c = idx < 32 ? c0 : idx % inner;
       const T* m = strip + gg * P.L * V;
       T val = m[c];
       for (uint32_t r = 1; r < P.R; ++r) val = Num<T>::add(val, m[c + r * inner]);
-      if (ks + 1 == P.ksplit) {                                     // rows past the last whole super-row (only when outer == 1)
+      if (ks + 1 == P.ksplit && nsr * P.R < P.nq) {                 // rows past the last whole super-row (only when outer == 1)
         for (uint64_t r = nsr * P.R; r < P.nq; ++r) val = Num<T>::madd(A[((o0 + gg) * P.nq + r) * inner + c], B[r], val);
       }
-      T* out = C + ((P.ksplit > 1 ? (uint64_t)ks * P.outer : 0) + o0) * inner + idx;
-      *out = (P.accumulate && P.ksplit == 1) ? Num<T>::add(*out, val) : val;
+      cout[idx] = (P.accumulate && single) ? Num<T>::add(cout[idx], val) : val;
     }
     __syncwarp();                                                   // the strip is rewritten by the next item
   }

@@ -631,13 +631,8 @@ cudaError_t TTVB_CAT(streamk_dtype_, TTVB_DTYPE)(const StreamkParams& K, const L
 cudaError_t TTVB_CAT(colf_dtype_, TTVB_DTYPE)(const ColfParams& F, const Launch& l, cudaStream_t stream)
 {
   if constexpr (sizeof(elem_t) <= 8) {
-    constexpr int kLo = sizeof(elem_t) == 8 ? 2 : 3;                 // l.udir carries the CTAs per SM the plan counts on
-    if (l.udir > (uint32_t)kLo) {
-      if (l.stream) return launch_k(ttv_colf_kernel<elem_t, 8, true, kLo + 1>, (unsigned)l.ctas, 256u, 0, stream, F);
-      return launch_k(ttv_colf_kernel<elem_t, 8, false, kLo + 1>, (unsigned)l.ctas, 256u, 0, stream, F);
-    }
-    if (l.stream) return launch_k(ttv_colf_kernel<elem_t, 8, true, kLo>, (unsigned)l.ctas, 256u, 0, stream, F);
-    return launch_k(ttv_colf_kernel<elem_t, 8, false, kLo>, (unsigned)l.ctas, 256u, 0, stream, F);
+    if (l.stream) return launch_k(ttv_colf_kernel<elem_t, 8, true>, (unsigned)l.ctas, 256u, 0, stream, F);
+    return launch_k(ttv_colf_kernel<elem_t, 8, false>, (unsigned)l.ctas, 256u, 0, stream, F);
   } else {
     (void)F; (void)l; (void)stream;
     return cudaErrorInvalidValue;                                    // 16-byte elements: every row is whole vectors

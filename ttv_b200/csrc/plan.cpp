@@ -603,8 +603,7 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
       l.stream = ty * L * 16 >= 128 ? 1 : 0;                         // lane groups narrower than a line reuse it from L1
       const uint64_t batch = ty * KUf;                               // super-rows of one batch of a lane group
       // persistent warps striding over the items (slab group, partition): twice the CTAs an SM holds
-      const uint64_t resident = (uint64_t)std::max(2, std::min(4, env_int("TTV_B200_COLF_MINB", s == 8 ? 2 : 3)));
-      l.udir = (uint32_t)resident;
+      const uint64_t resident = s == 8 ? 2 : 3;
       const uint64_t max_ctas = sms * (uint64_t)std::max(1, env_int("TTV_B200_COLF_CTAS", (int)(2 * resident)));
       const uint64_t vslots = max_ctas * 8;
       const uint64_t ogroups = ceil_div(v.outer, sw);
