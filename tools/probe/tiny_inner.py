@@ -32,13 +32,13 @@ def run(dt, na, q, settings):
     print(f"{dt:4s} {str(na):34s} q={q} view=[{pl['outer']}, {pl['nq']}, {pl['inner']}]  " + " | ".join(cells), flush=True)
 
 
-if which in ("all", "colf"):
+if which in ("all", "colf", "colfshort"):
     OFF = {"TTV_B200_USE_COLF": "0", "TTV_B200_USE_STREAMK": "0"}
     S = [OFF, {}, {"TTV_B200_COLF_ITEMS_PER_WARP": "2"}]
     run("f32", [2, 3, 1 << 20, 2, 4, 16], 3, S)                  # the named asym6 q=3: view [128, 2^20, 6]
     run("i32", [2, 3, 1 << 20, 2, 4, 16], 3, S)
     run("f32", [2, 1 << 17, 2, 4, 2, 2, 64], 2, S)               # the named asym7 q=2: rows of two floats
-    for dt, na in [("f32", [3, 1 << 20, 64]), ("f32", [5, 1 << 20, 48]), ("f32", [6, 1 << 20, 32]), ("f32", [7, 1 << 19, 64]),
+    for dt, na in [] if which == "colfshort" else [("f32", [3, 1 << 20, 64]), ("f32", [5, 1 << 20, 48]), ("f32", [6, 1 << 20, 32]), ("f32", [7, 1 << 19, 64]),
                    ("f64", [3, 1 << 19, 64]), ("f64", [5, 1 << 19, 48]), ("c64", [3, 1 << 19, 64]), ("f32", [9, 1 << 20, 24]), ("f32", [10, 1 << 20, 24]),
                    ("f32", [2, 1 << 20, 128]), ("i32", [2, 1 << 24, 16]), ("f32", [15, 1 << 18, 64]), ("f32", [21, 1 << 16, 256]), ("f64", [21, 1 << 16, 128]),
                    ("f32", [3, 1 << 26]), ("f32", [85, 1 << 16, 64]), ("f64", [63, 1 << 16, 64])]:

@@ -37,8 +37,8 @@ struct ColfParams {
 };
 
 template<class T, int KU, bool PRED, bool NA>
-__device__ __forceinline__ void colf_batch(T (&acc)[16 / sizeof(T)], const T* ap, const T* blo, const T* bhi, uint64_t astep, uint64_t bstep,
-                                           uint64_t sr, uint64_t step, uint64_t n, uint32_t sp)
+__device__ __forceinline__ void colf_batch(T (&acc)[16 / sizeof(T)], const T* ap, const T* blo, const T* bhi, uint32_t astep, uint32_t bstep,
+                                           uint64_t sr, uint32_t step, uint64_t n, uint32_t sp)
 {
   constexpr int V = 16 / (int)sizeof(T);
   Vec<T, V> x[KU];
@@ -88,7 +88,8 @@ ttv_colf_kernel(const ColfParams P)
   T* strip = strips[warp];
 
   const uint64_t nsr   = P.nq / P.R;                                // whole super-rows of a slab
-  const uint64_t astep = (uint64_t)G * V, bstep = (uint64_t)P.TY * P.R;
+  const uint32_t astep = G * V, bstep = P.TY * P.R;                 // elements of A / of b between two steps of a lane (<= 128)
+  const uint64_t slab_elems = P.nq * inner;
   const uint64_t ogroups = (P.outer + P.SW - 1) / P.SW;
   const uint64_t items = ogroups * P.ksplit;
   uint32_t span = 1;
@@ -104,8 +105,8 @@ ttv_colf_kernel(const ColfParams P)
     const uint64_t og = single ? item : item / P.ksplit;
     const uint32_t ks = single ? 0u : (uint32_t)(item - og * P.ksplit);
     const uint64_t o0 = og * P.SW;                                  // first slab of the item
-    const uint64_t srbeg = min((uint64_t)ks * P.srchunk, nsr), srend = min(srbeg + P.srchunk, nsr);
-    const uint64_t n = srend - srbeg;
+    const uint64_t srbeg = single ? 0 : min((uint64_t)ks * P.srchunk, nsr);
+    const uint64_t n = single ? nsr : min(srbeg + P.srchunk, nsr) - srbeg;
     const uint64_t o = o0 + g;
 
     T acc[V];
@@ -113,11 +114,11 @@ ttv_colf_kernel(const ColfParams P)
     for (int e = 0; e < V; ++e) acc[e] = Num<T>::zero();
 
     if (g < P.SW && o < P.outer) {
-      const T* ap  = A + (o * P.nq + srbeg * P.R) * inner + (uint64_t)t * V;
-      const T* blo = B + (srbeg + ty) * P.R + r0;
-      const T* bhi = B + (srbeg + ty) * P.R + rhi;
+      const T* ap  = A + o * slab_elems + srbeg * (P.R * inner) + t * V;
+      const T* blo = B + srbeg * P.R + (ty * P.R + r0);
+      const T* bhi = B + srbeg * P.R + (ty * P.R + rhi);
       uint64_t sr = ty;
-      for (; sr + (uint64_t)(KU - 1) * P.TY < n; sr += (uint64_t)KU * P.TY, ap += KU * astep, blo += KU * bstep, bhi += KU * bstep)
+      for (; sr + (KU - 1) * P.TY < n; sr += KU * P.TY, ap += KU * astep, blo += KU * bstep, bhi += KU * bstep)
         colf_batch<T, KU, false, NA>(acc, ap, blo, bhi, astep, bstep, sr, P.TY, n, sp);
       if (sr < n) colf_batch<T, KU, true, NA>(acc, ap, blo, bhi, astep, bstep, sr, P.TY, n, sp);
     }
