@@ -36,9 +36,14 @@ struct ColfParams {
   uint32_t accumulate;      // only honoured when ksplit == 1
 };
 
-template<class T, int KU, bool PRED, bool NA>
-__device__ __forceinline__ void colf_batch(T (&acc)[16 / sizeof(T)], const T* ap, const T* blo, const T* bhi, uint32_t astep, uint32_t bstep,
-                                           uint64_t sr, uint32_t step, uint64_t n, uint32_t sp)
+// STEP: the type the distances between the loads of a batch are computed in.  32 bits halve the address arithmetic, which
+// is what a short slab spends its time on (8 388 608 slabs of 128 x 2 floats: 5 708 -> 5 760 GB/s, 262 144 of 256 x 3: 4 069 ->
+// 4 355); long partitions measured 1.5-2.6 % FASTER with 64 bits (the loads of a batch leave in a different order), so each
+// keeps its own; 8-byte elements lose with 32 bits on short slabs too (32 768 slabs of 2048 x 3 doubles: 6 726 -> 6 232) and
+// always take 64 (tools/probe/tiny_inner.py, sessions 20-21).
+template<class T, int KU, bool PRED, bool NA, class STEP>
+__device__ __forceinline__ void colf_batch(T (&acc)[16 / sizeof(T)], const T* ap, const T* blo, const T* bhi, STEP astep, STEP bstep,
+                                           uint64_t sr, STEP step, uint64_t n, uint32_t sp)
 {
   constexpr int V = 16 / (int)sizeof(T);
   Vec<T, V> x[KU];
@@ -118,9 +123,16 @@ ttv_colf_kernel(const ColfParams P)
       const T* blo = B + srbeg * P.R + (ty * P.R + r0);
       const T* bhi = B + srbeg * P.R + (ty * P.R + rhi);
       uint64_t sr = ty;
-      for (; sr + (KU - 1) * P.TY < n; sr += KU * P.TY, ap += KU * astep, blo += KU * bstep, bhi += KU * bstep)
-        colf_batch<T, KU, false, NA>(acc, ap, blo, bhi, astep, bstep, sr, P.TY, n, sp);
-      if (sr < n) colf_batch<T, KU, true, NA>(acc, ap, blo, bhi, astep, bstep, sr, P.TY, n, sp);
+      if (single && sizeof(T) == 4) {
+        for (; sr + (KU - 1) * P.TY < n; sr += KU * P.TY, ap += KU * astep, blo += KU * bstep, bhi += KU * bstep)
+          colf_batch<T, KU, false, NA, uint32_t>(acc, ap, blo, bhi, astep, bstep, sr, P.TY, n, sp);
+        if (sr < n) colf_batch<T, KU, true, NA, uint32_t>(acc, ap, blo, bhi, astep, bstep, sr, P.TY, n, sp);
+      } else {
+        const uint64_t astep64 = astep, bstep64 = bstep, ty64 = P.TY;
+        for (; sr + (uint64_t)(KU - 1) * ty64 < n; sr += (uint64_t)KU * ty64, ap += KU * astep64, blo += KU * bstep64, bhi += KU * bstep64)
+          colf_batch<T, KU, false, NA, uint64_t>(acc, ap, blo, bhi, astep64, bstep64, sr, ty64, n, sp);
+        if (sr < n) colf_batch<T, KU, true, NA, uint64_t>(acc, ap, blo, bhi, astep64, bstep64, sr, ty64, n, sp);
+      }
     }
 
     // lanes of one phase j of one slab: rows ty + h are folded onto ty (a source lane lies inside the same group)
