@@ -39,8 +39,8 @@ struct ColfParams {
 // STEP: the type the distances between the loads of a batch are computed in.  32 bits halve the address arithmetic, which
 // is what a short slab spends its time on (8 388 608 slabs of 128 x 2 floats: 5 708 -> 5 760 GB/s, 262 144 of 256 x 3: 4 069 ->
 // 4 355); long partitions measured 1.5-2.6 % FASTER with 64 bits (the loads of a batch leave in a different order), so each
-// keeps its own; 8-byte elements lose with 32 bits on short slabs too (32 768 slabs of 2048 x 3 doubles: 6 726 -> 6 232) and
-// always take 64 (tools/probe/tiny_inner.py, sessions 20-21).
+// keeps its own -- 32 bits for slabs of at most two batches of 4-byte elements; 8-byte elements lose with 32 bits on short
+// slabs too (4 194 304 slabs of 16 x 3 doubles: 5 294 -> 4 800) and always take 64 (tools/probe/tiny_inner.py, sessions 20-21).
 template<class T, int KU, bool PRED, bool NA, class STEP>
 __device__ __forceinline__ void colf_batch(T (&acc)[16 / sizeof(T)], const T* ap, const T* blo, const T* bhi, STEP astep, STEP bstep,
                                            uint64_t sr, STEP step, uint64_t n, uint32_t sp)
@@ -105,6 +105,7 @@ ttv_colf_kernel(const ColfParams P)
   Vec<T, V>* my_cells = reinterpret_cast<Vec<T, V>*>(strip) + (g * P.L + t);
   const uint32_t gg0 = lane / inner, c0 = lane % inner;             // output `lane` of an item: slab gg0, column c0
   const bool single = P.ksplit == 1;                                // no partition index to divide out (every short slab)
+  const bool short32 = single && sizeof(T) == 4 && nsr <= 2ull * KU * P.TY;   // a slab is two batches at most: 32-bit steps
 
   for (uint64_t item = (uint64_t)blockIdx.x * 8 + warp; item < items; item += (uint64_t)gridDim.x * 8) {
     const uint64_t og = single ? item : item / P.ksplit;
@@ -123,7 +124,7 @@ ttv_colf_kernel(const ColfParams P)
       const T* blo = B + srbeg * P.R + (ty * P.R + r0);
       const T* bhi = B + srbeg * P.R + (ty * P.R + rhi);
       uint64_t sr = ty;
-      if (single && sizeof(T) == 4) {
+      if (short32) {
         for (; sr + (KU - 1) * P.TY < n; sr += KU * P.TY, ap += KU * astep, blo += KU * bstep, bhi += KU * bstep)
           colf_batch<T, KU, false, NA, uint32_t>(acc, ap, blo, bhi, astep, bstep, sr, P.TY, n, sp);
         if (sr < n) colf_batch<T, KU, true, NA, uint32_t>(acc, ap, blo, bhi, astep, bstep, sr, P.TY, n, sp);
