@@ -1,0 +1,14 @@
+#!/bin/bash
+# round 2, GPU session 21 (one B200): evidence pass of the tree with COLF / DOTP -- the whole GPU suite, smoke, both bench arms, the
+# launch list of the bench under ncu, every named config standalone (252 products), the tiny-extent A/B table, one ncu --set full
+# capture of each new kernel
+out=gpurun_out; mkdir -p $out
+bash tools/gpu_session.sh r02y
+(time timeout 300 python tools/sweep.py --set named --reps 7 --out $out/r02y_sweep_named.jsonl) > $out/r02y_sweep_named.txt 2>&1; tail -4 $out/r02y_sweep_named.txt | cut -c1-160
+timeout 300 python tools/probe/tiny_inner.py all > $out/r02y_tiny_ab.txt 2>&1; tail -3 $out/r02y_tiny_ab.txt | cut -c1-200
+for spec in "asym6 3 colf_long" "asym5n 2 colf_short" "asym10 1 dotp" "asym3n 2 colf_rows2"; do
+  set -- $spec
+  timeout 120 ncu --set full --clock-control none --import-source on -k regex:"ttv_(colf|dotp)" -s 3 -c 1 -f -o $out/r02y_ncu_$3 \
+    python tools/one.py --set named --cfg $1 --q $2 --dtype f32 --launches 4 > $out/r02y_ncu_$3.log 2>&1
+  tail -1 $out/r02y_ncu_$3.log | cut -c1-200
+done

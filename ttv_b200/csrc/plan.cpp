@@ -576,7 +576,7 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
     const uint64_t R = Vf / g, L = v.inner / g;
     const bool eligible = Vf > 1 && v.inner > 1 && R > 1 && L <= 32 && (v.nq % R == 0 || v.outer == 1) && (align_a % 16) == 0 &&
                           !(flags & TTV_B200_FLAG_NO_VEC);
-    // measured (tools/probe/tiny_inner.py, profiles/r02_colf_ab.txt): 4-byte elements win at every L <= 32 from slabs of 128
+    // measured (tools/probe/tiny_inner.py, profiles/r02_colf_dotp_ab.txt): 4-byte elements win at every L <= 32 from slabs of 128
     // bytes on (64-byte slabs lose: 3 347 against 4 235 GB/s); 8-byte elements, whose column kernel already loads 8 bytes
     // per lane, win with rows of 3 / 5 / 7 and lose with rows of 21 (5 957 against 6 360)
     const bool pays = v.nq * v.inner * s >= (uint64_t)env_int("TTV_B200_COLF_MIN_SLAB_B", 128) && (s == 4 || L <= 8);
