@@ -947,10 +947,14 @@ def test_colf_kernel_rows_that_are_not_whole_vectors(dtype, oracle, monkeypatch)
         a, b = random_case(rng, na, q, dtype)
         want = oracle.ttv(q, a, na, pia, b)
         assert ttv_b200.plan(q, na, pia, dtype=name, kernel="colf")["kernel"] == 10
-        for ks in (0, 1, 3):
-            assert np.array_equal(run_lowlevel(q, a, na, pia, b, kernel="colf", ksplit=ks), want), (na, pia, q, dtype, ks)
-        c0 = np.full(want.size, 3, dtype)
-        assert np.array_equal(run_lowlevel(q, a, na, pia, b, c0=c0, kernel="colf", flags=1), want + 3)
+        # rows of two 4-byte elements have a form of their own (ttv_colf2_kernel); the general kernel takes them as well
+        for pair in (("1", "0") if (vec == 4 and 2 in na[:1] + na[-1:]) else ("1",)):
+            monkeypatch.setenv("TTV_B200_COLF_PAIR", pair)
+            for ks in (0, 1, 3):
+                assert np.array_equal(run_lowlevel(q, a, na, pia, b, kernel="colf", ksplit=ks), want), (na, pia, q, dtype, ks, pair)
+            c0 = np.full(want.size, 3, dtype)
+            assert np.array_equal(run_lowlevel(q, a, na, pia, b, c0=c0, kernel="colf", flags=1), want + 3)
+        monkeypatch.delenv("TTV_B200_COLF_PAIR")
     for na in ((3, 4 * 6000, 2), (3, 4 * 30, 701), (2 if vec == 4 else 3, 256, 3000), (5, 64, 1001), (3, 32, 777), (2 if vec == 4 else 7, 32, 5003)):
         assert ttv_b200.plan(2, na, (1, 2, 3), dtype=name)["kernel"] == 10
         a, b = random_case(rng, na, 2, dtype)

@@ -169,4 +169,100 @@ ttv_colf_kernel(const ColfParams P)
   }
 }
 
+// ROWS OF TWO 4-byte elements (inner = 2: the leading extent 2 of the asymmetric family) are the one case where everything
+// above is known at compile time: a vector is the two rows of its super-row (R = 2, L = 1), so the two elements of b are ONE
+// aligned 8-byte load, no element needs a select, the two rows fold inside the lane, and after the shuffle tree lane 0 of a
+// slab's group holds the slab's two outputs and stores them as 8 bytes -- no strip, no second pass over the lanes.  The
+// general kernel spent 56 % of the issue slots on 8 388 608 slabs of 128 x 2 floats (ncu, 72 % gpu__dram_throughput).
+template<class T, int KU, bool NA>
+__global__ void __launch_bounds__(256, 3)
+ttv_colf2_kernel(const ColfParams P)
+{
+  static_assert(sizeof(T) == 4, "rows of two 4-byte elements");
+  pdl_prologue();
+  using V4 = Vec<T, 4>;
+  using V2 = Vec<T, 2>;
+  const T* __restrict__ A = static_cast<const T*>(P.a);
+  const T* __restrict__ B = static_cast<const T*>(P.b);
+  T* __restrict__       C = static_cast<T*>(P.c);
+
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t G = P.TY;                                          // lanes of one slab (L = 1)
+  const uint32_t g = lane / G, ty = lane % G;
+  const uint64_t nsr = P.nq / 2;
+  const uint64_t slab_elems = P.nq * 2;
+  const uint64_t ogroups = (P.outer + P.SW - 1) / P.SW;
+  const uint64_t items = ogroups * P.ksplit;
+  const bool single = P.ksplit == 1;
+  uint32_t span = 1;
+  while (span < P.TY) span <<= 1;
+
+  for (uint64_t item = (uint64_t)blockIdx.x * 8 + warp; item < items; item += (uint64_t)gridDim.x * 8) {
+    const uint64_t og = single ? item : item / P.ksplit;
+    const uint32_t ks = single ? 0u : (uint32_t)(item - og * P.ksplit);
+    const uint64_t srbeg = single ? 0 : min((uint64_t)ks * P.srchunk, nsr);
+    const uint64_t n = single ? nsr : min(srbeg + P.srchunk, nsr) - srbeg;
+    const uint64_t o = og * P.SW + g;
+    const bool live = g < P.SW && o < P.outer;
+
+    T acc[4] = {Num<T>::zero(), Num<T>::zero(), Num<T>::zero(), Num<T>::zero()};
+    if (live) {
+      const T* ap = A + o * slab_elems + (srbeg + ty) * 4;
+      const T* bp = B + (srbeg + ty) * 2;
+      const uint32_t astep = G * 4, bstep = G * 2;
+      uint64_t sr = ty;
+      for (; sr + (uint64_t)(KU - 1) * G < n; sr += (uint64_t)KU * G, ap += KU * astep, bp += KU * bstep) {
+        V4 x[KU];
+        V2 q[KU];
+#pragma unroll
+        for (int s = 0; s < KU; ++s) {
+          x[s] = load_a<T, 4>(ap + s * astep, NA);
+          q[s] = *reinterpret_cast<const V2*>(bp + s * bstep);
+        }
+#pragma unroll
+        for (int s = 0; s < KU; ++s) {
+          acc[0] = Num<T>::madd(x[s].e[0], q[s].e[0], acc[0]);
+          acc[1] = Num<T>::madd(x[s].e[1], q[s].e[0], acc[1]);
+          acc[2] = Num<T>::madd(x[s].e[2], q[s].e[1], acc[2]);
+          acc[3] = Num<T>::madd(x[s].e[3], q[s].e[1], acc[3]);
+        }
+      }
+      if (sr < n) {
+        V4 x[KU];
+        V2 q[KU];
+#pragma unroll
+        for (int s = 0; s < KU; ++s) {
+          const bool ok = sr + (uint64_t)s * G < n;
+          ld16_if<NA>(&x[s], ap + s * astep, ok);
+          q[s] = ok ? *reinterpret_cast<const V2*>(bp + s * bstep) : zero_vec<T, 2>();
+        }
+#pragma unroll
+        for (int s = 0; s < KU; ++s) {
+          acc[0] = Num<T>::madd(x[s].e[0], q[s].e[0], acc[0]);
+          acc[1] = Num<T>::madd(x[s].e[1], q[s].e[0], acc[1]);
+          acc[2] = Num<T>::madd(x[s].e[2], q[s].e[1], acc[2]);
+          acc[3] = Num<T>::madd(x[s].e[3], q[s].e[1], acc[3]);
+        }
+      }
+    }
+    T c0 = Num<T>::add(acc[0], acc[2]), c1 = Num<T>::add(acc[1], acc[3]);      // the two rows of the super-rows
+    for (uint32_t h = span >> 1; h > 0; h >>= 1) {
+      const T o0 = shfl_down_elem(c0, (int)h), o1 = shfl_down_elem(c1, (int)h);
+      if (ty < h && ty + h < P.TY) { c0 = Num<T>::add(c0, o0); c1 = Num<T>::add(c1, o1); }
+    }
+    if (live && ty == 0) {
+      if (ks + 1 == P.ksplit && (P.nq & 1)) {                       // an odd last row (only when outer == 1)
+        const uint64_t r = P.nq - 1;
+        c0 = Num<T>::madd(A[o * slab_elems + r * 2], B[r], c0);
+        c1 = Num<T>::madd(A[o * slab_elems + r * 2 + 1], B[r], c1);
+      }
+      V2* out = reinterpret_cast<V2*>(C + ((single ? 0 : (uint64_t)ks * P.outer) + o) * 2);
+      V2 val;
+      if (P.accumulate && single) { const V2 old = *out; val.e[0] = Num<T>::add(old.e[0], c0); val.e[1] = Num<T>::add(old.e[1], c1); }
+      else { val.e[0] = c0; val.e[1] = c1; }
+      *out = val;
+    }
+  }
+}
+
 } // namespace ttvb

@@ -630,6 +630,13 @@ cudaError_t TTVB_CAT(streamk_dtype_, TTVB_DTYPE)(const StreamkParams& K, const L
 
 cudaError_t TTVB_CAT(colf_dtype_, TTVB_DTYPE)(const ColfParams& F, const Launch& l, cudaStream_t stream)
 {
+  if constexpr (sizeof(elem_t) == 4) {
+    // rows of two elements: the form without selects, strip and second pass (TTV_B200_COLF_PAIR=0 keeps the general kernel)
+    if (l.pair) {
+      if (l.stream) return launch_k(ttv_colf2_kernel<elem_t, 8, true>, (unsigned)l.ctas, 256u, 0, stream, F);
+      return launch_k(ttv_colf2_kernel<elem_t, 8, false>, (unsigned)l.ctas, 256u, 0, stream, F);
+    }
+  }
   if constexpr (sizeof(elem_t) <= 8) {
     if (l.stream) return launch_k(ttv_colf_kernel<elem_t, 8, true>, (unsigned)l.ctas, 256u, 0, stream, F);
     return launch_k(ttv_colf_kernel<elem_t, 8, false>, (unsigned)l.ctas, 256u, 0, stream, F);

@@ -601,6 +601,7 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
       if (sw == 1) ty = ty_max;
       l.vec = (int)Vf; l.tx = (uint32_t)L; l.ty = (uint32_t)ty; l.to = (uint32_t)R; l.nu = (int)sw; l.ku = (int)KUf; l.udir = 0;
       l.stream = ty * L * 16 >= 128 ? 1 : 0;                         // lane groups narrower than a line reuse it from L1
+      l.pair = (v.inner == 2 && s == 4 && (align_b % 8) == 0 && (align_c % 8) == 0 && env_int("TTV_B200_COLF_PAIR", 1) != 0) ? 1 : 0;
       const uint64_t batch = ty * KUf;                               // super-rows of one batch of a lane group
       // persistent warps striding over the items (slab group, partition): twice the CTAs an SM holds
       const uint64_t resident = s == 8 ? 2 : 3;
