@@ -14,7 +14,7 @@ from ttv_b200.measure import Arena, kernel_label, measure_config  # noqa: E402
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 aa, ac = Arena(int(13.2e9)), Arena(int(6.6e9))
 SWITCHES = ("TTV_B200_USE_STREAMK", "TTV_B200_STREAMK_STAGE_KB", "TTV_B200_USE_DOTP", "TTV_B200_DOTP_KU", "TTV_B200_DOTP_CTAS",
-            "TTV_B200_USE_COLF", "TTV_B200_COLF_ITEMS_PER_WARP", "TTV_B200_COLF_CTAS", "TTV_B200_COLF_MIN_SLAB_B", "TTV_B200_COLF_PAIR")
+            "TTV_B200_USE_COLF", "TTV_B200_COLF_ITEMS_PER_WARP", "TTV_B200_COLF_CTAS", "TTV_B200_COLF_MIN_SLAB_B", "TTV_B200_COLF_PAIR", "TTV_B200_KSPLIT")
 
 
 def run(dt, na, q, settings):
