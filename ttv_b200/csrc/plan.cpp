@@ -615,7 +615,10 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
       auto parts = [&](uint64_t ks) { const uint64_t chunk = ceil_div(std::max<uint64_t>(1, ceil_div(nsr, ks)), batch) * batch; return std::max<uint64_t>(1, ceil_div(nsr, chunk)); };
       if (want > 0) ksplit = parts(std::min<uint64_t>((uint64_t)want, std::max<uint64_t>(1, nsr)));
       else if (sw == 1) {
-        const uint64_t hi = std::max<uint64_t>(1, std::min(ceil_div(vslots * (uint64_t)env_int("TTV_B200_COLF_ITEMS_PER_WARP", 4), ogroups), std::max<uint64_t>(1, nsr / (batch * 4))));
+        // (never more than 24 partitions per SM: every partition of an output is one more term of the reduce pass, which
+        // for one or a few slabs is a handful of CTAs -- [1, 2^26, 2] 13 108 partitions 4 557, 3 543 partitions 6 458 GB/s)
+        const uint64_t hi = std::max<uint64_t>(1, std::min(std::min(ceil_div(vslots * (uint64_t)env_int("TTV_B200_COLF_ITEMS_PER_WARP", 4), ogroups), sms * 24),
+                                                           std::max<uint64_t>(1, nsr / (batch * 4))));
         double best = -1.0;
         for (uint64_t ks = hi; ks >= std::max<uint64_t>(1, hi / 2); --ks) {
           const uint64_t k2 = parts(ks);
