@@ -108,11 +108,13 @@ enum ttv_b200_kernel {
   TTV_B200_KERNEL_COLT   = 7,  /* column GEMV with A staged through shared memory by TMA tensor tiles (cp.async.bulk.tensor),
                                   producer warp + mbarrier ring; chosen only when forced (measured against COL) */
   TTV_B200_KERNEL_STREAMK = 8, /* tiny odd inner extent under a long contraction: rows and b staged through shared memory by
-                                  bulk copies, threads along n_q, `inner` accumulators each, tree at the end                */
+                                  bulk copies, threads along n_q, `inner` accumulators each, tree at the end; by rule only
+                                  where COLF cannot go (several slabs that start off the 16-byte grid)                      */
   TTV_B200_KERNEL_DOTP   = 9,  /* fibers of two elements (inner = 1, n_q = 2; 4- and 8-byte types): a lane loads consecutive
                                   16-byte vectors of whole fibers and stores their 8 bytes of C, b in registers             */
-  TTV_B200_KERNEL_COLF   = 10, /* rows narrower than / not a multiple of a 16-byte vector under a long contraction: V / gcd rows
-                                  are whole vectors, the slab is streamed flat, a thread keeps one accumulator per element   */
+  TTV_B200_KERNEL_COLF   = 10, /* rows narrower than / not a multiple of a 16-byte vector (inner = 2, 3, 5, 6 ...): V / gcd(inner, V)
+                                  rows are whole vectors, so a warp streams its slab (or slab partition, or several short
+                                  slabs side by side) flat, one accumulator per element of a lane's vector                   */
   TTV_B200_KERNEL_COUNT  = 11
 };
 
