@@ -955,10 +955,18 @@ def test_colf_kernel_rows_that_are_not_whole_vectors(dtype, oracle, monkeypatch)
             c0 = np.full(want.size, 3, dtype)
             assert np.array_equal(run_lowlevel(q, a, na, pia, b, c0=c0, kernel="colf", flags=1), want + 3)
         monkeypatch.delenv("TTV_B200_COLF_PAIR")
-    for na in ((3, 4 * 6000, 2), (3, 4 * 30, 701), (2 if vec == 4 else 3, 256, 3000), (5, 64, 1001), (3, 32, 777), (2 if vec == 4 else 7, 32, 5003)):
+    # slabs of at most one batch have a form of their own (ttv_colfs_kernel: b in registers); the general kernels take them as well
+    for na in ((3, 4 * 6000, 2), (3, 4 * 30, 701), (2 if vec == 4 else 3, 256, 3000), (5, 64, 1001), (3, 32, 777), (2 if vec == 4 else 7, 32, 5003),
+               (2 if vec == 4 else 3, 16, 40001), (3, 4 * 77, 33)):
         assert ttv_b200.plan(2, na, (1, 2, 3), dtype=name)["kernel"] == 10
         a, b = random_case(rng, na, 2, dtype)
-        assert np.array_equal(run_lowlevel(2, a, na, (1, 2, 3), b), oracle.ttv(2, a, na, (1, 2, 3), b)), na
+        want = oracle.ttv(2, a, na, (1, 2, 3), b)
+        for short in ("1", "0"):
+            monkeypatch.setenv("TTV_B200_COLF_SHORT", short)
+            assert np.array_equal(run_lowlevel(2, a, na, (1, 2, 3), b), want), (na, short)
+            c0 = np.full(want.size, 5, dtype)
+            assert np.array_equal(run_lowlevel(2, a, na, (1, 2, 3), b, c0=c0, flags=1), want + 5), (na, short)
+        monkeypatch.delenv("TTV_B200_COLF_SHORT")
     with pytest.raises(ttv_b200.TTVError):                          # rows of whole vectors
         ttv_b200.plan(2, (2 * vec, 5000), (1, 2), dtype=name, kernel="colf")
     with pytest.raises(ttv_b200.TTVError):                          # more than 32 vectors per super-row

@@ -265,4 +265,132 @@ ttv_colf2_kernel(const ColfParams P)
   }
 }
 
+// SHORT slabs -- a slab is at most ONE batch of its lane group (n_q / R <= KU TY; always unsplit) -- leave the kernels above
+// issue-bound: ncu counted 440 warp instructions per 4 KB item on 8 388 608 slabs of 128 x 2 floats, 127 of them IMAD (the
+// addresses of A, b and C from scratch for every item), 43 ISETP, 27 BRA, against 24 loads and 64 FFMA / FSEL.  But nothing
+// except the address of A changes from slab to slab: which of a lane's KU steps exist, and the elements of b that go with
+// them.  This form therefore loads b ONCE per lane into registers, keeps the validity of the steps as per-lane constants
+// (whole batches take plain loads), and walks A and C with one pointer increment per item.  PAIR is the rows-of-two form
+// (see ttv_colf2_kernel): no selects, no strip.
+template<class T, int KU, bool NA, bool PAIR>
+__global__ void __launch_bounds__(256, sizeof(T) == 8 ? 2 : 3)
+ttv_colfs_kernel(const ColfParams P)
+{
+  static_assert(!PAIR || sizeof(T) == 4, "rows of two 4-byte elements");
+  pdl_prologue();
+  constexpr int V = 16 / (int)sizeof(T);
+  __shared__ __align__(16) T strips[PAIR ? 1 : 8][PAIR ? 4 : 32 * V];
+
+  const T* __restrict__ A = static_cast<const T*>(P.a);
+  const T* __restrict__ B = static_cast<const T*>(P.b);
+  T* __restrict__       C = static_cast<T*>(P.c);
+
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t inner = (uint32_t)P.inner;
+  const uint32_t G  = P.TY * P.L;
+  const uint32_t g  = lane / G, t = lane % G;
+  const uint32_t j  = t % P.L, ty = t / P.L;
+  const uint32_t r0  = (V * j) / inner;
+  const uint32_t sp  = min((uint32_t)V, (r0 + 1) * inner - V * j);
+  const uint32_t rhi = min(r0 + 1, P.R - 1);
+  const uint32_t nsr = (uint32_t)(P.nq / P.R);                      // <= KU * TY
+  const uint32_t astep = G * V;
+  const uint64_t slab_elems = P.nq * inner;
+  const bool in_group = g < P.SW;
+
+  // the lane's steps and its elements of b: the same for every slab
+  uint32_t okm = 0;                                                 // bit s: step s of this lane exists
+  T lo[KU], hi[KU];
+#pragma unroll
+  for (int s = 0; s < KU; ++s) {
+    const bool ok = in_group && ty + s * P.TY < nsr;
+    okm |= ok ? 1u << s : 0u;
+    lo[s] = ok ? B[(ty + s * P.TY) * P.R + r0] : Num<T>::zero();
+    hi[s] = ok ? B[(ty + s * P.TY) * P.R + rhi] : Num<T>::zero();
+  }
+  const bool whole = (okm >> (KU - 1)) & 1u;                        // every step of this lane exists
+  uint32_t span = 1;
+  while (span < P.TY) span <<= 1;
+
+  const uint64_t items = (P.outer + P.SW - 1) / P.SW;
+  uint64_t item = (uint64_t)blockIdx.x * 8 + warp;
+  const uint32_t istride = gridDim.x * 8;
+  const T* ap = A + (item * P.SW + g) * slab_elems + t * V;         // (never dereferenced by a lane without a slab)
+  const uint32_t astride = istride * P.SW * (uint32_t)slab_elems;   // a warp's item is at most 32 KU vectors: fits 32 bits
+  const uint32_t cell = PAIR ? 0u : (g * P.L + t) * V;              // where the lane's V cells go in the warp's strip
+  const uint32_t wrow = PAIR ? 0u : warp;
+
+  for (; item < items; item += istride, ap += astride) {
+    const uint64_t left = P.outer - item * P.SW;                    // slabs from the item's first one to the end
+    const bool live = in_group && g < left;
+    Vec<T, V> x[KU];
+    if (whole && live) {
+#pragma unroll
+      for (int s = 0; s < KU; ++s) x[s] = load_a<T, V>(ap + s * astep, NA);
+    } else {
+#pragma unroll
+      for (int s = 0; s < KU; ++s) ld16_if<NA>(&x[s], ap + s * astep, live && ((okm >> s) & 1u));
+    }
+    T acc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = Num<T>::zero();
+#pragma unroll
+    for (int s = 0; s < KU; ++s)
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        if constexpr (PAIR) acc[e] = Num<T>::madd(x[s].e[e], e < 2 ? lo[s] : hi[s], acc[e]);
+        else                acc[e] = Num<T>::madd(x[s].e[e], (uint32_t)e < sp ? lo[s] : hi[s], acc[e]);
+      }
+    T* cout = C + item * P.SW * inner;
+
+    if constexpr (PAIR) {
+      T c0 = Num<T>::add(acc[0], acc[2]), c1 = Num<T>::add(acc[1], acc[3]);
+      for (uint32_t h = span >> 1; h > 0; h >>= 1) {
+        const T o0 = shfl_down_elem(c0, (int)h), o1 = shfl_down_elem(c1, (int)h);
+        if (ty < h && ty + h < P.TY) { c0 = Num<T>::add(c0, o0); c1 = Num<T>::add(c1, o1); }
+      }
+      if (live && ty == 0) {
+        if (P.nq & 1) {                                             // an odd last row (only when outer == 1)
+          const uint64_t r = P.nq - 1;
+          c0 = Num<T>::madd(ap[r * 2], B[r], c0);
+          c1 = Num<T>::madd(ap[r * 2 + 1], B[r], c1);
+        }
+        Vec<T, 2>* out = reinterpret_cast<Vec<T, 2>*>(cout + g * 2);
+        Vec<T, 2> val;
+        if (P.accumulate) { const Vec<T, 2> old = *out; val.e[0] = Num<T>::add(old.e[0], c0); val.e[1] = Num<T>::add(old.e[1], c1); }
+        else { val.e[0] = c0; val.e[1] = c1; }
+        *out = val;
+      }
+    } else {
+      for (uint32_t h = span >> 1; h > 0; h >>= 1) {
+        const bool take = ty < h && ty + h < P.TY;
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const T other = shfl_down_elem(acc[e], (int)(h * P.L));
+          if (take) acc[e] = Num<T>::add(acc[e], other);
+        }
+      }
+      if (in_group && t < P.L) {
+        Vec<T, V> cells;
+#pragma unroll
+        for (int e = 0; e < V; ++e) cells.e[e] = acc[e];
+        *reinterpret_cast<Vec<T, V>*>(&strips[wrow][cell]) = cells;
+      }
+      __syncwarp();
+      const uint32_t outs = (uint32_t)min((uint64_t)P.SW, left) * inner;
+      for (uint32_t idx = lane; idx < outs; idx += 32) {
+        const uint32_t gg = idx / inner, c = idx - gg * inner;
+        const uint32_t m = gg * P.L * V + c;
+        T val = strips[wrow][m];
+        for (uint32_t r = 1; r < P.R; ++r) val = Num<T>::add(val, strips[wrow][m + r * inner]);
+        if ((uint64_t)nsr * P.R < P.nq) {                           // rows past the last whole super-row (only when outer == 1)
+          for (uint64_t r = (uint64_t)nsr * P.R; r < P.nq; ++r) val = Num<T>::madd(A[((item * P.SW + gg) * P.nq + r) * inner + c], B[r], val);
+        }
+        cout[idx] = P.accumulate ? Num<T>::add(cout[idx], val) : val;
+      }
+      __syncwarp();
+    }
+  }
+}
+
 } // namespace ttvb

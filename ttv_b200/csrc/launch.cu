@@ -630,6 +630,19 @@ cudaError_t TTVB_CAT(streamk_dtype_, TTVB_DTYPE)(const StreamkParams& K, const L
 
 cudaError_t TTVB_CAT(colf_dtype_, TTVB_DTYPE)(const ColfParams& F, const Launch& l, cudaStream_t stream)
 {
+  // a slab is at most one batch: b in registers, one pointer increment per item (TTV_B200_COLF_SHORT=0 keeps the general kernels)
+  if constexpr (sizeof(elem_t) == 4) {
+    if (l.short1 && l.pair) {
+      if (l.stream) return launch_k(ttv_colfs_kernel<elem_t, 8, true, true>, (unsigned)l.ctas, 256u, 0, stream, F);
+      return launch_k(ttv_colfs_kernel<elem_t, 8, false, true>, (unsigned)l.ctas, 256u, 0, stream, F);
+    }
+  }
+  if constexpr (sizeof(elem_t) <= 8) {
+    if (l.short1) {
+      if (l.stream) return launch_k(ttv_colfs_kernel<elem_t, 8, true, false>, (unsigned)l.ctas, 256u, 0, stream, F);
+      return launch_k(ttv_colfs_kernel<elem_t, 8, false, false>, (unsigned)l.ctas, 256u, 0, stream, F);
+    }
+  }
   if constexpr (sizeof(elem_t) == 4) {
     // rows of two elements: the form without selects, strip and second pass (TTV_B200_COLF_PAIR=0 keeps the general kernel)
     if (l.pair) {

@@ -630,6 +630,7 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
       }
       const uint64_t srchunk = ceil_div(std::max<uint64_t>(1, ceil_div(nsr, ksplit)), batch) * batch;
       l.ksplit = (uint32_t)ksplit; l.kchunk = srchunk * R;
+      l.short1 = (ksplit == 1 && nsr <= batch && env_int("TTV_B200_COLF_SHORT", 1) != 0) ? 1 : 0;
       l.itiles = 1; l.otiles = ogroups;
       l.tiles = ogroups * ksplit;
       l.ctas = std::min<uint64_t>(ceil_div(l.tiles, 8), max_ctas);
