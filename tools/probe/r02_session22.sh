@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU session 22 (one B200): evidence pass of the FINAL tree (COLF with the rows-of-two form and the partition cap, DOTP):
+# round 2, GPU sessions 22 and 26 (one B200): evidence pass of the FINAL tree (COLF with its rows-of-two and short-slab forms, DOTP):
 # the whole GPU suite, smoke, both bench arms, the launch list of the bench under ncu, every named config standalone (252 products),
 # one ncu --set full capture of each new kernel
 out=gpurun_out; mkdir -p $out
