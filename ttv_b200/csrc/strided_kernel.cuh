@@ -199,23 +199,7 @@ ttv_strided_dot_kernel(const StridedParams P, const uint32_t G)
     strided_decode(P, valid ? j : 0, offa, offc);
     const T* ap = A + offa;
     T acc = Num<T>::zero();
-    uint64_t k = g;
-    if (valid) {
-      // whole batches: no test per load (ncu had this kernel at 76 % of the issue slots with one branch per load)
-      for (; k + (uint64_t)(KU - 1) * G < kv; k += (uint64_t)G * KU) {
-        Vec<T, V> v[KU], bv[KU];
-#pragma unroll
-        for (int s = 0; s < KU; ++s) {
-          v[s]  = *reinterpret_cast<const Vec<T, V>*>(ap + (k + (uint64_t)s * G) * V);
-          bv[s] = *reinterpret_cast<const Vec<T, V>*>(B + (k + (uint64_t)s * G) * V);
-        }
-#pragma unroll
-        for (int s = 0; s < KU; ++s)
-#pragma unroll
-          for (int e = 0; e < V; ++e) acc = Num<T>::madd(v[s].e[e], bv[s].e[e], acc);
-      }
-    }
-    for (; k < kv; k += (uint64_t)G * KU) {
+    for (uint64_t k = g; k < kv; k += (uint64_t)G * KU) {
       Vec<T, V> v[KU], bv[KU];
 #pragma unroll
       for (int s = 0; s < KU; ++s) {
