@@ -299,6 +299,12 @@ def test_chooser_only_picks_instantiated_kernels():
                 assert inner == 1 and nq == 2 and size[dt] <= 8 and pl["vec"] == 16 // size[dt] and pl["ku"] in (4, 8) and pl["smem_bytes"] == 0 and pl["ksplit"] == 1
                 assert pl["ctas"] == max(1, -(-(outer * 2 * size[dt] // 16) // (256 * pl["ku"])))          # one tile per CTA
                 continue
+            if pl["kernel"] == 10 and size[dt] == 4 and inner == 2 and nq <= 32 and nq & (nq - 1) == 0:
+                # COLF, tiny slabs of two-element rows: consecutive lanes on consecutive vectors, transposing butterfly
+                G = nq // 2
+                assert (pl["tx"], pl["ty"], pl["to"], pl["nu"], pl["ku"]) == (1, G, 2, 32 // G, 8) and pl["smem_bytes"] == 0 and pl["ksplit"] == 1
+                assert pl["ctas"] == min(-(-(-(-outer // (8 * (32 // G)))) // 8), 148 * 8) and pl["workspace_bytes"] == 0
+                continue
             if pl["kernel"] == 10:      # COLF: narrow / odd rows as a flat stream of super-rows, a warp per slab (partition) or several short slabs per warp
                 vec = 16 // size[dt]
                 g = math.gcd(inner, vec)

@@ -975,6 +975,34 @@ def test_colf_kernel_rows_that_are_not_whole_vectors(dtype, oracle, monkeypatch)
         ttv_b200.plan(2, (3, 4001, 2), (1, 2, 3), dtype=name, kernel="colf")
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.int32])
+def test_colf_tiny_slabs_of_two_element_rows(dtype, oracle, monkeypatch):
+    """n_q = 2 .. 32 rows of two 4-byte elements: a slab is 1 .. 16 vectors, the lanes of a warp read consecutive vectors and the
+    partial sums of a slab meet in a transposing butterfly (ttv_colf_tiny_kernel).  Every slab size, slab counts below / at / above
+    one item of a warp (256 vectors) and one round of the grid, accumulate; the other kernels take the same shapes with
+    TTV_B200_COLF_TINY=0."""
+    rng = np.random.default_rng(41)
+    name = "f32" if np.dtype(dtype) == np.float32 else "i32"
+    for nq in (2, 4, 8, 16, 32):
+        per_item = 8 * (32 // (nq // 2))
+        for outer in (1, 3, per_item - 1, per_item, per_item + 1, 5 * per_item + 7, 40 * per_item + 3):
+            for na, pia in (((2, nq, outer), (1, 2, 3)), ((outer, nq, 2), (3, 2, 1))):
+                a, b = random_case(rng, na, 2, dtype)
+                want = oracle.ttv(2, a, na, pia, b)
+                pl = ttv_b200.plan(2, na, pia, dtype=name)
+                assert (pl["kernel"], pl["ty"], pl["nu"]) == (10, nq // 2, 32 // (nq // 2)), (na, pl)
+                assert np.array_equal(run_lowlevel(2, a, na, pia, b), want), (na, pia, dtype)
+                c0 = np.full(want.size, 3, dtype)
+                assert np.array_equal(run_lowlevel(2, a, na, pia, b, c0=c0, flags=1), want + 3), (na, pia, dtype)
+    na = (2, 16, 70001)                                             # several rounds of the persistent grid
+    a, b = random_case(rng, na, 2, dtype)
+    want = oracle.ttv(2, a, na, (1, 2, 3), b)
+    assert np.array_equal(run_lowlevel(2, a, na, (1, 2, 3), b), want)
+    monkeypatch.setenv("TTV_B200_COLF_TINY", "0")
+    assert ttv_b200.plan(2, na, (1, 2, 3), dtype=name)["ty"] != 8
+    assert np.array_equal(run_lowlevel(2, a, na, (1, 2, 3), b), want)
+
+
 @pytest.mark.parametrize("dtype", ALL_DTYPES)
 def test_streamk_kernel_tiny_inner_long_contraction(dtype, oracle, monkeypatch):
     """kernel="streamk": rows of a few elements under a long contraction, staged through shared memory by bulk copies with the

@@ -393,4 +393,104 @@ ttv_colfs_kernel(const ColfParams P)
   }
 }
 
+// TINY slabs of two-element rows: n_q = 2, 4, 8, 16, 32 rows of two 4-byte elements, i.e. a slab of G = n_q / 2 = 1 .. 16 vectors
+// (16 .. 256 bytes; n = (2, 8, 2^25): the leading extent 2 with a small second mode).  With a lane per slab (what the short-slab
+// form does from 128 bytes on) a load instruction touches 32 different lines and the L1 tag stage becomes the limit
+// ([16777216, 16, 2]: 4 729 GB/s; the column kernel 1 814).  Here the lanes of a warp read CONSECUTIVE vectors -- G lanes per
+// slab, 32 / G slabs per instruction, KU = 8 instructions = 4 KB in flight -- so a lane ends up with the partial sums of KU
+// different slabs, one vector each, and the G partials of a slab sit in G neighbouring lanes.  They are added by a TRANSPOSING
+// butterfly: at level m a lane sends the half of its values that its partner (lane ^ m) keeps and adds the half it receives
+// to the half it keeps -- 4 + 2 + 1 shuffles per component instead of 3 x 8 -- and after log2(G) levels every lane holds the
+// complete sums of 8 / G slabs, which it stores as 8 bytes each.  b (two elements per lane) lives in registers.
+struct ColfTinyParams {
+  const void* a;
+  const void* b;
+  void*       c;
+  uint64_t outer;           // slabs
+  uint32_t G;               // vectors (= lanes) per slab: 1, 2, 4, 8 or 16
+  uint32_t accumulate;
+};
+
+template<class T>
+__global__ void __launch_bounds__(256, 4)
+ttv_colf_tiny_kernel(const ColfTinyParams P)
+{
+  static_assert(sizeof(T) == 4, "rows of two 4-byte elements");
+  pdl_prologue();
+  constexpr int KU = 8;
+  using V4 = Vec<T, 4>;
+  using V2 = Vec<T, 2>;
+  const V4* __restrict__ A = static_cast<const V4*>(P.a);
+  const T* __restrict__  B = static_cast<const T*>(P.b);
+  T* __restrict__        C = static_cast<T*>(P.c);
+
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t G = P.G, t = lane % G, g = lane / G, spw = 32u / G;     // vector inside the slab, slab inside a step, slabs per step
+  const T b0 = B[2 * t], b1 = B[2 * t + 1];                              // the vector holds rows 2t and 2t + 1
+  // the step whose complete sum ends up in slot i of this lane: i + the halves kept on the way (bit k of t keeps the upper half at level k)
+  uint32_t sbase = 0;
+  if (G > 1) sbase += (t & 1u) ? 4u : 0u;
+  if (G > 2) sbase += (t & 2u) ? 2u : 0u;
+  if (G > 4) sbase += (t & 4u) ? 1u : 0u;
+  const uint32_t cnt = G >= 8 ? 1u : 8u / G;                             // complete sums per lane at the end
+  const bool stores = G < 16 || !(t & 8u);
+
+  const uint64_t per_item = (uint64_t)KU * spw;                          // slabs of one item (256 vectors, 4 KB)
+  const uint64_t items = (P.outer + per_item - 1) / per_item;
+  for (uint64_t item = (uint64_t)blockIdx.x * 8 + warp; item < items; item += (uint64_t)gridDim.x * 8) {
+    const uint64_t slab0 = item * per_item;
+    const V4* ap = A + item * (uint64_t)(KU * 32) + lane;
+    V4 x[KU];
+    if (slab0 + per_item <= P.outer) {
+#pragma unroll
+      for (int s = 0; s < KU; ++s) x[s] = load_a<T, 4>(reinterpret_cast<const T*>(ap + s * 32), true);
+    } else {
+#pragma unroll
+      for (int s = 0; s < KU; ++s) ld16_if<true>(&x[s], ap + s * 32, slab0 + (uint64_t)s * spw + g < P.outer);
+    }
+    T c0[KU], c1[KU];
+#pragma unroll
+    for (int s = 0; s < KU; ++s) {
+      c0[s] = Num<T>::madd(x[s].e[2], b1, Num<T>::madd(x[s].e[0], b0, Num<T>::zero()));
+      c1[s] = Num<T>::madd(x[s].e[3], b1, Num<T>::madd(x[s].e[1], b0, Num<T>::zero()));
+    }
+    // transposing butterfly over the G lanes of a slab: 8 -> 4 -> 2 -> 1 values per lane
+#pragma unroll
+    for (int level = 0; level < 3; ++level) {
+      const uint32_t m = 1u << level;
+      constexpr int kHalf[3] = {4, 2, 1};
+      const int half = kHalf[level];
+      if (G > m) {
+        const bool up = lane & m;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+          const T s0 = up ? c0[i] : c0[i + half], s1 = up ? c1[i] : c1[i + half];
+          const T r0 = shfl_xor_elem(s0, (int)m), r1 = shfl_xor_elem(s1, (int)m);
+          c0[i] = Num<T>::add(up ? c0[i + half] : c0[i], r0);
+          c1[i] = Num<T>::add(up ? c1[i + half] : c1[i], r1);
+        }
+      }
+    }
+    if (G == 16) {                                                       // the two halves of a 16-lane slab
+      c0[0] = Num<T>::add(c0[0], shfl_xor_elem(c0[0], 8));
+      c1[0] = Num<T>::add(c1[0], shfl_xor_elem(c1[0], 8));
+    }
+    if (stores) {
+#pragma unroll
+      for (int i = 0; i < KU; ++i) {
+        if ((uint32_t)i < cnt) {
+          const uint64_t slab = slab0 + (uint64_t)(sbase + i) * spw + g;
+          if (slab < P.outer) {
+            V2* out = reinterpret_cast<V2*>(C + slab * 2);
+            V2 val;
+            if (P.accumulate) { const V2 old = *out; val.e[0] = Num<T>::add(old.e[0], c0[i]); val.e[1] = Num<T>::add(old.e[1], c1[i]); }
+            else { val.e[0] = c0[i]; val.e[1] = c1[i]; }
+            *out = val;
+          }
+        }
+      }
+    }
+  }
+}
+
 } // namespace ttvb

@@ -35,6 +35,7 @@ using strided_fn_t = cudaError_t (*)(const StridedParams&, int, cudaStream_t);
 using streamk_fn_t = cudaError_t (*)(const StreamkParams&, const Launch&, cudaStream_t);
 using dotp_fn_t   = cudaError_t (*)(const DotpParams&, const Launch&, cudaStream_t);
 using colf_fn_t   = cudaError_t (*)(const ColfParams&, const Launch&, cudaStream_t);
+using colf_tiny_fn_t = cudaError_t (*)(const ColfTinyParams&, const Launch&, cudaStream_t);
 using colt_fn_t   = cudaError_t (*)(const CUtensorMap&, const ColtParams&, const Launch&, cudaStream_t);
 
 #define TTVB_DECLARE(k)                                                                                          \
@@ -49,7 +50,8 @@ using colt_fn_t   = cudaError_t (*)(const CUtensorMap&, const ColtParams&, const
   cudaError_t colt_dtype_##k(const CUtensorMap&, const ColtParams&, const Launch&, cudaStream_t);                \
   cudaError_t streamk_dtype_##k(const StreamkParams&, const Launch&, cudaStream_t);                             \
   cudaError_t dotp_dtype_##k(const DotpParams&, const Launch&, cudaStream_t);                                   \
-  cudaError_t colf_dtype_##k(const ColfParams&, const Launch&, cudaStream_t);
+  cudaError_t colf_dtype_##k(const ColfParams&, const Launch&, cudaStream_t);                                   \
+  cudaError_t colf_tiny_dtype_##k(const ColfTinyParams&, const Launch&, cudaStream_t);
 TTVB_DECLARE(0) TTVB_DECLARE(1) TTVB_DECLARE(2) TTVB_DECLARE(3) TTVB_DECLARE(4) TTVB_DECLARE(5)
 #undef TTVB_DECLARE
 
@@ -100,6 +102,7 @@ static const strided_fn_t k_strided[] = {strided_dtype_0, strided_dtype_1, strid
 static const streamk_fn_t k_streamk[] = {streamk_dtype_0, streamk_dtype_1, streamk_dtype_2, streamk_dtype_3, streamk_dtype_4, streamk_dtype_5};
 static const dotp_fn_t   k_dotp[]   = {dotp_dtype_0, dotp_dtype_1, dotp_dtype_2, dotp_dtype_3, dotp_dtype_4, dotp_dtype_5};
 static const colf_fn_t   k_colf[]   = {colf_dtype_0, colf_dtype_1, colf_dtype_2, colf_dtype_3, colf_dtype_4, colf_dtype_5};
+static const colf_tiny_fn_t k_colf_tiny[] = {colf_tiny_dtype_0, colf_tiny_dtype_1, colf_tiny_dtype_2, colf_tiny_dtype_3, colf_tiny_dtype_4, colf_tiny_dtype_5};
 static const colt_fn_t   k_colt[]   = {colt_dtype_0, colt_dtype_1, colt_dtype_2, colt_dtype_3, colt_dtype_4, colt_dtype_5};
 
 // cuTensorMapEncodeTiled lives in the driver library; the runtime hands out its address, so nothing links against libcuda
@@ -194,6 +197,11 @@ cudaError_t launch_view(int dtype, const View& v, const Launch& l, const void* a
     cudaError_t e = launch_colt(dtype, v, l, a, b, c, workspace, accumulate, stream);
     if (e != cudaSuccess || l.ksplit <= 1) return e;
     return k_reduce[dtype](workspace, c, v.outer * v.inner, l.ksplit, accumulate, v.outer * v.inner, sm_count, stream);
+  }
+  if (l.kernel == TTV_B200_KERNEL_COLF && l.tiny) {
+    ColfTinyParams Y;
+    Y.a = a; Y.b = b; Y.c = c; Y.outer = v.outer; Y.G = l.ty; Y.accumulate = accumulate ? 1u : 0u;
+    return k_colf_tiny[dtype](Y, l, stream);
   }
   if (l.kernel == TTV_B200_KERNEL_COLF) {
     ColfParams F;
@@ -626,6 +634,16 @@ cudaError_t TTVB_CAT(streamk_dtype_, TTVB_DTYPE)(const StreamkParams& K, const L
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem_bytes);
   if (e != cudaSuccess) return e;
   return launch_k(kern, (unsigned)l.ctas, 256u, l.smem_bytes, stream, K);
+}
+
+cudaError_t TTVB_CAT(colf_tiny_dtype_, TTVB_DTYPE)(const ColfTinyParams& Y, const Launch& l, cudaStream_t stream)
+{
+  if constexpr (sizeof(elem_t) == 4) {
+    return launch_k(ttv_colf_tiny_kernel<elem_t>, (unsigned)l.ctas, 256u, 0, stream, Y);
+  } else {
+    (void)Y; (void)l; (void)stream;
+    return cudaErrorInvalidValue;
+  }
 }
 
 cudaError_t TTVB_CAT(colf_dtype_, TTVB_DTYPE)(const ColfParams& F, const Launch& l, cudaStream_t stream)

@@ -496,6 +496,31 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
       return TTV_B200_OK;
     }
   }
+  // COLF, tiny slabs: n_q = 2 .. 32 rows of two 4-byte elements (a slab is 1 .. 16 vectors): consecutive lanes on consecutive
+  // vectors, transposing butterfly over the lanes of a slab (ttv_colf_tiny_kernel).  STREAM / COL / the lane-per-slab form of
+  // COLF took these before ([16777216, 16, 2]: COL 1 814, COLF 4 729 GB/s).
+  {
+    const bool eligible = s == 4 && v.inner == 2 && v.nq >= 2 && v.nq <= 32 && (v.nq & (v.nq - 1)) == 0 && (align_a % 16) == 0 && (align_c % 8) == 0 &&
+                          (!opts || opts->ksplit <= 1) && !(flags & TTV_B200_FLAG_NO_VEC);
+    const int mode = env_int("TTV_B200_COLF_TINY", -1);                                // -1 auto, 0 never, 1 whenever eligible
+    const bool pick = (forced == TTV_B200_KERNEL_COLF || forced == 0) && eligible && mode != 0 && env_int("TTV_B200_USE_COLF", -1) != 0;
+    if (pick) {
+      l.kernel = TTV_B200_KERNEL_COLF;
+      l.tiny = 1;
+      l.threads = 256;
+      const uint64_t G = v.nq / 2;
+      l.vec = 4; l.tx = 1; l.ty = (uint32_t)G; l.to = 2; l.nu = (int)(32 / G); l.ku = 8; l.stream = 1; l.udir = 0; l.ksplit = 1;
+      l.kchunk = v.nq; l.kb = 0;
+      l.itiles = 1; l.otiles = ceil_div(v.outer, 8 * (32 / G));
+      l.tiles = l.otiles;
+      l.ctas = std::min<uint64_t>(ceil_div(l.tiles, 8), sms * (uint64_t)std::max(1, env_int("TTV_B200_COLF_CTAS", 8)));
+      l.smem_bytes = 0;
+      l.workspace_bytes = 0;
+      *out = l;
+      return TTV_B200_OK;
+    }
+  }
+
   // STREAM: small slabs staged through shared memory by TMA bulk copies (stream_kernel.cuh).  Eligible when a slab and
   // b are small, A is 16-byte aligned and n_q is not split.
   {

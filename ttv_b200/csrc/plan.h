@@ -67,6 +67,7 @@ struct Launch {
   uint32_t warp = 0;        // COLX: warp-autonomous form (ttv_colw_kernel)
   uint32_t pair = 0;        // COLF: rows of two 4-byte elements, b and C 8-byte aligned (ttv_colf2_kernel)
   uint32_t short1 = 0;      // COLF: a slab is at most one batch of its lane group, unsplit (ttv_colfs_kernel)
+  uint32_t tiny = 0;        // COLF: slabs of 1 .. 16 vectors of two-element rows, transposing butterfly (ttv_colf_tiny_kernel)
   // STREAMK kernel only: rows per shared-memory stage (slabs_per_chunk), bytes of a stage of rows (stage_bytes) / of b
   uint32_t b_stage_bytes = 0;
   // COLT kernel only: box of the TMA tensor tile (wt 32-bit words of a row x kt rows), boxes per column tile
