@@ -14,7 +14,7 @@ from ttv_b200.measure import Arena, kernel_label, measure_config  # noqa: E402
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 aa, ac = Arena(int(13.2e9)), Arena(int(6.6e9))
 SWITCHES = ("TTV_B200_USE_STREAMK", "TTV_B200_STREAMK_STAGE_KB", "TTV_B200_USE_DOTP", "TTV_B200_DOTP_KU", "TTV_B200_DOTP_CTAS",
-            "TTV_B200_USE_COLF", "TTV_B200_COLF_ITEMS_PER_WARP", "TTV_B200_COLF_CTAS", "TTV_B200_COLF_MIN_SLAB_B", "TTV_B200_COLF_PAIR", "TTV_B200_KSPLIT", "TTV_B200_COLF_SHORT", "TTV_B200_COLF_TINY")
+            "TTV_B200_USE_COLF", "TTV_B200_COLF_ITEMS_PER_WARP", "TTV_B200_COLF_CTAS", "TTV_B200_COLF_MIN_SLAB_B", "TTV_B200_COLF_PAIR", "TTV_B200_KSPLIT", "TTV_B200_COLF_SHORT", "TTV_B200_COLF_TINY", "TTV_B200_COLF_TINY_CTAS")
 
 
 def run(dt, na, q, settings):
@@ -43,7 +43,7 @@ if which in ("all", "colf", "colfshort"):
                    ("f32", [2, 1 << 20, 128]), ("i32", [2, 1 << 24, 16]), ("f32", [15, 1 << 18, 64]), ("f32", [21, 1 << 16, 256]), ("f64", [21, 1 << 16, 128]),
                    ("f32", [3, 1 << 26]), ("f32", [85, 1 << 16, 64]), ("f64", [63, 1 << 16, 64])]:
         run(dt, na, 2, S)
-    T = [OFF, {"TTV_B200_COLF_SHORT": "0"}, {}]
+    T = [OFF, {}, {"TTV_B200_COLF_CTAS": "16"}, {"TTV_B200_COLF_CTAS": "32"}]
     for dt, na in [("f32", [3, 8192, 1 << 14]), ("f32", [5, 4096, 1 << 15]), ("f32", [3, 1024, 1 << 17]), ("f32", [3, 256, 1 << 18]), ("f32", [5, 64, 1 << 20]),
                    ("f32", [2, 512, 1 << 19]), ("f64", [3, 2048, 1 << 15]), ("f32", [2, 128, 1 << 21]), ("f32", [6, 64, 1 << 20]), ("i32", [2, 16, 1 << 24]),
                    ("f32", [3, 32, 1 << 22]), ("c64", [3, 128, 1 << 19]), ("f64", [3, 16, 1 << 22]), ("f32", [6, 1024, 1 << 16]), ("f32", [2, 128, 2, 2, 1 << 21])]:
@@ -60,7 +60,7 @@ if which in ("all", "pair"):      # rows of two 4-byte elements: the general COL
         run(dt, na, 2, P2)
 
 if which in ("all", "tiny"):      # slabs of 1 .. 16 vectors of two-element rows: what took them before against ttv_colf_tiny_kernel
-    Y = [{"TTV_B200_COLF_TINY": "0"}, {}]
+    Y = [{"TTV_B200_COLF_TINY": "0"}, {}, {"TTV_B200_COLF_TINY_CTAS": "8"}, {"TTV_B200_COLF_TINY_CTAS": "32"}]
     for dt, na in [("f32", [2, 2, 1 << 27]), ("f32", [2, 4, 1 << 26]), ("f32", [2, 8, 1 << 25]), ("f32", [2, 16, 1 << 24]), ("f32", [2, 32, 1 << 23]),
                    ("i32", [2, 2, 1 << 27]), ("i32", [2, 16, 1 << 24]), ("f32", [2, 2, 4, 2, 1 << 15, 2, 3, 2, 2, 128])]:
         run(dt, na, 2, Y)

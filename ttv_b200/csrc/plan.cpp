@@ -513,7 +513,9 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
       l.kchunk = v.nq; l.kb = 0;
       l.itiles = 1; l.otiles = ceil_div(v.outer, 8 * (32 / G));
       l.tiles = l.otiles;
-      l.ctas = std::min<uint64_t>(ceil_div(l.tiles, 8), sms * (uint64_t)std::max(1, env_int("TTV_B200_COLF_CTAS", 8)));
+      // a CTA per eight items, no striding (a lane's set-up is two elements of b): 8 CTAs per SM striding over the items measured
+      // 6 297-6 630 GB/s, 32 per SM 6 608-6 873, a CTA per eight items 7 002-7 081 (profiles/r02_colf_dotp_ab.txt, section 16)
+      l.ctas = std::min<uint64_t>(ceil_div(l.tiles, 8), std::min<uint64_t>(0x7fffffffull, sms * (uint64_t)std::max(1, env_int("TTV_B200_COLF_TINY_CTAS", 1 << 20))));
       l.smem_bytes = 0;
       l.workspace_bytes = 0;
       *out = l;
