@@ -14,7 +14,7 @@ from ttv_b200.measure import Arena, kernel_label, measure_config  # noqa: E402
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 aa, ac = Arena(int(13.2e9)), Arena(int(6.6e9))
 SWITCHES = ("TTV_B200_USE_STREAMK", "TTV_B200_STREAMK_STAGE_KB", "TTV_B200_USE_DOTP", "TTV_B200_DOTP_KU", "TTV_B200_DOTP_CTAS",
-            "TTV_B200_USE_COLF", "TTV_B200_COLF_ITEMS_PER_WARP", "TTV_B200_COLF_CTAS", "TTV_B200_COLF_MIN_SLAB_B", "TTV_B200_COLF_PAIR", "TTV_B200_KSPLIT", "TTV_B200_COLF_SHORT", "TTV_B200_COLF_TINY", "TTV_B200_COLF_TINY_CTAS")
+            "TTV_B200_USE_COLF", "TTV_B200_COLF_ITEMS_PER_WARP", "TTV_B200_COLF_CTAS", "TTV_B200_COLF_MIN_SLAB_B", "TTV_B200_COLF_PAIR", "TTV_B200_KSPLIT", "TTV_B200_COLF_SHORT", "TTV_B200_COLF_TINY", "TTV_B200_COLF_TINY_CTAS", "TTV_B200_COLF_PAIR_CTAS")
 
 
 def run(dt, na, q, settings):
@@ -50,7 +50,7 @@ if which in ("all", "colf", "colfshort"):
         run(dt, na, 2, T)                                        # short slabs: one CTA item is a few batches at most
 
 if which in ("all", "pair"):      # rows of two 4-byte elements: the general COLF kernel against ttv_colf2_kernel
-    P2 = [{"TTV_B200_COLF_PAIR": "0", "TTV_B200_COLF_SHORT": "0"}, {"TTV_B200_COLF_SHORT": "0"}, {}]
+    P2 = [{"TTV_B200_COLF_SHORT": "0"}, {"TTV_B200_COLF_PAIR_CTAS": "6"}, {}, {"TTV_B200_COLF_PAIR_CTAS": "64"}, {"TTV_B200_COLF_PAIR_CTAS": "1000000"}]
     run("f32", [2, 1 << 17, 2, 4, 2, 2, 64], 2, P2)              # the named asym7 q=2
     run("f32", [2, 1 << 20, 512], 2, P2)                         # the named asym3n q=2
     run("f32", [2, 128, 2, 2, 1 << 21], 2, P2)                   # the named asym5n q=2

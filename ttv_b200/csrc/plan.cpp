@@ -658,9 +658,13 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
       const uint64_t srchunk = ceil_div(std::max<uint64_t>(1, ceil_div(nsr, ksplit)), batch) * batch;
       l.ksplit = (uint32_t)ksplit; l.kchunk = srchunk * R;
       l.short1 = (ksplit == 1 && nsr <= batch && env_int("TTV_B200_COLF_SHORT", 1) != 0) ? 1 : 0;
+      // the short-slab form of two-element rows sets a lane up with eight pairs of b only: more, shorter-lived CTAs measured
+      // faster (6 per SM 6 691-6 768, 16 per SM 6 869-6 915, 32 per SM 7 026-7 079 GB/s); the general short form loses with them
+      uint64_t grid_cap = max_ctas;
+      if (l.short1 && l.pair) grid_cap = sms * (uint64_t)std::max(1, env_int("TTV_B200_COLF_PAIR_CTAS", 32));
       l.itiles = 1; l.otiles = ogroups;
       l.tiles = ogroups * ksplit;
-      l.ctas = std::min<uint64_t>(ceil_div(l.tiles, 8), max_ctas);
+      l.ctas = std::min<uint64_t>(ceil_div(l.tiles, 8), grid_cap);
       l.kb = 0;
       l.smem_bytes = 8 * 32 * 16;                                    // static: a strip of 32 vectors per warp
       l.workspace_bytes = ksplit > 1 ? ksplit * v.outer * v.inner * s : 0;
