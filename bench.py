@@ -18,7 +18,7 @@ with HOST (pinned) buffers, host<->device copies inside the timed region.
 
 Beside the contract's keys the line carries (none of them inside the timed region of `value`):
   configs   N = 1: EVERY named BASELINE config (ttv_b200/workloads.py "named": cfg1, the symmetric fp32/fp64 sweep, the
-            asymmetric fp32/int32 sweep, the complex family with last-order / random layouts, the cfg5 slab: 252 products)
+            asymmetric fp32/int32 sweep, the complex family with last-order / random layouts, the cfg5 slab: 254 products)
             timed device-resident AND checked on sampled fibers against a host long-double dot (bit-exact for int32):
             n, min / median GB/s, everything below 0.8 x 8 TB/s, parity failures, the whole table
   cfg5      BASELINE configs[4]: 2048^3 fp64 STRONG scaling over the N ranks, q = 1 (free split) and q = 3 (n_q split +

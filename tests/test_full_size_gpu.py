@@ -2,7 +2,7 @@
 big-slab STREAM form, n_q split + direct b, 128-thread CTAs, the (1,16) deep batch, COLX / COLW, DOTF on 16-byte elements,
 the peeled DOT, fibers cut into pieces, ...).  Small shapes reach those kernel FAMILIES when forced, but not these exact
 plans; here every one of them runs on its BASELINE-sized tensor and sampled outputs are compared with a host long-double dot
-on regenerated fibers (ttv_b200/selfcheck.py; int32 bit-exact).  bench.py's sweep leg does the same for all 252 named
+on regenerated fibers (ttv_b200/selfcheck.py; int32 bit-exact).  bench.py's sweep leg does the same for all 254 named
 products; this is the subset that pins one product per chooser branch in the test suite.
 
 The reference's own grid only reaches extents {2,4,8}^p (test/src/gtest_tlib_ttv.cpp:192-425)."""
@@ -42,6 +42,8 @@ BRANCHES = [
     ("asym5n", "f32", 2, dict(kernel=10, ksplit=1)),                     # 8 388 608 slabs of 128 x 2 floats: COLF, four slabs per warp
     ("asym5n", "i32", 2, dict(kernel=10, ksplit=1)),
     ("asym3n", "f32", 1, dict(kernel=9)),                                # DOTP: fibers of two floats
+    ("asym10", "f32", 2, dict(kernel=10, ty=1, nu=32)),                  # 805 306 368 slabs of 2 x 2 floats: COLF, tiny slabs (a vector per slab)
+    ("asym10", "i32", 2, dict(kernel=10, ty=1, nu=32)),
     ("asym10", "i32", 1, dict(kernel=9)),                                # n_q = 2: a third of the traffic is writes
     ("asym10", "f32", 10, None),
     ("asym8", "f32", 2, None),

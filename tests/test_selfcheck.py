@@ -51,12 +51,12 @@ def test_full_product_matches_the_oracle_for_every_layout(oracle):
                     assert np.array_equal(sc.full_product(a, na, pia, q, b), oracle.ttv(q, a, na, pia, b)), (na, pia, q)
 
 
-def test_named_workloads_are_the_252_products_of_baseline_json():
+def test_named_workloads_are_the_254_products_of_baseline_json():
     named = workloads.configs("named")
-    assert len(named) == 252 and len(workloads.configs("all")) == 120 and len(workloads.configs("cplxall")) == 90 and len(workloads.configs("asym2")) == 42
+    assert len(named) == 254 and len(workloads.configs("all")) == 122 and len(workloads.configs("cplxall")) == 90 and len(workloads.configs("asym2")) == 42
     assert {len(c[2]) for c in named if c[0].startswith("asym")} == set(range(2, 11))      # BASELINE configs[2]: every order p = 2..10
     assert ("cfg1", "f32", [512, 512, 512], [1, 2, 3], 2) in named                      # BASELINE configs[0]
-    assert sum(1 for c in named if c[1] == "i32") == 44 and {c[1] for c in named} == {"f32", "f64", "c64", "c128", "i32"}
+    assert sum(1 for c in named if c[1] == "i32") == 45 and {c[1] for c in named} == {"f32", "f64", "c64", "c128", "i32"}
     for name, dt, na, pia, q, *rest in named:
         assert sorted(pia) == list(range(1, len(na) + 1)) and 1 <= q <= len(na)
         assert workloads.algo_bytes(dt, na, q) == workloads.SIZE[dt] * (int(np.prod(na, dtype=object)) * (na[q - 1] + 1) // na[q - 1] + na[q - 1])

@@ -74,7 +74,7 @@ def configs(which: str):
             out += [("asym4", dt, [16, 1024, 4, 1 << 14], first(4), q) for q in (1, 2, 3, 4)]
             out += [("asym6", dt, [2, 3, 1 << 20, 2, 4, 16], first(6), q) for q in (1, 2, 3, 4, 6)]
             out += [("asym8", dt, [4, 1 << 16, 2, 2, 3, 2, 2, 64], first(8), q) for q in (1, 2, 5, 8)]
-            out += [("asym10", dt, [2, 2, 4, 2, 1 << 15, 2, 3, 2, 2, 128], first(10), q) for q in (1, 3, 5, 7, 10)]
+            out += [("asym10", dt, [2, 2, 4, 2, 1 << 15, 2, 3, 2, 2, 128], first(10), q) for q in (1, 2, 3, 5, 7, 10)]
     if which in ("asym2", "named"):      # the remaining orders of BASELINE configs[2] (p = 2..10): 2, 3, 7, 9 (round 2)
         for dt in ("f32", "i32"):
             out += [("asym2", dt, [4, 1 << 26], first(2), q) for q in (1, 2)]
