@@ -152,6 +152,8 @@ typedef struct ttv_b200_plan_t {
   int32_t  vec;         /* elements per vector load                                                          */
   int32_t  tx, ty, to;  /* thread tile: threads along inner / along n_q / along outer inside one CTA         */
   int32_t  nu, ku;      /* loads in flight per thread: ku k-steps for each of nu independent outputs          */
+                        /* (COLF: tx = vectors per super-row, ty = super-rows per step of a slab's lane group, */
+                        /*  to = rows per super-row, nu = slabs a warp works on side by side)                  */
   int32_t  ksplit;      /* n_q partitions (second pass reduces them when > 1)                                */
   int32_t  threads;     /* threads per CTA                                                                   */
   int32_t  stream;      /* 1: A is loaded with L1::no_allocate                                               */
