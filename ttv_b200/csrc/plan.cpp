@@ -743,7 +743,10 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
       l.slabs_per_chunk = 256 / nvf;                                  // whole fibers per chunk of 256 vectors
       l.chunks = ceil_div(v.outer, l.slabs_per_chunk);
       l.tiles = l.chunks;
-      l.ctas = std::min<uint64_t>(ceil_div(l.chunks, 8), sms * 24);
+      // CTAs per SM the grid is capped at (session 33, profiles/r02_dotf_grid_ab.txt): 64 instead of 24 gains 1-2 % for 4- and 8-byte
+      // elements (84 floats 6 921 -> 7 070, 48 complex<float> 6 732 -> 6 867, 16 floats 6 836 -> 6 989), loses up to 3 % for 16-byte
+      // ones (40 complex<double> 6 438 -> 6 242); a CTA per eight chunks loses 8-40 % everywhere
+      l.ctas = std::min<uint64_t>(ceil_div(l.chunks, 8), std::min<uint64_t>(0x7fffffffull, sms * (uint64_t)std::max(1, env_int("TTV_B200_DOTF_CTAS", s >= 16 ? 24 : 64))));
       l.kchunk = v.nq; l.kb = (uint32_t)v.nq;
       l.smem_bytes = v.nq * s + 8 * 256 * s;
       l.workspace_bytes = 0;
