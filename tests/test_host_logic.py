@@ -320,7 +320,7 @@ def test_chooser_only_picks_instantiated_kernels():
                 assert pl["workspace_bytes"] == (pl["ksplit"] > 1) * pl["ksplit"] * outer * inner * size[dt]
                 continue
             if pl["kernel"] == 8:       # STREAMK: rows of a few elements under a long contraction, staged through shared memory
-                assert 1 < inner <= 16 and inner * size[dt] <= 64 and inner % (16 // size[dt]) != 0 and nq >= 4096
+                assert 1 < inner <= 16 and size[dt] == 4 and inner % 2 == 1 and nq >= 4096              # odd rows of 4-byte elements
                 assert outer > 1 and nq % ((16 // size[dt]) // math.gcd(inner, 16 // size[dt])) != 0      # what COLF cannot take
                 assert pl["smem_bytes"] <= 113 * 1024 and pl["ctas"] <= 148 * 2 and pl["ksplit"] >= 1 and pl["threads"] == 256
                 continue

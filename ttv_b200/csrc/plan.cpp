@@ -687,7 +687,10 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
                     : forced != 0 ? false
                     : mode == 1 ? eligible
                     : mode == 0 ? false
-                    : (eligible && misaligned && v.outer * v.nq * v.inner * s >= (64ull << 20));
+                    // odd rows of 4-byte elements only: there the column kernel is down to 4-byte loads (rows of 3 / 5 floats off the
+                    // 16-byte grid: 4 274 / 4 336 -> 5 810 / 5 963 GB/s); even rows and 8-byte elements it loads 8 bytes at a time and
+                    // is ahead or level (rows of 2 floats 6 191 against 5 600, 3 doubles 5 694 / 5 811) -- tools/probe/streamk_niche.py
+                    : (eligible && misaligned && s == 4 && (v.inner & 1) && v.outer * v.nq * v.inner * s >= (64ull << 20));
     if (pick) {
       l.kernel = TTV_B200_KERNEL_STREAMK;
       l.threads = 256;
