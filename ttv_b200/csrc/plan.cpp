@@ -647,12 +647,12 @@ int choose_launch(int dtype, const View& v, const ttv_b200_opts* opts, uint64_t 
         const uint64_t hi = std::max<uint64_t>(1, std::min(std::min(ceil_div(vslots * (uint64_t)env_int("TTV_B200_COLF_ITEMS_PER_WARP", 4), ogroups), sms * 24),
                                                            std::max<uint64_t>(1, nsr / (batch * 4))));
         double best = -1.0;
-        for (uint64_t ks = hi; ks >= std::max<uint64_t>(1, hi / 2); --ks) {
+        const uint64_t lo = std::max<uint64_t>(1, hi / 2), step = std::max<uint64_t>(1, (hi - lo) / 64);   // at most ~64 candidates: this runs per call
+        for (uint64_t ks = hi; ks >= lo; ks -= std::min(step, ks - lo ? ks - lo : step)) {
           const uint64_t k2 = parts(ks);
           const double x = (double)(ogroups * k2) / (double)vslots, eff = x / (double)ceil_div(ogroups * k2, vslots);
           if (eff > best + 1e-9) { best = eff; ksplit = k2; }
-          if (ks == 1) break;
-          (void)x;
+          if (ks == lo) break;
         }
       }
       const uint64_t srchunk = ceil_div(std::max<uint64_t>(1, ceil_div(nsr, ksplit)), batch) * batch;
