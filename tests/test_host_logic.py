@@ -201,6 +201,31 @@ def test_chooser_named_configs():
     # many short aligned fibers: one flat stream (DOTF); long ones keep a lane group per fiber (DOT)
     assert ttv_b200.plan(1, [40] * 6, [1, 2, 3, 4, 5, 6], dtype="f32")["kernel"] == 5
     assert ttv_b200.plan(1, [256] * 4, [1, 2, 3, 4], dtype="f32")["kernel"] == 1
+    # tiny extents of the asymmetric family ("Tiny extents"): fibers of two elements -> DOTP, a CTA per tile
+    pl = ttv_b200.plan(1, [2, 2, 4, 2, 1 << 15, 2, 3, 2, 2, 128], list(range(1, 11)), dtype="i32")
+    assert (pl["kernel"], pl["vec"], pl["ku"], pl["ctas"]) == (9, 4, 8, 1610612736 // 2 // 2048)
+    assert ttv_b200.plan(1, [2, 1 << 20], [1, 2], dtype="f64")["kernel"] == 9 and ttv_b200.plan(1, [2, 1 << 20], [1, 2], dtype="c128")["kernel"] != 9
+    # rows that are not whole vectors -> COLF: long slabs cut over warps, super-rows of two rows (rows of 6) / four rows (rows of 3)
+    pl = ttv_b200.plan(3, [2, 3, 1 << 20, 2, 4, 16], [1, 2, 3, 4, 5, 6], dtype="f32")
+    assert (pl["kernel"], pl["tx"], pl["ty"], pl["to"], pl["nu"]) == (10, 3, 10, 2, 1) and 50 <= pl["ksplit"] <= 3552 and pl["ctas"] == 148 * 6
+    pl = ttv_b200.plan(2, [3, 1 << 20, 64], [1, 2, 3], dtype="f32")
+    assert (pl["kernel"], pl["tx"], pl["ty"], pl["to"]) == (10, 3, 10, 4) and pl["workspace_bytes"] == pl["ksplit"] * 64 * 3 * 4
+    assert ttv_b200.plan(2, [3, 1 << 26], [1, 2], dtype="f32")["ksplit"] <= 148 * 24                    # one slab: at most 24 partitions per SM
+    # short slabs side by side in a warp (8 388 608 slabs of 128 x 2: eight lanes per slab, four slabs per warp, 32 CTAs per SM)
+    pl = ttv_b200.plan(2, [2, 128, 2, 2, 1 << 21], [1, 2, 3, 4, 5], dtype="f32")
+    assert (pl["kernel"], pl["tx"], pl["ty"], pl["to"], pl["nu"], pl["ksplit"], pl["ctas"]) == (10, 1, 8, 2, 4, 1, 148 * 32)
+    pl = ttv_b200.plan(2, [5, 64, 1 << 20], [1, 2, 3], dtype="f32")
+    assert (pl["kernel"], pl["tx"], pl["ty"], pl["to"], pl["nu"], pl["ksplit"], pl["ctas"]) == (10, 5, 2, 4, 3, 1, 148 * 6)
+    # tiny slabs of two-element rows: consecutive lanes on consecutive vectors, a CTA per eight items
+    pl = ttv_b200.plan(2, [2, 2, 4, 2, 1 << 15, 2, 3, 2, 2, 128], list(range(1, 11)), dtype="f32")
+    assert (pl["kernel"], pl["ty"], pl["nu"], pl["smem_bytes"], pl["ctas"]) == (10, 1, 32, 0, 805306368 // 256 // 8)
+    assert ttv_b200.plan(2, [2, 16, 1 << 20], [1, 2, 3], dtype="i32")["ty"] == 8 and ttv_b200.plan(2, [2, 16, 1 << 20], [1, 2, 3], dtype="f64")["kernel"] == 2
+    # 8-byte elements: COLF for rows of up to 8 vectors only; rows of whole vectors never
+    assert ttv_b200.plan(2, [3, 1 << 19, 64], [1, 2, 3], dtype="f64")["kernel"] == 10 and ttv_b200.plan(2, [21, 1 << 16, 128], [1, 2, 3], dtype="f64")["kernel"] == 2
+    assert ttv_b200.plan(2, [4, 1 << 20, 64], [1, 2, 3], dtype="f32")["kernel"] == 2
+    # several slabs of odd 4-byte rows off the 16-byte grid: the one place STREAMK is taken by rule
+    assert ttv_b200.plan(2, [3, (1 << 20) + 1, 64], [1, 2, 3], dtype="f32")["kernel"] == 8
+    assert ttv_b200.plan(2, [2, (1 << 20) + 1, 128], [1, 2, 3], dtype="f32")["kernel"] == 2 and ttv_b200.plan(2, [3, (1 << 19) + 1, 64], [1, 2, 3], dtype="f64")["kernel"] == 2
     # a single huge fiber: split n_q across CTAs
     pl = ttv_b200.plan(1, [1 << 26, 2], [1, 2], dtype="f32")
     assert pl["kernel"] == 1 and pl["ksplit"] > 64 and pl["workspace_bytes"] == pl["ksplit"] * 2 * 4
